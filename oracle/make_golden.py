@@ -1,0 +1,208 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (where /root/reference is mounted):
+
+    python -m oracle.make_golden
+
+For every case it (1) runs the reference's own functions (src.ellipsoid_utils.clustering,
+src.ellipsoid_fitting.weighted_ellipsoid_fitting_batch, convex_loss.compute_sdf_ellipsoids_batch
++ the SDF-half reduction of src/utils.py:407-425, autograd backward) in fp32 and in fp64,
+(2) runs oracle/restatement.py on the same inputs with the same RNG seeds and prints the
+difference, and (3) stores inputs + the reference's outputs.  The fixtures are what pins the
+oracle on machines that do not have the reference tree (the GPU box).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader, restatement as R  # noqa: E402
+from prifit_b200 import synthetic  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _seed(s):
+    torch.manual_seed(s)
+    np.random.seed(s)
+
+
+def ref_fit_loss(ns, E, P, quantile, iterations, max_num_clusters, seed):
+    """The reference's stage functions wired as convex_loss wires them (convex_loss.py:37-70,
+    src/utils.py:407-425, SDF half only), backward to the un-normalised embeddings."""
+    _seed(seed)
+    E = E.detach().clone().requires_grad_(True)
+    X = torch.nn.functional.normalize(E, dim=2, p=2)
+    X = torch.nn.functional.normalize(X, dim=2, p=2)
+    weights, labels = ns.ellipsoid_utils.clustering(
+        X, quantile=quantile, iterations=iterations, max_num_clusters=max_num_clusters, num_samples=X.shape[1])
+    n_attempt = [w.shape[1] for w in weights]
+    params = ns.ellipsoid_fitting.weighted_ellipsoid_fitting_batch(P, weights)
+    sdfs = ns.convex_loss.compute_sdf_ellipsoids_batch(P, params)
+    per_shape = []
+    for b in range(P.shape[0]):
+        if len(params[b]) == 0:
+            continue
+        s = torch.abs(torch.stack(sdfs[b], 1))
+        per_shape.append(torch.mean(torch.min(s, 1)[0] ** 2) / 2.0)
+    loss = torch.stack(per_shape).mean()
+    loss.backward()
+    return {"loss": loss.detach(), "grad_E": E.grad.detach(), "params": params, "labels": labels,
+            "weights": weights, "n_attempt": n_attempt}
+
+
+def drawn_noise(seed, n_attempt, kcap):
+    """Replays the torch.rand(3,3) draws of src/ellipsoid_fitting.py:38 (b-major, k-minor)."""
+    torch.manual_seed(seed)
+    out = torch.zeros(len(n_attempt), kcap, 3, 3)
+    for b, k in enumerate(n_attempt):
+        for i in range(k):
+            out[b, i] = torch.rand(3, 3)
+    return out
+
+
+def pack_params(params, kcap, dtype):
+    B = len(params)
+    s = np.zeros((B, kcap, 3), dtype)
+    V = np.zeros((B, kcap, 3, 3), dtype)
+    c = np.zeros((B, kcap, 3), dtype)
+    n = np.zeros((B,), np.int32)
+    for b, ps in enumerate(params):
+        n[b] = len(ps)
+        for k, (r, v, cc) in enumerate(ps):
+            s[b, k] = r.detach().numpy()
+            V[b, k] = v.detach().numpy()
+            c[b, k] = cc.detach().numpy()
+    return s, V, c, n
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def pipeline_case(ns, name, E, P, quantile, iterations, max_num_clusters, seed=7, kcap=32):
+    out = {}
+    ref32 = ref_fit_loss(ns, E, P, quantile, iterations, max_num_clusters, seed)
+    ref64 = ref_fit_loss(ns, E.double(), P.double(), quantile, iterations, max_num_clusters, seed)
+    noise = drawn_noise(seed, ref32["n_attempt"], kcap)
+    # restatement, same global RNG streams
+    _seed(seed)
+    info32 = []
+    o32 = R.fit_loss(E, P, quantile, iterations, max_num_clusters, info=info32)
+    _seed(seed)
+    info64 = []
+    o64 = R.fit_loss(E.double(), P.double(), quantile, iterations, max_num_clusters, info=info64)
+    print("[%s] K=%s passes=%s  bw=%s" % (name, ref32["n_attempt"], [i["passes"] for i in info32],
+                                           ["%.6f" % i["bw"] for i in info32]))
+    print("   loss ref32 %.9g ref64 %.9g | oracle32-ref32 rel %.2e, oracle64-ref64 rel %.2e" % (
+        float(ref32["loss"]), float(ref64["loss"]), rel(o32["loss"], ref32["loss"]), rel(o64["loss"], ref64["loss"])))
+    print("   grad: |ref32-ref64| rel %.2e | oracle32-ref32 rel %.2e | oracle64-ref64 rel %.2e" % (
+        rel(ref32["grad_E"], ref64["grad_E"]), rel(o32["grad_E"], ref32["grad_E"]), rel(o64["grad_E"], ref64["grad_E"])))
+    for b in range(E.shape[0]):
+        assert torch.equal(o32["labels"][b], ref32["labels"][b]), "oracle labels differ from reference (fp32)"
+    s32, V32, c32, n32 = pack_params(ref32["params"], kcap, np.float32)
+    s64, V64, c64, n64 = pack_params(ref64["params"], kcap, np.float64)
+    W32 = np.zeros((E.shape[0], kcap, E.shape[1]), np.float32)
+    for b, w in enumerate(ref32["weights"]):
+        W32[b, :w.shape[1]] = w.detach().numpy().T
+    out.update(
+        E=E.numpy(), P=P.numpy(), quantile=np.float64(quantile), iterations=np.int32(iterations),
+        max_num_clusters=np.int32(max_num_clusters), noise=noise.numpy(),
+        n_attempt=np.asarray(ref32["n_attempt"], np.int32),
+        bw32=np.asarray([i["bw"] for i in info32], np.float64),
+        bw64=np.asarray([i["bw"] for i in info64], np.float64),
+        passes=np.asarray([i["passes"] for i in info32], np.int32),
+        labels32=np.stack([l.numpy() for l in ref32["labels"]]).astype(np.int32),
+        labels64=np.stack([l.numpy() for l in ref64["labels"]]).astype(np.int32),
+        W32=W32, s32=s32, V32=V32, c32=c32, nfit32=n32, s64=s64, V64=V64, c64=c64, nfit64=n64,
+        loss32=np.float64(ref32["loss"]), loss64=np.float64(ref64["loss"]),
+        grad32=ref32["grad_E"].numpy(), grad64=ref64["grad_E"].numpy().astype(np.float64),
+    )
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
+def fit_kat_case(ns):
+    """fitting.py recipe (src/ellipsoid_fitting.py:144-193): one-hot memberships on sampled ellipsoid
+    surfaces; planted semi-axes must come back sorted by variance; empty columns are dropped."""
+    axes = [(5.0, 2.0, 1.0), (11.0, 7.0, 3.0), (19.0, 9.0, 4.0)]
+    n_each, kcols = 400, 6
+    pts = torch.cat([synthetic.ellipsoid_surface(a, n_each, seed=i) + torch.tensor([30.0 * i, 0, 0])
+                     for i, a in enumerate(axes)])
+    W = torch.zeros(pts.shape[0], kcols)
+    for i in range(3):
+        W[i * n_each:(i + 1) * n_each, 2 * i] = 1.0        # columns 1,3,5 stay empty -> dropped
+    _seed(11)
+    params = ns.ellipsoid_fitting.weighted_ellipsoid_fitting_batch(pts[None], [W])
+    noise = drawn_noise(11, [kcols], kcols)
+    s, V, c, n = pack_params(params, kcols, np.float32)
+    print("[fit_kat] fitted %d of %d columns; axes:" % (n[0], kcols), s[0, :n[0]])
+    assert n[0] == 3
+    _seed(11)
+    op = R.weighted_ellipsoid_fitting_batch(pts[None], [W])
+    so, Vo, co, no = pack_params(op, kcols, np.float32)
+    print("   oracle-ref: s %.2e c %.2e" % (rel(so, s), rel(co, c)))
+    np.savez_compressed(os.path.join(OUT, "fit_kat.npz"), P=pts.numpy()[None], W=W.numpy().T[None].copy(),
+                        noise=noise.numpy(), s=s, V=V, c=c, nfit=n, planted=np.asarray(axes, np.float32))
+
+
+def svd_backward_case(ns):
+    """CustomSVD backward (src/fitting_utils.py:67-136) on random symmetric-ish 3x3 inputs, including
+    one with two nearly equal singular values (the epsilon-clamped 1/(s_i - s_j) branch)."""
+    torch.manual_seed(3)
+    As, gSs, gVs, outs, Us, Ss, Vs = [], [], [], [], [], [], []
+    for i in range(6):
+        M = torch.randn(3, 3)
+        A = M @ M.T / 3 + 1e-3 * torch.rand(3, 3)
+        if i == 5:
+            A = torch.diag(torch.tensor([2.0, 1.0, 1.0 + 2e-7])) + 1e-9 * torch.rand(3, 3)
+        A = A.clone().requires_grad_(True)
+        U, S, V = ns.fitting_utils.customsvd(A)
+        gS, gV = torch.randn(3), torch.randn(3, 3)
+        (S * gS).sum().add((V * gV).sum()).backward()
+        As.append(A.detach().numpy()); gSs.append(gS.numpy()); gVs.append(gV.numpy())
+        outs.append(A.grad.numpy()); Us.append(U.detach().numpy()); Ss.append(S.detach().numpy()); Vs.append(V.detach().numpy())
+    np.savez_compressed(os.path.join(OUT, "svd_backward.npz"), A=np.stack(As), gS=np.stack(gSs), gV=np.stack(gVs),
+                        gA=np.stack(outs), U=np.stack(Us), S=np.stack(Ss), V=np.stack(Vs))
+    print("[svd_backward] 6 matrices stored")
+
+
+def stage_case(ns):
+    """Stage-level vectors on one small shape: bandwidth, T iterations, NMS, membership."""
+    E, P, _ = synthetic.planted_shapes(1, n_points=320, n_clusters=3, sigma=0.05, seed=21)
+    X = R.normalize_twice(E)[0]
+    ms = ns.mean_shift.MeanShift()
+    np.random.seed(5)
+    bw = ms.compute_bandwidth(X, 320, 0.05)
+    newX, _ = ms.mean_shift_(X, bw, iterations=6)
+    centres, ids, labels = ms.nms(newX, newX, bw)
+    mem = ms.membership(centres, X, bw)
+    np.random.seed(5)
+    bw_sub = ms.compute_bandwidth(X, 200, 0.1)
+    perm = np.arange(320); np.random.seed(5); np.random.shuffle(perm)
+    print("[stages] bw %.7f bw_sub %.7f K %d" % (float(bw), float(bw_sub), ids.shape[0]))
+    np.savez_compressed(os.path.join(OUT, "stages.npz"), X=X.numpy(), bw=np.float64(bw), newX=newX.numpy(),
+                        ids=ids.numpy().astype(np.int32), labels=labels.numpy().astype(np.int32),
+                        membership=mem.numpy(), bw_sub=np.float64(bw_sub), perm=perm.astype(np.int32))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_loader.load()
+    stage_case(ns)
+    svd_backward_case(ns)
+    fit_kat_case(ns)
+    E, P, _ = synthetic.planted_shapes(2, n_points=512, n_clusters=4, sigma=0.02, seed=100)
+    pipeline_case(ns, "planted_small", E, P, 0.05, 10, 25)
+    E, P, _ = synthetic.planted_shapes(1, n_points=768, n_clusters=12, sigma=0.02, seed=200)
+    pipeline_case(ns, "guard_small", E, P, 0.01, 10, 8)
+    E, P = synthetic.random_shapes(1, n_points=256, seed=300)
+    pipeline_case(ns, "random_small", E, P, 0.05, 5, 25)
+
+
+if __name__ == "__main__":
+    main()

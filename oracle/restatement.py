@@ -1,0 +1,267 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (the "oracle") of PRIFIT's mean-shift + ellipsoid-fit path.
+
+This file is the checker, never the product: only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The product package
+``prifit_b200`` never does and fails loudly when its CUDA library is missing.
+
+It restates, in eager torch on the CPU and for any floating dtype (fp32 = what the reference
+runs, fp64 = the gradient acceptance oracle of SURVEY.md 0.9), the algorithm of
+
+    src/guard.py:6-18                         guard_exp / guard_sqrt
+    src/mean_shift.py:18-84,138-202,230-247   bandwidth, mean-shift iterations, NMS, membership
+    src/ellipsoid_utils.py:9-73               guard loop, per-shape clustering
+    src/ellipsoid_fitting.py:19-141           weighted moments -> covariance -> SVD -> extents
+    src/fitting_utils.py:67-139               custom SVD backward
+    convex_loss.py:37-41,57,313-343           double normalisation, approximate ellipsoid SDF
+    src/utils.py:407-425                      SDF half of analytic_chamfer_distance
+
+Pinning: the reference ships no tests or golden vectors.  ``oracle/make_golden.py``
+runs the unmodified reference (through ``oracle/ref_loader.py``) in the build container, checks
+this restatement against it, and commits the reference's outputs as fixtures under
+``tests/golden/``; ``tests/test_oracle_golden.py`` re-checks the restatement against those
+fixtures everywhere.
+
+Dense on purpose: it materialises the N x N kernel matrix per iteration and lets autograd run the
+dense backward, exactly like the reference, so timing it is a fair CPU baseline ("port").
+"""
+import numpy as np
+import torch
+
+LO, HI = -13.0, 75.0
+
+
+# ----------------------------------------------------------------------------- guards
+def guard_exp(x, max_value=HI, min_value=LO):
+    """src/guard.py:6-11."""
+    return torch.exp(torch.clamp(x, min=min_value, max=max_value))
+
+
+def guard_sqrt(x, minimum=1e-5):
+    """src/guard.py:13-18."""
+    return torch.sqrt(torch.clamp(x, min=minimum))
+
+
+def normalize_twice(E):
+    """convex_loss.py:41,57 -- F.normalize(dim=-1) applied twice (two autograd nodes)."""
+    X = torch.nn.functional.normalize(E, dim=-1, p=2)
+    return torch.nn.functional.normalize(X, dim=-1, p=2)
+
+
+# ----------------------------------------------------------------------------- mean shift
+def compute_bandwidth(X, num_samples, quantile, perm=None):
+    """src/mean_shift.py:138-160.  ``perm`` replaces the host np.random.shuffle (line 150)."""
+    N = X.shape[0]
+    if perm is None:
+        perm = np.arange(N)
+        np.random.shuffle(perm)
+    Xs = X[torch.as_tensor(np.asarray(perm[:num_samples]), dtype=torch.long)]
+    dist = 2 - 2 * Xs @ Xs.T
+    k = int(quantile * num_samples)
+    kth = torch.topk(dist, k=k, dim=1, largest=False)[0][:, -1]
+    return torch.mean(guard_sqrt(kth, 1e-6))
+
+
+def mean_shift_iterations(X, b, iterations):
+    """src/mean_shift.py:50-84 (gaussian branch).  Returns the shifted seeds new_X[N,d]."""
+    Y = X.clone()
+    for _ in range(iterations):
+        dist = 2.0 - 2.0 * Y @ X.T
+        K = guard_exp(-dist / (b ** 2) / 2)
+        D = 1 / torch.sum(K, 1, keepdim=True)
+        M = (K @ X) * D - Y
+        Y = Y + 1 * M
+        Y = Y / torch.norm(Y, dim=1, p=2, keepdim=True)
+    return Y
+
+
+def nms(C, X, b):
+    """src/mean_shift.py:162-202.  Returns (centres, ids[int64, ascending], labels[int64])."""
+    nearest = torch.min(2.0 - 2.0 * C @ X.T, 0)[1]
+    uniq, counts = np.unique(nearest.cpu().numpy(), return_counts=True)
+    votes = torch.zeros(X.shape[0], dtype=torch.float32)
+    votes[torch.from_numpy(uniq)] = torch.from_numpy(counts.astype(np.float32))
+    nbrs = ((2.0 - 2.0 * C @ C.T) < b).float()
+    ids = torch.unique(torch.max(nbrs[torch.from_numpy(uniq)] * votes.reshape(1, -1), 1)[1])
+    centres = C[ids]
+    labels = torch.max(centres @ X.T, 0)[1]
+    return centres, ids, labels
+
+
+def mean_shift(X, num_samples, quantile, iterations, bw=None, perm=None):
+    """src/mean_shift.py:18-48 (eff=False)."""
+    if bw is None:
+        with torch.no_grad():
+            bw = compute_bandwidth(X, num_samples, quantile, perm)
+    Y = mean_shift_iterations(X, bw, iterations)
+    with torch.no_grad():
+        _, ids, labels = nms(Y, Y, bw)
+    return Y[ids], bw, labels, ids
+
+
+def guard_mean_shift(X, num_samples, quantile, iterations, max_num_clusters):
+    """src/ellipsoid_utils.py:9-27.  Also returns the representative ids and the pass count."""
+    passes = 0
+    while True:
+        centre, bw, labels, ids = mean_shift(X, num_samples, quantile, iterations)
+        passes += 1
+        if torch.unique(labels).shape[0] > max_num_clusters:
+            quantile *= 2
+        else:
+            break
+    return centre, bw, labels, ids, passes
+
+
+def membership(C, X, bw):
+    """src/mean_shift.py:230-247.  Returns [K, N]."""
+    sim = (C @ X.T) / (bw ** 2)
+    sim = sim - sim.max().detach()
+    e = guard_exp(sim)
+    return e / torch.sum(e, 0).unsqueeze(0)
+
+
+def clustering(X, num_samples=1000, quantile=0.01, iterations=5, max_num_clusters=25, info=None):
+    """src/ellipsoid_utils.py:31-73 (visualize=False).  X[B,N,d] -> (list of W[N,K_b], list of labels)."""
+    weights, labels = [], []
+    for b in range(X.shape[0]):
+        centre, bw, lab, ids, passes = guard_mean_shift(X[b], num_samples, quantile, iterations, max_num_clusters)
+        weights.append(membership(centre, X[b], bw).T)
+        labels.append(lab)
+        if info is not None:
+            info.append({"bw": float(bw), "ids": ids.clone(), "passes": passes, "centres": centre.detach().clone()})
+    return weights, labels
+
+
+# ----------------------------------------------------------------------------- fit
+def _svd_grad_K(S):
+    """src/fitting_utils.py:82-105."""
+    n = S.shape[0]
+    diff = S.view(n, 1) - S.view(1, n)
+    plus = S.view(n, 1) + S.view(1, n)
+    eps = torch.full((n, n), 1e-6, dtype=S.dtype)
+    kneg = torch.sign(diff) * torch.max(diff.abs(), eps)
+    kneg[torch.arange(n), torch.arange(n)] = 1e-6
+    off = torch.ones(n, n, dtype=S.dtype) - torch.eye(n, dtype=S.dtype)
+    return (1 / kneg) * (1 / plus) * off
+
+
+class _CustomSVD(torch.autograd.Function):
+    """src/fitting_utils.py:108-136 with compute_grad_V (:67-79): dA = U dS V^T + 2 U S sym(K^T o V^T dV) V^T."""
+
+    @staticmethod
+    def forward(ctx, A):
+        U, S, Vh = torch.linalg.svd(A, full_matrices=False)
+        V = Vh.transpose(-1, -2).contiguous()
+        ctx.save_for_backward(U, S, V)
+        return U, S, V
+
+    @staticmethod
+    def backward(ctx, gU, gS, gV):
+        U, S, V = ctx.saved_tensors
+        K = _svd_grad_K(S)
+        inner = K.T * (V.T @ gV)
+        inner = (inner + inner.T) / 2.0
+        out = 2 * U @ torch.diag(S) @ inner @ V.T
+        return U @ torch.diag(gS) @ V.T + out
+
+
+customsvd = _CustomSVD.apply
+
+
+def principal_axis_ellipsoid(points, weights, V):
+    """src/ellipsoid_fitting.py:119-141, mode="slow".  points are already centred once."""
+    q = points - torch.sum(points * weights, 0) / torch.sum(weights)
+    r = q * weights
+    if torch.det(V.T) < 0:
+        V = torch.stack([V[:, 0], V[:, 1], -1 * V[:, 2]], 1)
+    t = r @ V
+    hi, arg_hi = torch.max(t, 0)
+    lo, arg_lo = torch.min(t, 0)
+    return torch.abs(hi - lo) / 2.0, V, (arg_hi, arg_lo)
+
+
+def weighted_ellipsoid_fitting(points, weights, noise=None, aux=None):
+    """src/ellipsoid_fitting.py:19-69.  weights[N,1].  Returns (s, V, centre) or -1.
+
+    ``noise`` (3x3, U[0,1)) replaces the CPU ``torch.rand(3,3)`` of line 38; drawn here if None.
+    """
+    W = torch.sum(weights)
+    centre = torch.sum(points * weights, 0) / W
+    q = points - centre
+    cov = (q * weights).T @ q / W
+    if noise is None:
+        noise = torch.rand(3, 3)
+    A = cov + 1e-4 * cov.mean() * noise.to(cov.dtype)
+    try:
+        with torch.no_grad():
+            S = torch.linalg.svdvals(A)
+            if not bool(torch.isfinite(S).all()):
+                raise RuntimeError("non-finite covariance")
+            if S[0] / S[2] > 1e5:
+                return -1
+        U, S, V = customsvd(A)
+        s, V, arg = principal_axis_ellipsoid(q, weights, V)
+        if aux is not None:
+            aux.append({"cov": cov.detach(), "S": S.detach(), "arg": arg})
+        return s, V, centre
+    except RuntimeError:
+        return -1
+
+
+def weighted_ellipsoid_fitting_batch(points, weights_batch, noise=None, aux=None):
+    """src/ellipsoid_fitting.py:74-117: loops b-major, k-minor; failed clusters are dropped.
+
+    ``noise``: optional [B, K_cap, 3, 3]; entry (b, k) is used for attempted cluster k of shape b.
+    """
+    params = []
+    for b in range(points.shape[0]):
+        per_shape = []
+        for k in range(weights_batch[b].shape[1]):
+            nz = None if noise is None else noise[b, k]
+            p = weighted_ellipsoid_fitting(points[b], weights_batch[b][:, k:k + 1], nz, aux)
+            if not isinstance(p, int):
+                per_shape.append(p)
+        params.append(per_shape)
+    return params
+
+
+# ----------------------------------------------------------------------------- SDF loss
+def compute_sdf_ellipsoid(points, centre, r, V):
+    """convex_loss.py:313-328."""
+    z = (V.T @ (points - centre).T).T
+    k0 = torch.norm(z / (r + 1e-6), p=2, dim=1)
+    k1 = torch.norm(z / (r ** 2 + 1e-6), p=2, dim=1)
+    return k0 * (k0 - 1.0) / (k1 + 1e-6)
+
+
+def sdf_loss(points_batch, params_batch):
+    """SDF half of analytic_chamfer_distance (src/utils.py:407-411,418,425): per shape with >= 1
+    ellipsoid, 0.5 * mean_j (min_k |sdf_kj|)^2; mean over those shapes; zeros(1) if none."""
+    per_shape = []
+    for b, params in enumerate(params_batch):
+        if len(params) == 0:
+            continue
+        sdf = torch.stack([compute_sdf_ellipsoid(points_batch[b], c, r, V) for (r, V, c) in params], 1)
+        per_shape.append(torch.mean(torch.min(sdf.abs(), 1)[0] ** 2) / 2.0)
+    if not per_shape:
+        return torch.zeros(1, dtype=points_batch.dtype, requires_grad=True)
+    return torch.stack(per_shape).mean()
+
+
+# ----------------------------------------------------------------------------- whole path
+def fit_loss(E, P, quantile=0.05, iterations=10, max_num_clusters=25, noise=None, Q=None,
+             backward=True, info=None):
+    """normalise x2 -> clustering -> fit -> SDF loss (-> backward to E).  E[B,N,d], P[B,N,3].
+
+    Returns dict(loss, grad_E, params, labels, weights).  Q = clouds the SDF is evaluated on (default P).
+    """
+    E = E.detach().clone().requires_grad_(backward)
+    X = normalize_twice(E)
+    weights, labels = clustering(X, num_samples=X.shape[1], quantile=quantile, iterations=iterations,
+                                 max_num_clusters=max_num_clusters, info=info)
+    params = weighted_ellipsoid_fitting_batch(P, weights, noise)
+    loss = sdf_loss(P if Q is None else Q, params)
+    grad = None
+    if backward:
+        loss.sum().backward()
+        grad = E.grad.detach()
+    return {"loss": loss.detach(), "grad_E": grad, "params": params, "labels": labels, "weights": weights}
