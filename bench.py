@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the mean-shift + ellipsoid-fit hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4|cfg1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A step = forward + backward of the fitting loss over one batch of synthetic shapes
+(normalise x2 -> bandwidth -> T mean-shift iterations -> NMS -> K fp32 seed trajectories -> membership
+-> ellipsoid fit -> SDF loss -> backward to the un-normalised embeddings).  Per-GPU work is fixed
+(24 shapes of 2048 points on every rank: weak scaling; 8 GPUs = the 192-shape config), the only
+collective is the 8-byte loss all-reduce.
+
+Prints ONE JSON line on rank 0 (see README / DESIGN.md for the fields).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (shapes per GPU, points, quantile, iterations, max clusters, planted clusters)
+    "cfg1": (1, 2048, 0.05, 10, 25, 16),
+    "cfg2": (24, 2048, 0.05, 10, 25, 16),
+    "cfg4": (16, 10000, 0.05, 10, 50, 16),
+}
+D = 128
+N_SETS = 8          # rotating input sets: 8 x 25 MB of embeddings > 126 MB of L2
+
+
+def algorithmic_flops_per_shape(N, T, K, passes=1):
+    """G*2N^2 d(2T+2) + 12 T K N d + 8 K N d."""
+    return passes * 2.0 * N * N * D * (2 * T + 2) + 12.0 * T * K * N * D + 8.0 * K * N * D
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            top = sorted(sm)[len(sm) // 2:]          # samples under load = upper half
+            out = {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    from prifit_b200 import _lib, dist as pdist, ops, pipeline, synthetic
+    import prifit_b200.convex_loss as cl
+    import torch.distributed as dist
+
+    rank, world, local = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    _lib.load()
+    B, N, q, T, kmax, kc = WORKLOADS[args.workload]
+    engine = ops.MS_FP32_SIMT if args.engine == "fp32" else ops.MS_TF32_TCGEN05
+    ops.DEFAULT_ENGINE = engine
+
+    # rotating synthetic input sets; rank r, set s uses shapes seeded (s*world + r) * B + b
+    host_E, host_P = [], []
+    for s in range(N_SETS):
+        E, P, _ = synthetic.planted_shapes(B, n_points=N, n_clusters=kc, seed=1000 + (s * world + rank) * B)
+        host_E.append(E.pin_memory()); host_P.append(P.pin_memory())
+    dev_E = [e.to(dev) for e in host_E]
+    dev_P = [p.to(dev) for p in host_P]
+    # channel-first copies for the reference-shaped public API (convex_loss takes [B,128,N] / [B,3,N])
+    host_Xcf = [e.permute(0, 2, 1).contiguous().pin_memory() for e in host_E]
+    host_Pcf = [p.permute(0, 2, 1).contiguous().pin_memory() for p in host_P]
+    torch.manual_seed(1234 + rank)
+
+    ms_events = []
+
+    def step_resident(i, timed):
+        E = dev_E[i % N_SETS].detach().requires_grad_(True)
+        ops.TIMING = ms_events if timed else None
+        out = pipeline.fit_loss(E, dev_P[i % N_SETS], quantile=q, iterations=T, max_num_clusters=kmax)
+        ops.TIMING = None
+        L, Lb = pdist.global_masked_mean(out["loss_b"], out["has"])
+        Lb.backward()
+        return L, out
+
+    def step_e2e(i):
+        X = host_Xcf[i % N_SETS].to(dev, non_blocking=True).requires_grad_(True)
+        pts = host_Pcf[i % N_SETS].to(dev, non_blocking=True)
+        total, l, params, labels = cl.convex_loss(pts, pts, X, quantile=q, iterations=T, max_num_clusters=kmax)
+        if world > 1:
+            valid = params.padded[3]
+            n_local = (valid.sum(1) > 0).float().sum()
+            L, Lb = pdist.global_mean_from_local(total, n_local)
+            Lb.backward()
+            return float(L.item())
+        total.backward()
+        return float(total.item())               # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i, False)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i, True)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1])
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    last = {}
+
+    def resident(i, timed):
+        L, out = step_resident(i, timed)
+        last["L"], last["out"] = L, out
+
+    ms_total, _ = timed_region(resident, args.steps, args.warmup)
+    launches_total = _lib.launch_count()
+    n_ms_launch = len(ms_events)
+    ms_kernel = sum(a.elapsed_time(b) for a, b in ms_events) / max(n_ms_launch, 1)
+    e2e_ms, _ = timed_region(lambda i, timed: step_e2e(i), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    res = last["out"]["cluster"]
+    K_mean = sum(res.K_host) / len(res.K_host)
+    passes = sum(res.passes) / len(res.passes)
+    ms_per_step = ms_total / args.steps
+    shapes_per_s = world * B / (ms_per_step * 1e-3)
+    e2e_sps = world * B / (e2e_ms / args.steps * 1e-3)
+    pk = peaks()
+    # dominant kernel: the all-seed mean-shift pass (2 GEMMs x T x N^2 d per shape)
+    flops_launch = 4.0 * N * N * D * T * B
+    tf32_peak = 0.5 * pk["bf16_tflops_sustained"]
+    achieved = flops_launch / (ms_kernel * 1e-3) / 1e12 if ms_kernel > 0 else 0.0
+    line = {
+        "metric": "shapes/sec mean-shift+ellipsoid fit fwd+bwd (2048 pts)" if N == 2048 else
+                  "shapes/sec mean-shift+ellipsoid fit fwd+bwd (%d pts)" % N,
+        "value": round(shapes_per_s, 2), "unit": "shapes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (all-seed mean-shift GEMMs: %s)" % ("tf32 tcgen05" if engine == ops.MS_TF32_TCGEN05 else "f32 simt"),
+        "data": "synthetic",
+        "config": {"workload": "%s: %d shapes x %d pts x %d-d per GPU, T=%d, quantile=%g, max_num_clusters=%d, "
+                               "%d planted clusters (S1)" % (args.workload, B, N, D, T, q, kmax, kc),
+                   "shapes_per_gpu": B, "global_shapes": world * B, "clusters_found_mean": K_mean,
+                   "guard_passes_mean": passes, "loss": float(last["L"]),
+                   "l2": "rotating %d input sets (%.0f MB of embeddings) > 126 MB L2" % (N_SETS, N_SETS * B * N * D * 4 / 1e6),
+                   "parallelism": "shapes sharded %d/GPU, one 8-byte NCCL all-reduce per step" % B},
+        "e2e": {"value": round(e2e_sps, 2), "unit": "shapes/s", "ms_per_step": round(e2e_ms / args.steps, 4),
+                "h2d_bytes_per_step": int(host_Xcf[0].numel() * 4 + host_Pcf[0].numel() * 4), "d2h_bytes_per_step": 4,
+                "api": "prifit_b200.convex_loss.convex_loss(points[B,3,N], chamfer[B,3,N], X[B,128,N]) + backward"},
+        "gpu_launches": int(round(launches_total / (args.steps + args.warmup) * args.steps)),
+        "gpu_launches_per_step": round(launches_total / (args.steps + args.warmup), 1),
+        "roofline": {"bound": "tensor", "kernel": "meanshift_fwd (%s)" % args.engine, "achieved": round(achieved, 2),
+                     "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(achieved / tf32_peak, 4),
+                     "traffic": None, "kernel_ms": round(ms_kernel, 4), "launches_timed": n_ms_launch,
+                     "flops_per_launch": flops_launch,
+                     "peak_source": "%s bf16 sustained %.0f TF/s x 0.5 (kind::tf32 runs at half the bf16 rate)" % (pk["source"], pk["bf16_tflops_sustained"]),
+                     "whole_step_tflops": round(shapes_per_s / world * algorithmic_flops_per_shape(N, T, K_mean, passes) / 1e12, 2)},
+        "clocks": clocks,
+    }
+    if rank == 0:
+        line["cpu_baseline"] = cpu_baseline(args.workload, shapes=min(B, 6))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def _oracle_step(E, P, q, T, kmax):
+    from oracle import restatement as R
+    return R.fit_loss(E, P, q, T, kmax)
+
+
+def cpu_baseline(workload, shapes):
+    """The oracle port (oracle/restatement.py: the reference's dense eager-torch algorithm) timed on the
+    host cores on a bounded sample of the same workload."""
+    from prifit_b200 import synthetic
+    B, N, q, T, kmax, kc = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if N > 4096:
+        shapes = 1
+    E, P, _ = synthetic.planted_shapes(shapes, n_points=N, n_clusters=kc, seed=1000)
+    _oracle_step(E[:1], P[:1], q, T, kmax)                     # warm-up
+    t0 = time.perf_counter()
+    _oracle_step(E, P, q, T, kmax)
+    dt = time.perf_counter() - t0
+    return {"value": round(shapes / dt, 3), "unit": "shapes/s", "cores": cores, "threads": torch.get_num_threads(),
+            "kind": "port", "sample": "%d of the %d shapes of one step, fwd+bwd, %.1f s" % (shapes, B, dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  /root/reference is pure Python
+    with unavailable GUI dependencies and does not exist on the GPU box, so the arm times the oracle
+    port (same dense eager-torch op sequence, all host threads)."""
+    from prifit_b200 import synthetic
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, N, q, T, kmax, kc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    per_step = 2 if N <= 4096 else 1
+    E, P, _ = synthetic.planted_shapes(per_step * 2, n_points=N, n_clusters=kc, seed=1000)
+    for i in range(args.warmup):
+        _oracle_step(E[:1], P[:1], q, T, kmax)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        o = (i % 2) * per_step
+        _oracle_step(E[o:o + per_step], P[o:o + per_step], q, T, kmax)
+    dt = time.perf_counter() - t0
+    sps = args.steps * per_step / dt
+    sample = "%d shapes per step (of %d), fwd+bwd, oracle port on %d threads" % (per_step, B, torch.get_num_threads())
+    print(json.dumps({
+        "impl": "reference", "metric": "shapes/sec mean-shift+ellipsoid fit fwd+bwd (%d pts)" % N,
+        "value": round(sps, 3), "unit": "shapes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %d pts x %d-d, T=%d, quantile=%g, max_num_clusters=%d (CPU sample: %s)" % (
+            args.workload, N, D, T, q, kmax, sample)},
+        "cpu_baseline": {"value": round(sps, 3), "unit": "shapes/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(sps, 3), "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "fp32"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,133 @@
+/*
+ * prifit_b200 -- C ABI of the B200-native mean-shift + ellipsoid-fit path.
+ *
+ * The reference (Hippogriff/prifit) is pure Python/eager-torch and has no FFI of its own; the
+ * boundary it exposes is the Python call surface of src/mean_shift.py, src/ellipsoid_utils.py,
+ * src/ellipsoid_fitting.py, src/fitting_utils.py and convex_loss.py.  `prifit_b200/*.py` keeps that
+ * surface and calls the entry points below through ctypes.  Each entry point cites the reference
+ * code it replaces (paths relative to the reference root).
+ *
+ * Common rules
+ *   - extern "C"; every function returns int: 0 = ok, <0 = bad argument (PRIFIT_E_*),
+ *     >0 = cudaError_t of the failed runtime call.  prifit_last_error_string() describes it.
+ *   - never throws, never allocates device memory, never synchronises the host; work is enqueued
+ *     on `stream` (a cudaStream_t passed as void*).  Scratch memory is caller-provided
+ *     (`ws`, sized by the matching *_workspace_bytes()).  Re-entrant across streams as long as
+ *     workspaces are distinct.
+ *   - all pointers are DEVICE pointers to contiguous row-major fp32 / int32 / uint8 arrays.
+ *   - padded layouts: per-shape cluster lists are [B, Kcap, ...] with int32 K[B] valid entries.
+ *   - B shapes, N points per shape, d embedding width (multiple of 4; tcgen05 path: d == 128),
+ *     T mean-shift iterations, Kcap cluster capacity (multiple of 4, <= 64).
+ */
+#ifndef PRIFIT_B200_H
+#define PRIFIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRIFIT_VERSION 100
+
+#define PRIFIT_E_BADARG   (-1)   /* null pointer / non-positive size */
+#define PRIFIT_E_SHAPE    (-2)   /* unsupported shape (d, Kcap, N limits) */
+#define PRIFIT_E_WS       (-3)   /* workspace too small */
+#define PRIFIT_E_NODEVICE (-4)   /* no sm_100 device / driver entry point missing */
+
+/* mean-shift forward engines */
+#define PRIFIT_MS_TF32_TCGEN05 0 /* tensor cores: tcgen05.mma kind::tf32, TMEM accumulators, TMA */
+#define PRIFIT_MS_FP32_SIMT    1 /* CUDA-core fp32, used to cross-check the tensor-core kernel */
+
+int prifit_version(void);
+const char* prifit_last_error_string(void);
+/* 1 if the current device is compute capability 10.x, else 0 (or <0 on error) */
+int prifit_device_ok(void);
+
+/* A0 -- X = normalize(normalize(E)) row-wise, eps 1e-12.  convex_loss.py:41,57 */
+int prifit_normalize_fwd(const float* E, int64_t rows, int d, float* X, void* stream);
+/* backward of the two stacked F.normalize nodes; gE may alias gX */
+int prifit_normalize_bwd(const float* E, const float* gX, int64_t rows, int d, float* gE, void* stream);
+
+/* k1 -- bandwidth.  src/mean_shift.py:138-160 (compute_bandwidth)
+ *   rows: optional [B, n_s] int32 subset (the first num_samples entries of the host shuffle,
+ *   line 150); NULL = all N rows (n_s must equal N).  kth[B] = int(quantile * n_s) per shape
+ *   (1-based rank of the order statistic).  bw_out[B] = mean_i sqrt(max(kth-smallest_i, 1e-6)). */
+size_t prifit_bandwidth_workspace_bytes(int B, int N, int d, int n_s);
+int prifit_bandwidth_fwd(const float* X, int B, int N, int d, const int32_t* rows, int n_s,
+                         const int32_t* kth, float* bw_out, void* ws, size_t ws_bytes, void* stream);
+
+/* k2 -- T mean-shift iterations of all N seeds.  src/mean_shift.py:50-84 (mean_shift_, gaussian)
+ *   newX_out[B,N,d].  engine = PRIFIT_MS_*.  Never materialises the N x N kernel matrix. */
+size_t prifit_meanshift_workspace_bytes(int B, int N, int d, int engine);
+int prifit_meanshift_fwd(const float* X, const float* bw, int B, int N, int d, int T, float* newX_out,
+                         int engine, void* ws, size_t ws_bytes, void* stream);
+
+/* k3 -- NMS mode pruning + hard labels.  src/mean_shift.py:162-202 (nms(new_X, new_X, bw)) and the
+ *   guard predicate of src/ellipsoid_utils.py:19-26.
+ *   idx_out[B,Kcap]  representative point index per cluster, ascending, -1 padded
+ *   K_out[B]         number of representatives (may exceed Kcap; only Kcap are stored)
+ *   labels_out[B,N]  argmax_k <newX[idx[k]], newX[j]>, lowest k on ties
+ *   n_labels_out[B]  number of distinct labels (== torch.unique(labels).shape[0]); K if K > Kcap */
+size_t prifit_nms_workspace_bytes(int B, int N, int d);
+int prifit_nms_fwd(const float* newX, const float* bw, int B, int N, int d, int Kcap,
+                   int32_t* idx_out, int32_t* K_out, int32_t* labels_out, int32_t* n_labels_out,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* k2 rows -- fp32 trajectories of the K selected seeds (center = new_X[indices],
+ *   src/mean_shift.py:46): traj_out[B, T+1, Kcap, d] (y^0..y^T), stat_out[B, T, Kcap, 2] =
+ *   (Z_t, ||u_t||), C_out[B,Kcap,d] = y^T.  Rows k >= K[b] are zero. */
+int prifit_meanshift_rows_fwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K,
+                              int B, int N, int d, int T, int Kcap,
+                              float* traj_out, float* stat_out, float* C_out, void* stream);
+/* k2 backward -- autograd of mean_shift_ restricted to the K seeds that carry gradient (rows are
+ *   independent given X).  gC[B,Kcap,d] = dL/d center; accumulates dL/dX into gX_inout[B,N,d]. */
+int prifit_meanshift_rows_bwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K,
+                              const float* traj, const float* stat, const float* gC,
+                              int B, int N, int d, int T, int Kcap, float* gX_inout, void* stream);
+
+/* k4 -- soft membership.  src/mean_shift.py:230-247 (membership); W_out[B,Kcap,N] (cluster-major,
+ *   i.e. the reference's [K,N] before the caller's transpose), smax_out[B] = the detached global max. */
+size_t prifit_membership_workspace_bytes(int B, int N, int Kcap);
+int prifit_membership_fwd(const float* C, const float* X, const float* bw, const int32_t* K,
+                          int B, int N, int d, int Kcap, float* W_out, float* smax_out,
+                          void* ws, size_t ws_bytes, void* stream);
+/* gC_out[B,Kcap,d] is overwritten; dL/dX is accumulated into gX_inout[B,N,d] */
+int prifit_membership_bwd(const float* C, const float* X, const float* bw, const int32_t* K,
+                          const float* W, const float* smax, const float* gW,
+                          int B, int N, int d, int Kcap, float* gC_out, float* gX_inout, void* stream);
+
+/* k5-k7 -- weighted ellipsoid fit.  src/ellipsoid_fitting.py:19-69,119-141 and the SVD of
+ *   src/fitting_utils.py:108-139.
+ *   P[B,N,3], W[B,Kcap,N], noise[B,Kcap,3,3] = the U[0,1) draw of line 38.
+ *   s_out[B,Kcap,3] half extents, V_out[B,Kcap,3,3] principal axes (columns), c_out[B,Kcap,3],
+ *   valid_out[B,Kcap] uint8: 0 = dropped (the reference's `return -1`: cond > 1e5, or non-finite),
+ *   ctx_out[B,Kcap,PRIFIT_FIT_CTX] saved for backward. */
+#define PRIFIT_FIT_CTX 48
+int prifit_fit_fwd(const float* P, const float* W, const int32_t* K, const float* noise,
+                   int B, int N, int Kcap, float* s_out, float* V_out, float* c_out,
+                   uint8_t* valid_out, float* ctx_out, void* stream);
+/* gs/gV/gc: dL/d(s,V,c) (entries of dropped clusters are ignored).  gW_out[B,Kcap,N] overwritten
+ *   (zero for dropped / padded clusters); gP_inout[B,N,3] optional accumulation (may be NULL).
+ *   Includes the custom SVD backward of src/fitting_utils.py:67-105. */
+int prifit_fit_bwd(const float* P, const float* W, const int32_t* K, const float* noise,
+                   const float* ctx, const uint8_t* valid, const float* gs, const float* gV, const float* gc,
+                   int B, int N, int Kcap, float* gW_out, float* gP_inout, void* stream);
+
+/* k8 -- SDF half of the fitting loss.  convex_loss.py:313-343 + src/utils.py:407-411.
+ *   Q[B,M,3]; loss_out[B] = 0.5 * mean_j (min_k |sdf_kj|)^2 over valid ellipsoids (0 if none);
+ *   argmin_out[B,M] = arg of the min (-1 if none); sdf_out[B,M] = signed sdf of that ellipsoid. */
+size_t prifit_sdf_workspace_bytes(int B, int M);
+int prifit_sdf_loss_fwd(const float* Q, const float* s, const float* V, const float* c, const uint8_t* valid,
+                        const int32_t* K, int B, int M, int Kcap, float* loss_out, int32_t* argmin_out,
+                        float* sdf_out, void* ws, size_t ws_bytes, void* stream);
+/* gloss[B] = dL/d loss_b.  gs/gV/gc [B,Kcap,...] overwritten; gQ_out[B,M,3] optional (may be NULL) */
+int prifit_sdf_loss_bwd(const float* Q, const float* s, const float* V, const float* c, const uint8_t* valid,
+                        const int32_t* K, const int32_t* argmin, const float* gloss, int B, int M, int Kcap,
+                        float* gs_out, float* gV_out, float* gc_out, float* gQ_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRIFIT_B200_H */

@@ -1,0 +1,98 @@
+"""ctypes binding of libprifit_b200.so -- the C ABI declared in include/prifit_b200.h.
+
+There is no CPU fallback: if the library is missing, or a call fails, this raises.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libprifit_b200.so")
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/prifit_b200.h one to one
+SIGNATURES = {
+    "prifit_version": (_i, []),
+    "prifit_last_error_string": (ctypes.c_char_p, []),
+    "prifit_device_ok": (_i, []),
+    "prifit_normalize_fwd": (_i, [_p, _i64, _i, _p, _p]),
+    "prifit_normalize_bwd": (_i, [_p, _p, _i64, _i, _p, _p]),
+    "prifit_bandwidth_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "prifit_bandwidth_fwd": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _sz, _p]),
+    "prifit_meanshift_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "prifit_meanshift_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _sz, _p]),
+    "prifit_nms_workspace_bytes": (_sz, [_i, _i, _i]),
+    "prifit_nms_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "prifit_meanshift_rows_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "prifit_meanshift_rows_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "prifit_membership_workspace_bytes": (_sz, [_i, _i, _i]),
+    "prifit_membership_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "prifit_membership_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "prifit_fit_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "prifit_fit_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "prifit_sdf_workspace_bytes": (_sz, [_i, _i]),
+    "prifit_sdf_loss_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "prifit_sdf_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
+}
+
+FIT_CTX = 48
+MS_TF32_TCGEN05 = 0
+MS_FP32_SIMT = 1
+
+_lib = None
+
+
+class PrifitError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and declare every prototype.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PrifitError(
+            "libprifit_b200.so not found at %s -- build it with `python -m prifit_b200.build` "
+            "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().prifit_last_error_string().decode("utf-8", "replace")
+        raise PrifitError("%s failed with code %d: %s" % (what, rc, msg))
+
+
+# kernels (and memset nodes) each entry point enqueues; bench.py reports the sum as `gpu_launches`
+LAUNCHES = {
+    "prifit_normalize_fwd": 1, "prifit_normalize_bwd": 1, "prifit_bandwidth_fwd": 2, "prifit_meanshift_fwd": 1,
+    "prifit_nms_fwd": 8, "prifit_meanshift_rows_fwd": 1, "prifit_meanshift_rows_bwd": 1,
+    "prifit_membership_fwd": 2, "prifit_membership_bwd": 1, "prifit_fit_fwd": 1, "prifit_fit_bwd": 1,
+    "prifit_sdf_loss_fwd": 2, "prifit_sdf_loss_bwd": 1,
+}
+_launches = 0
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count():
+    return _launches
+
+
+def call(name, *args):
+    global _launches
+    check(getattr(load(), name)(*args), name)
+    _launches += LAUNCHES.get(name, 0)

@@ -1,0 +1,61 @@
+"""Mirror of the hot-path part of the reference's convex_loss.py.
+
+    convex_loss                     reference :27-103   normalise -> cluster -> fit -> loss
+    compute_sdf_ellipsoid[s][_batch] reference :313-343
+
+Scope: the fitting loss computed here is the analytic SDF half of
+`analytic_chamfer_distance` (src/utils.py:407-411,418,425) evaluated on `chamfer_points`.  The other
+half needs trimesh surface sampling + an sklearn KD-tree on the CPU (src/utils.py:413-416,
+src/sample_ellipsoid.py) and is a "next" row; the optional entropy / intersection / pruning terms
+are likewise out of scope and raise if requested.
+"""
+import torch
+
+from . import ops, pipeline
+from .ellipsoid_fitting import ParamsBatch
+from .ellipsoid_utils import meanshift
+
+
+def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, quantile=0.01, iterations=5,
+                visualize=False, max_num_clusters=25, class_list=[], include_intersect_loss=False, alpha=1, beta=1,
+                if_cuboid=False, include_pruning=False, include_entropy_loss=False, evaluation=False):
+    """points[B,3,N], chamfer_points[B,3,M], X[B,128,N] -> (total[1,1], l[1,1], params, labels).
+
+    Same signature, defaults and return structure as the reference.  `params` is a lazy sequence of
+    per-shape lists of (s, V, center); `labels` a list of int64 [N] tensors."""
+    if include_intersect_loss or include_pruning or include_entropy_loss or if_cuboid:
+        raise NotImplementedError("intersection / pruning / entropy / cuboid terms are outside the accelerated path")
+    E = X.permute(0, 2, 1).contiguous()                       # reference :37
+    P = points.permute(0, 2, 1).contiguous()                  # reference :38
+    Q = None if evaluation else chamfer_points.permute(0, 2, 1).contiguous()   # reference :84
+    out = pipeline.fit_loss(E, P, quantile=quantile, iterations=iterations, max_num_clusters=max_num_clusters,
+                            Q=Q, engine=meanshift.engine)
+    res = out["cluster"]
+    params = ParamsBatch(out["s"], out["V"], out["c"], out["valid"], res.K, res.K_host)
+    labels = list(res.labels.long().unbind(0))
+    l = out["loss"] if not evaluation else torch.zeros(1, device=E.device, requires_grad=True)   # reference :92-94
+    total = l
+    return total.view(1, 1), l.view(1, 1), params, labels
+
+
+def compute_sdf_ellipsoid(points, center, r, V):
+    """Approximate SDF of points[M,3] w.r.t. one ellipsoid (reference :313-328); torch expression."""
+    z = (V.T @ (points - center).T).T
+    k0 = torch.norm(z / (r + 1e-6), p=2, dim=1)
+    k1 = torch.norm(z / (r ** 2 + 1e-6), p=2, dim=1)
+    return k0 * (k0 - 1.0) / (k1 + 1e-6)
+
+
+def compute_sdf_ellipsoids(points, ellipsoids_parameters):
+    return [compute_sdf_ellipsoid(points, c, r, V) for (r, V, c) in ellipsoids_parameters]
+
+
+def compute_sdf_ellipsoids_batch(points, ellipsoids_parameters_batch):
+    return [compute_sdf_ellipsoids(points[b], p) for b, p in enumerate(ellipsoids_parameters_batch)]
+
+
+def sdf_fitting_loss(points, ellipsoids_parameters_batch):
+    """SDF half of analytic_chamfer_distance on the device kernel: points[B,M,3] -> scalar loss."""
+    s, V, c, valid, K = ellipsoids_parameters_batch.padded
+    loss_b = ops.SdfLoss.apply(ops._chk(points), s, V, c, valid, K)
+    return pipeline.masked_mean(loss_b, valid)[0]

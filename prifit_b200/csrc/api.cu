@@ -1,0 +1,137 @@
+// Diagnostics entry points + the two row-normalisation kernels (A0).
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+static thread_local char g_err[512] = "ok";
+
+void prifit_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int prifit_version(void) { return PRIFIT_VERSION; }
+extern "C" const char* prifit_last_error_string(void) { return g_err; }
+
+extern "C" int prifit_device_ok(void) {
+    int dev = 0;
+    PF_CUDA(cudaGetDevice(&dev));
+    int major = 0;
+    PF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    return major == 10 ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// X = normalize(normalize(E)), F.normalize semantics: v / max(||v||, 1e-12).  One warp per row.
+// reference convex_loss.py:41,57
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) normalize_fwd_kernel(const float* __restrict__ E, int64_t rows, int d,
+                                                            float* __restrict__ X) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* e4 = reinterpret_cast<const float4*>(E + row * d);
+    float4* x4 = reinterpret_cast<float4*>(X + row * d);
+    const int nv = d >> 2;
+    float ss = 0.f;
+    for (int c = lane; c < nv; c += 32) {
+        float4 v = e4[c];
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    const float n0 = fmaxf(sqrtf(ss), 1e-12f);
+    float ss1 = 0.f;
+    for (int c = lane; c < nv; c += 32) {
+        float4 v = e4[c];
+        v.x /= n0; v.y /= n0; v.z /= n0; v.w /= n0;
+        ss1 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss1 = warp_sum(ss1);
+    const float n1 = fmaxf(sqrtf(ss1), 1e-12f);
+    for (int c = lane; c < nv; c += 32) {
+        float4 v = e4[c];
+        v.x = (v.x / n0) / n1; v.y = (v.y / n0) / n1; v.z = (v.z / n0) / n1; v.w = (v.w / n0) / n1;
+        x4[c] = v;
+    }
+}
+
+// backward of y = v / max(||v||, eps) applied twice: g1 = (g - x (x.g)) / n1 ; gE = (g1 - x1 (x1.g1)) / n0
+// (when the clamp is active, i.e. ||v|| < eps, the node is a plain division by eps.)
+__global__ void __launch_bounds__(256) normalize_bwd_kernel(const float* __restrict__ E, const float* __restrict__ gX,
+                                                            int64_t rows, int d, float* __restrict__ gE) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* e4 = reinterpret_cast<const float4*>(E + row * d);
+    const float4* g4 = reinterpret_cast<const float4*>(gX + row * d);
+    float4* o4 = reinterpret_cast<float4*>(gE + row * d);
+    const int nv = d >> 2;
+    float ss = 0.f;
+    for (int c = lane; c < nv; c += 32) {
+        float4 v = e4[c];
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    const float r0 = sqrtf(ss), n0 = fmaxf(r0, 1e-12f);
+    float ss1 = 0.f;
+    for (int c = lane; c < nv; c += 32) {
+        float4 v = e4[c];
+        v.x /= n0; v.y /= n0; v.z /= n0; v.w /= n0;
+        ss1 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss1 = warp_sum(ss1);
+    const float r1 = sqrtf(ss1), n1 = fmaxf(r1, 1e-12f);
+    // x.g with x = x1 / n1
+    float xg = 0.f;
+    for (int c = lane; c < nv; c += 32) {
+        float4 v = e4[c], g = g4[c];
+        xg += ((v.x / n0) / n1) * g.x + ((v.y / n0) / n1) * g.y + ((v.z / n0) / n1) * g.z + ((v.w / n0) / n1) * g.w;
+    }
+    xg = warp_sum(xg);
+    const bool proj1 = r1 >= 1e-12f, proj0 = r0 >= 1e-12f;
+    // x1.g1 where g1 = (g - x xg)/n1
+    float x1g1 = 0.f;
+    for (int c = lane; c < nv; c += 32) {
+        float4 v = e4[c], g = g4[c];
+        float x1[4] = {v.x / n0, v.y / n0, v.z / n0, v.w / n0};
+        float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float g1 = (gg[i] - (proj1 ? (x1[i] / n1) * xg : 0.f)) / n1;
+            x1g1 += x1[i] * g1;
+        }
+    }
+    x1g1 = warp_sum(x1g1);
+    for (int c = lane; c < nv; c += 32) {
+        float4 v = e4[c], g = g4[c];
+        float x1[4] = {v.x / n0, v.y / n0, v.z / n0, v.w / n0};
+        float gg[4] = {g.x, g.y, g.z, g.w};
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float g1 = (gg[i] - (proj1 ? (x1[i] / n1) * xg : 0.f)) / n1;
+            o[i] = (g1 - (proj0 ? x1[i] * x1g1 : 0.f)) / n0;
+        }
+        o4[c] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+extern "C" int prifit_normalize_fwd(const float* E, int64_t rows, int d, float* X, void* stream) {
+    PF_CHECK_ARG(E && X, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(rows > 0 && d > 0 && d % 4 == 0, PRIFIT_E_SHAPE, "rows > 0 and d % 4 == 0 required");
+    const int wpb = 8;
+    normalize_fwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, pf_stream(stream)>>>(E, rows, d, X);
+    PF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int prifit_normalize_bwd(const float* E, const float* gX, int64_t rows, int d, float* gE, void* stream) {
+    PF_CHECK_ARG(E && gX && gE, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(rows > 0 && d > 0 && d % 4 == 0, PRIFIT_E_SHAPE, "rows > 0 and d % 4 == 0 required");
+    const int wpb = 8;
+    normalize_bwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, pf_stream(stream)>>>(E, gX, rows, d, gE);
+    PF_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,376 @@
+// k5-k7 -- soft-membership weighted ellipsoid fit, one CTA per (shape, cluster), forward + backward.
+// reference src/ellipsoid_fitting.py:19-69 (weighted_ellipsoid_fitting), :119-141
+// (principal_axis_ellipsoid, mode "slow"), src/fitting_utils.py:67-139 (CustomSVD and its backward).
+//
+//   W = sum w ; c = sum w p / W ; q = p - c ; cov = sum w q q^T / W            (10 weighted moments)
+//   A = cov + 1e-4 mean(cov) R                                                  (R = host U[0,1) draw, :37-38)
+//   drop if sigma_0 / sigma_2 > 1e5 or anything is non-finite                   (:41-47, :52-69)
+//   (U, S, V) = svd(A);  if det(V) < 0: V[:,2] = -V[:,2]                        (:48, :133-135)
+//   t = (w q) V ; s_a = |max_j t_ja - min_j t_ja| / 2                           (:136-140)
+//
+// The three reductions read W[b,k,:] (contiguous) and P[b] (L2 resident); the 3x3 SVD is a one-sided
+// Jacobi iteration in fp64 on one thread (a few hundred flops), so its accuracy is not the limit.
+#include "common.cuh"
+
+namespace {
+
+constexpr int FIT_THREADS = 256;
+
+// ctx layout (floats)
+constexpr int CX_U = 0, CX_S = 9, CX_V = 12, CX_FLIP = 21, CX_W = 22, CX_C = 23, CX_COV = 26,
+              CX_AMAX = 35, CX_AMIN = 38, CX_SGN = 41;
+static_assert(CX_SGN + 3 <= PRIFIT_FIT_CTX, "ctx too small");
+
+// One-sided Jacobi SVD of a 3x3 matrix (row-major A): A = U diag(S) V^T, S descending.
+__device__ void svd3(const double* A, double* U, double* S, double* V) {
+    double G[3][3], Vm[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { G[i][j] = A[3 * i + j]; Vm[i][j] = i == j ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        bool rotated = false;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int i = 0; i < 3; ++i) { alpha += G[i][p] * G[i][p]; beta += G[i][q] * G[i][q]; gamma += G[i][p] * G[i][q]; }
+                if (fabs(gamma) > 1e-16 * sqrt(alpha * beta) && gamma != 0.0) {
+                    rotated = true;
+                    const double zeta = (beta - alpha) / (2.0 * gamma);
+                    const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                    for (int i = 0; i < 3; ++i) {
+                        const double gp = G[i][p], gq = G[i][q];
+                        G[i][p] = cs * gp - sn * gq; G[i][q] = sn * gp + cs * gq;
+                        const double vp = Vm[i][p], vq = Vm[i][q];
+                        Vm[i][p] = cs * vp - sn * vq; Vm[i][q] = sn * vp + cs * vq;
+                    }
+                }
+            }
+        if (!rotated) break;
+    }
+    double sv[3];
+    int ord[3] = {0, 1, 2};
+    for (int j = 0; j < 3; ++j) sv[j] = sqrt(G[0][j] * G[0][j] + G[1][j] * G[1][j] + G[2][j] * G[2][j]);
+    for (int a = 0; a < 2; ++a)
+        for (int bq = a + 1; bq < 3; ++bq)
+            if (sv[ord[bq]] > sv[ord[a]]) { int tmp = ord[a]; ord[a] = ord[bq]; ord[bq] = tmp; }
+    for (int j = 0; j < 3; ++j) {
+        const int o = ord[j];
+        S[j] = sv[o];
+        const double inv = sv[o] > 0 ? 1.0 / sv[o] : 0.0;
+        for (int i = 0; i < 3; ++i) { U[3 * i + j] = G[i][o] * inv; V[3 * i + j] = Vm[i][o]; }
+    }
+}
+
+__device__ __forceinline__ double det3(const double* M) {
+    return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+
+struct ArgVal { float v; int i; };
+__device__ __forceinline__ ArgVal arg_max2(ArgVal a, ArgVal b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
+__device__ __forceinline__ ArgVal arg_min2(ArgVal a, ArgVal b) { return (b.v < a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
+
+__global__ void __launch_bounds__(FIT_THREADS) fit_fwd_kernel(
+    const float* __restrict__ P, const float* __restrict__ Wt, const int32_t* __restrict__ K,
+    const float* __restrict__ noise, int N, int Kcap,
+    float* __restrict__ s_out, float* __restrict__ V_out, float* __restrict__ c_out,
+    uint8_t* __restrict__ valid_out, float* __restrict__ ctx_out) {
+    __shared__ float red[10 * 32];
+    __shared__ float vs[9];
+    __shared__ int ok_s;
+    __shared__ float av[8][6];
+    __shared__ int ai[8][6];
+    const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const size_t bk = (size_t)b * Kcap + k;
+    float* ctx = ctx_out + bk * PRIFIT_FIT_CTX;
+    if (k >= min(K[b], Kcap)) {
+        if (tid < 3) { s_out[bk * 3 + tid] = 0.f; c_out[bk * 3 + tid] = 0.f; }
+        if (tid < 9) V_out[bk * 9 + tid] = 0.f;
+        if (tid < PRIFIT_FIT_CTX) ctx[tid] = 0.f;
+        if (tid == 0) valid_out[bk] = 0;
+        return;
+    }
+    const float* w = Wt + bk * N;
+    const float* p = P + (size_t)b * N * 3;
+
+    // pass 1: W, sum w p
+    float m[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = tid; j < N; j += FIT_THREADS) {
+        const float wj = w[j];
+        m[0] += wj; m[1] += wj * p[3 * j]; m[2] += wj * p[3 * j + 1]; m[3] += wj * p[3 * j + 2];
+    }
+    block_sum<4>(m, red);
+    const float Wsum = m[0];
+    const float cx = m[1] / Wsum, cy = m[2] / Wsum, cz = m[3] / Wsum;
+
+    // pass 2: sum w q q^T
+    float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = tid; j < N; j += FIT_THREADS) {
+        const float wj = w[j];
+        const float qx = p[3 * j] - cx, qy = p[3 * j + 1] - cy, qz = p[3 * j + 2] - cz;
+        cv[0] += wj * qx * qx; cv[1] += wj * qx * qy; cv[2] += wj * qx * qz;
+        cv[3] += wj * qy * qy; cv[4] += wj * qy * qz; cv[5] += wj * qz * qz;
+    }
+    block_sum<6>(cv, red);
+
+    if (tid == 0) {
+        float cov[9] = {cv[0] / Wsum, cv[1] / Wsum, cv[2] / Wsum, cv[1] / Wsum, cv[3] / Wsum, cv[4] / Wsum,
+                        cv[2] / Wsum, cv[4] / Wsum, cv[5] / Wsum};
+        float mean = 0.f;
+        for (int i = 0; i < 9; ++i) mean += cov[i];
+        mean /= 9.0f;
+        const float* R = noise + bk * 9;
+        double A[9], U[9], S[3], V[9];
+        bool finite = true;
+        for (int i = 0; i < 9; ++i) {
+            const float a = cov[i] + (1e-4f * mean) * R[i];
+            finite = finite && isfinite(a);
+            A[i] = (double)a;
+        }
+        int ok = 0;
+        if (finite) {
+            svd3(A, U, S, V);
+            ok = !((float)S[0] / (float)S[2] > 1e5f) && S[2] > 0.0;
+        }
+        ok_s = ok;
+        if (ok) {
+            const bool flip = det3(V) < 0.0;
+            for (int i = 0; i < 9; ++i) { ctx[CX_U + i] = (float)U[i]; ctx[CX_V + i] = (float)V[i]; ctx[CX_COV + i] = cov[i]; }
+            for (int i = 0; i < 3; ++i) ctx[CX_S + i] = (float)S[i];
+            ctx[CX_FLIP] = flip ? 1.f : 0.f;
+            ctx[CX_W] = Wsum;
+            ctx[CX_C] = cx; ctx[CX_C + 1] = cy; ctx[CX_C + 2] = cz;
+            for (int i = 0; i < 9; ++i) {
+                const float v = (float)((flip && (i % 3) == 2) ? -V[i] : V[i]);
+                vs[i] = v;
+                V_out[bk * 9 + i] = v;
+            }
+            c_out[bk * 3] = cx; c_out[bk * 3 + 1] = cy; c_out[bk * 3 + 2] = cz;
+        } else {
+            for (int i = 0; i < 9; ++i) V_out[bk * 9 + i] = 0.f;
+            for (int i = 0; i < 3; ++i) { s_out[bk * 3 + i] = 0.f; c_out[bk * 3 + i] = 0.f; }
+            for (int i = 0; i < PRIFIT_FIT_CTX; ++i) ctx[i] = 0.f;
+        }
+        valid_out[bk] = (uint8_t)ok;
+    }
+    __syncthreads();
+    if (!ok_s) return;
+
+    // pass 3: extents of the weighted, rotated points
+    ArgVal hi[3], lo[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { hi[a].v = -INFINITY; hi[a].i = 0x7fffffff; lo[a].v = INFINITY; lo[a].i = 0x7fffffff; }
+    for (int j = tid; j < N; j += FIT_THREADS) {
+        const float wj = w[j];
+        const float rx = (p[3 * j] - cx) * wj, ry = (p[3 * j + 1] - cy) * wj, rz = (p[3 * j + 2] - cz) * wj;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float t = rx * vs[a] + ry * vs[3 + a] + rz * vs[6 + a];
+            if (t > hi[a].v) { hi[a].v = t; hi[a].i = j; }
+            if (t < lo[a].v) { lo[a].v = t; lo[a].i = j; }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ArgVal x, y;
+            x.v = __shfl_xor_sync(0xffffffffu, hi[a].v, o); x.i = __shfl_xor_sync(0xffffffffu, hi[a].i, o);
+            y.v = __shfl_xor_sync(0xffffffffu, lo[a].v, o); y.i = __shfl_xor_sync(0xffffffffu, lo[a].i, o);
+            hi[a] = arg_max2(hi[a], x);
+            lo[a] = arg_min2(lo[a], y);
+        }
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            av[tid >> 5][a] = hi[a].v; ai[tid >> 5][a] = hi[a].i;
+            av[tid >> 5][3 + a] = lo[a].v; ai[tid >> 5][3 + a] = lo[a].i;
+        }
+    }
+    __syncthreads();
+    if (tid < 3) {
+        ArgVal h, l;
+        h.v = av[0][tid]; h.i = ai[0][tid]; l.v = av[0][3 + tid]; l.i = ai[0][3 + tid];
+        for (int wq = 1; wq < FIT_THREADS / 32; ++wq) {
+            ArgVal x, y;
+            x.v = av[wq][tid]; x.i = ai[wq][tid]; y.v = av[wq][3 + tid]; y.i = ai[wq][3 + tid];
+            h = arg_max2(h, x);
+            l = arg_min2(l, y);
+        }
+        const float diff = h.v - l.v;
+        s_out[bk * 3 + tid] = fabsf(diff) / 2.0f;
+        ctx[CX_AMAX + tid] = __int_as_float(h.i);
+        ctx[CX_AMIN + tid] = __int_as_float(l.i);
+        ctx[CX_SGN + tid] = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(FIT_THREADS) fit_bwd_kernel(
+    const float* __restrict__ P, const float* __restrict__ Wt, const int32_t* __restrict__ K,
+    const float* __restrict__ noise, const float* __restrict__ ctx_in, const uint8_t* __restrict__ valid,
+    const float* __restrict__ gs, const float* __restrict__ gV, const float* __restrict__ gc,
+    int N, int Kcap, float* __restrict__ gW, float* __restrict__ gP) {
+    __shared__ float red[3 * 32];
+    __shared__ float dcov_s[9];     // dL/dcov
+    __shared__ float sym_s[9];      // dcov + dcov^T
+    __shared__ float sp_dr[6][3];   // sparse dL/dr at the arg-extreme points
+    __shared__ int sp_j[6];
+    __shared__ float misc[8];       // W, cx, cy, cz, cov:dcov
+    const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const size_t bk = (size_t)b * Kcap + k;
+    float* gw = gW + bk * N;
+    if (k >= min(K[b], Kcap) || !valid[bk]) {
+        for (int j = tid; j < N; j += FIT_THREADS) gw[j] = 0.f;
+        return;
+    }
+    const float* ctx = ctx_in + bk * PRIFIT_FIT_CTX;
+    const float* w = Wt + bk * N;
+    const float* p = P + (size_t)b * N * 3;
+
+    if (tid == 0) {
+        double U[9], S[3], V[9], Vo[9], cov[9];
+        for (int i = 0; i < 9; ++i) { U[i] = ctx[CX_U + i]; V[i] = ctx[CX_V + i]; cov[i] = ctx[CX_COV + i]; }
+        for (int i = 0; i < 3; ++i) S[i] = ctx[CX_S + i];
+        const bool flip = ctx[CX_FLIP] != 0.f;
+        const double Wsum = ctx[CX_W];
+        const double c[3] = {ctx[CX_C], ctx[CX_C + 1], ctx[CX_C + 2]};
+        for (int i = 0; i < 9; ++i) Vo[i] = (flip && (i % 3) == 2) ? -V[i] : V[i];
+        double gVt[9];
+        for (int i = 0; i < 9; ++i) gVt[i] = gV[bk * 9 + i];
+        // extents: s_a = |hi_a - lo_a| / 2, hi/lo = t at the arg-extreme points, t_ja = r_j . Vo[:,a], r = w q
+        for (int a = 0; a < 3; ++a) {
+            const double ghi = 0.5 * (double)ctx[CX_SGN + a] * (double)gs[bk * 3 + a];
+            const int jj[2] = {__float_as_int(ctx[CX_AMAX + a]), __float_as_int(ctx[CX_AMIN + a])};
+            const double gt[2] = {ghi, -ghi};
+            for (int e = 0; e < 2; ++e) {
+                const int j = jj[e];
+                const double wj = w[j];
+                const double r[3] = {((double)p[3 * j] - c[0]) * wj, ((double)p[3 * j + 1] - c[1]) * wj, ((double)p[3 * j + 2] - c[2]) * wj};
+                for (int i = 0; i < 3; ++i) {
+                    gVt[3 * i + a] += gt[e] * r[i];
+                    sp_dr[2 * a + e][i] = (float)(gt[e] * Vo[3 * i + a]);
+                }
+                sp_j[2 * a + e] = j;
+            }
+        }
+        if (flip) for (int i = 0; i < 3; ++i) gVt[3 * i + 2] = -gVt[3 * i + 2];
+        // CustomSVD backward (src/fitting_utils.py:67-105), grad_S = 0 in "slow" mode
+        double Kt[9];   // K^T
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double kij = 0.0;       // K[i][j]
+                if (i != j) {
+                    const double diff = S[i] - S[j];
+                    const double sg = diff > 0 ? 1.0 : (diff < 0 ? -1.0 : 0.0);
+                    const double kneg = sg * fmax(fabs(diff), 1e-6);
+                    kij = (1.0 / kneg) * (1.0 / (S[i] + S[j]));
+                }
+                Kt[3 * j + i] = kij;
+            }
+        double inner[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double vtg = 0.0;
+                for (int q = 0; q < 3; ++q) vtg += V[3 * q + i] * gVt[3 * q + j];
+                inner[3 * i + j] = Kt[3 * i + j] * vtg;
+            }
+        double symi[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) symi[3 * i + j] = 0.5 * (inner[3 * i + j] + inner[3 * j + i]);
+        double tmp[9], dA[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double acc = 0.0;
+                for (int q = 0; q < 3; ++q) acc += U[3 * i + q] * S[q] * symi[3 * q + j];
+                tmp[3 * i + j] = acc;
+            }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double acc = 0.0;
+                for (int q = 0; q < 3; ++q) acc += tmp[3 * i + q] * V[3 * j + q];
+                dA[3 * i + j] = 2.0 * acc;
+            }
+        // A = cov + 1e-4 mean(cov) R
+        const float* R = noise + bk * 9;
+        double rdot = 0.0;
+        for (int i = 0; i < 9; ++i) rdot += (double)R[i] * dA[i];
+        double cdot = 0.0;
+        for (int i = 0; i < 9; ++i) {
+            const double dc = dA[i] + 1e-4 * rdot / 9.0;
+            dcov_s[i] = (float)dc;
+            cdot += cov[i] * dc;
+        }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) sym_s[3 * i + j] = dcov_s[3 * i + j] + dcov_s[3 * j + i];
+        misc[0] = (float)Wsum; misc[1] = (float)c[0]; misc[2] = (float)c[1]; misc[3] = (float)c[2];
+        misc[4] = (float)cdot;
+    }
+    __syncthreads();
+    const float Wsum = misc[0], cx = misc[1], cy = misc[2], cz = misc[3], cdot = misc[4];
+    const float invW = 1.0f / Wsum;
+
+    // pass A: G = sum_j dL/dq_j
+    float G[3] = {0.f, 0.f, 0.f};
+    for (int j = tid; j < N; j += FIT_THREADS) {
+        const float wj = w[j];
+        const float q[3] = {p[3 * j] - cx, p[3 * j + 1] - cy, p[3 * j + 2] - cz};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float dq = wj * (sym_s[3 * i] * q[0] + sym_s[3 * i + 1] * q[1] + sym_s[3 * i + 2] * q[2]) * invW;
+#pragma unroll
+            for (int e = 0; e < 6; ++e)
+                if (sp_j[e] == j) dq += wj * sp_dr[e][i];
+            G[i] += dq;
+        }
+    }
+    block_sum<3>(G, red);
+    const float dc[3] = {gc[bk * 3] - G[0], gc[bk * 3 + 1] - G[1], gc[bk * 3 + 2] - G[2]};
+
+    // pass B: dL/dw_j (and optionally dL/dp_j)
+    for (int j = tid; j < N; j += FIT_THREADS) {
+        const float wj = w[j];
+        const float q[3] = {p[3 * j] - cx, p[3 * j + 1] - cy, p[3 * j + 2] - cz};
+        float quad = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            quad += q[i] * (dcov_s[3 * i] * q[0] + dcov_s[3 * i + 1] * q[1] + dcov_s[3 * i + 2] * q[2]);
+        float g = (quad - cdot) * invW + (q[0] * dc[0] + q[1] * dc[1] + q[2] * dc[2]) * invW;
+#pragma unroll
+        for (int e = 0; e < 6; ++e)
+            if (sp_j[e] == j) g += sp_dr[e][0] * q[0] + sp_dr[e][1] * q[1] + sp_dr[e][2] * q[2];
+        gw[j] = g;
+        if (gP) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                float dq = wj * (sym_s[3 * i] * q[0] + sym_s[3 * i + 1] * q[1] + sym_s[3 * i + 2] * q[2]) * invW;
+#pragma unroll
+                for (int e = 0; e < 6; ++e)
+                    if (sp_j[e] == j) dq += wj * sp_dr[e][i];
+                atomicAdd(gP + ((size_t)b * N + j) * 3 + i, dq + wj * invW * dc[i]);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int prifit_fit_fwd(const float* P, const float* W, const int32_t* K, const float* noise,
+                              int B, int N, int Kcap, float* s_out, float* V_out, float* c_out,
+                              uint8_t* valid_out, float* ctx_out, void* stream) {
+    PF_CHECK_ARG(P && W && K && noise && s_out && V_out && c_out && valid_out && ctx_out, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(B > 0 && N > 0 && Kcap > 0, PRIFIT_E_BADARG, "B, N, Kcap > 0 required");
+    fit_fwd_kernel<<<dim3(Kcap, B), FIT_THREADS, 0, pf_stream(stream)>>>(P, W, K, noise, N, Kcap, s_out, V_out, c_out, valid_out, ctx_out);
+    PF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int prifit_fit_bwd(const float* P, const float* W, const int32_t* K, const float* noise,
+                              const float* ctx, const uint8_t* valid, const float* gs, const float* gV, const float* gc,
+                              int B, int N, int Kcap, float* gW_out, float* gP_inout, void* stream) {
+    PF_CHECK_ARG(P && W && K && noise && ctx && valid && gs && gV && gc && gW_out, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(B > 0 && N > 0 && Kcap > 0, PRIFIT_E_BADARG, "B, N, Kcap > 0 required");
+    fit_bwd_kernel<<<dim3(Kcap, B), FIT_THREADS, 0, pf_stream(stream)>>>(P, W, K, noise, ctx, valid, gs, gV, gc, N, Kcap, gW_out, gP_inout);
+    PF_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,169 @@
+"""CPU: the C-ABI library loads and exports what include/prifit_b200.h declares; host-side logic;
+world_size-2 gloo run of the sharding helper.  No kernel is launched here."""
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from prifit_b200 import build, _lib
+
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from prifit_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "prifit_b200.h")).read()
+    declared = set(re.findall(r"\b(prifit_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.prifit_version() == 100
+    assert lib.prifit_last_error_string() is not None
+
+
+def test_bad_arguments_return_codes(lib):
+    """Argument validation happens before any CUDA call, so it is testable without a GPU."""
+    assert lib.prifit_normalize_fwd(None, 4, 128, None, None) == -1
+    assert lib.prifit_meanshift_fwd(None, None, 1, 16, 128, 1, None, 0, None, 0, None) == -1
+    assert lib.prifit_bandwidth_workspace_bytes(2, 100, 128, 100) == 2 * 100 * 4
+    assert lib.prifit_nms_workspace_bytes(1, 10, 128) == (4 * 10 + 64) * 4
+    assert b"null pointer" in lib.prifit_last_error_string()
+
+
+def test_ops_refuse_cpu_tensors(lib):
+    from prifit_b200 import _lib, ops
+
+    with pytest.raises(_lib.PrifitError):
+        ops.normalize_fwd(torch.randn(4, 128))
+
+
+def test_missing_library_is_loud(monkeypatch, tmp_path):
+    from prifit_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.PrifitError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_kcap_and_kth():
+    from prifit_b200 import _lib, ops, pipeline
+
+    assert ops.kcap_for(25) == 32 and ops.kcap_for(32) == 32 and ops.kcap_for(50) == 64
+    with pytest.raises(_lib.PrifitError):
+        ops.kcap_for(65)
+    assert pipeline._kth_tensor([0.05, 0.1], 2048, torch.device("cpu")).tolist() == [102, 204]
+    with pytest.raises(_lib.PrifitError):
+        pipeline._kth_tensor([1e-5], 2048, torch.device("cpu"))
+
+
+def test_noise_stream_matches_reference_order():
+    """One batched CPU draw == the reference's per-cluster torch.rand(3,3) calls (ellipsoid_fitting.py:38)."""
+    from prifit_b200 import pipeline
+
+    K_host = [3, 0, 2]
+    torch.manual_seed(5)
+    ours = pipeline.draw_noise(K_host, 4, torch.device("cpu"))
+    torch.manual_seed(5)
+    for b, k in enumerate(K_host):
+        for i in range(k):
+            assert torch.equal(ours[b, i], torch.rand(3, 3))
+    assert float(ours[1].abs().sum()) == 0.0
+
+
+def test_sample_rows_replays_host_shuffle():
+    from prifit_b200 import pipeline
+
+    np.random.seed(3)
+    rows = pipeline._sample_rows(2, 50, 20, torch.device("cpu"))
+    np.random.seed(3)
+    for b in range(2):
+        L = np.arange(50)
+        np.random.shuffle(L)
+        assert rows[b].tolist() == L[:20].tolist()
+    assert pipeline._sample_rows(2, 50, 50, torch.device("cpu")) is None
+
+
+def test_shard_range_partitions():
+    from prifit_b200 import dist as pdist
+
+    for n, w in [(192, 8), (24, 1), (10, 4), (3, 8)]:
+        spans = [pdist.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_synthetic_is_shard_invariant():
+    from prifit_b200 import synthetic
+
+    E, P, ids = synthetic.planted_shapes(4, n_points=64, n_clusters=4, seed=10)
+    E2, P2, _ = synthetic.planted_shapes(2, n_points=64, n_clusters=4, seed=12)
+    assert torch.equal(E[2:], E2) and torch.equal(P[2:], P2)
+    assert E.shape == (4, 64, 128) and P.shape == (4, 64, 3) and int(ids.max()) == 3
+
+
+def test_install_redirects_reference_imports():
+    import prifit_b200
+
+    saved = {k: sys.modules.get(k) for k in list(prifit_b200._MIRRORS) + ["src"]}
+    try:
+        prifit_b200.install()
+        from src.mean_shift import MeanShift
+        import convex_loss
+
+        assert MeanShift.__module__ == "prifit_b200.mean_shift"
+        assert convex_loss.convex_loss.__module__ == "prifit_b200.convex_loss"
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from prifit_b200 import dist as pdist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+loss_all = torch.tensor([0.5, 0.25, 2.0, 1.0, 4.0, 0.125], dtype=torch.float64)
+has_all = torch.tensor([1., 1., 0., 1., 1., 1.], dtype=torch.float64)
+lo, hi = pdist.shard_range(6, rank, 2)
+lb = loss_all[lo:hi].clone().requires_grad_(True)
+L, Lb = pdist.global_masked_mean(lb, has_all[lo:hi])
+Lb.backward()
+ref = (loss_all * has_all).sum() / has_all.sum()
+assert abs(float(L) - float(ref)) < 1e-12, (float(L), float(ref))
+assert torch.allclose(lb.grad, has_all[lo:hi] / has_all.sum()), lb.grad
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_global_mean_world_size_2_gloo(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out.decode()

@@ -1,0 +1,91 @@
+"""CPU: pins oracle/restatement.py against the fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py ran the reference's own functions in the build container)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import axes_close, label_map, rel_err
+from oracle import restatement as R
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def test_stage_vectors(golden_dir):
+    g = _load(golden_dir, "stages")
+    X = torch.from_numpy(g["X"])
+    perm = g["perm"]
+    bw = R.compute_bandwidth(X, 320, 0.05, perm=perm)
+    assert rel_err(bw, g["bw"]) < 1e-6
+    bw_sub = R.compute_bandwidth(X, 200, 0.1, perm=perm)
+    assert rel_err(bw_sub, g["bw_sub"]) < 1e-6
+    newX = R.mean_shift_iterations(X, torch.tensor(float(g["bw"])), 6)
+    assert rel_err(newX, g["newX"]) < 1e-5
+    _, ids, labels = R.nms(torch.from_numpy(g["newX"]), torch.from_numpy(g["newX"]), torch.tensor(float(g["bw"])))
+    assert ids.numpy().tolist() == g["ids"].tolist()
+    assert labels.numpy().tolist() == g["labels"].tolist()
+    mem = R.membership(torch.from_numpy(g["newX"])[ids], X, torch.tensor(float(g["bw"])))
+    assert rel_err(mem, g["membership"]) < 1e-5
+
+
+def test_custom_svd_backward(golden_dir):
+    g = _load(golden_dir, "svd_backward")
+    for i in range(g["A"].shape[0]):
+        A = torch.from_numpy(g["A"][i]).clone().requires_grad_(True)
+        U, S, V = R.customsvd(A)
+        (S * torch.from_numpy(g["gS"][i])).sum().add((V * torch.from_numpy(g["gV"][i])).sum()).backward()
+        denom = np.abs(g["gA"][i]).max()
+        assert np.abs(A.grad.numpy() - g["gA"][i]).max() <= 2e-3 * denom, i
+
+
+def test_fit_known_answer(golden_dir):
+    """fitting.py recipe: one-hot memberships on sampled ellipsoid surfaces return the planted semi-axes
+    (sorted by variance) and the all-zero membership columns are dropped."""
+    g = _load(golden_dir, "fit_kat")
+    P = torch.from_numpy(g["P"])
+    W = torch.from_numpy(g["W"][0]).T.contiguous()
+    params = R.weighted_ellipsoid_fitting_batch(P, [W], noise=torch.from_numpy(g["noise"]))
+    assert len(params[0]) == int(g["nfit"][0]) == 3
+    for k, (s, V, c) in enumerate(params[0]):
+        assert rel_err(s, g["s"][0, k]) < 1e-5
+        assert rel_err(c, g["c"][0, k]) < 1e-5
+        assert axes_close(V.numpy(), g["V"][0, k], 1e-4)[0]
+        assert np.allclose(s.numpy(), g["planted"][k], rtol=0.02)
+
+
+@pytest.mark.parametrize("name", ["planted_small", "guard_small", "random_small"])
+def test_pipeline_against_reference(golden_dir, name):
+    g = _load(golden_dir, name)
+    E, P = torch.from_numpy(g["E"]), torch.from_numpy(g["P"])
+    info = []
+    np.random.seed(7)      # make_golden's seed: same bandwidth shuffle -> same rounding -> same NMS representatives
+    out = R.fit_loss(E, P, float(g["quantile"]), int(g["iterations"]), int(g["max_num_clusters"]),
+                     noise=torch.from_numpy(g["noise"]), info=info)
+    assert [i["passes"] for i in info] == g["passes"].tolist()
+    assert rel_err([i["bw"] for i in info], g["bw32"]) < 1e-6
+    for b in range(E.shape[0]):
+        label_map(out["labels"][b].numpy(), g["labels32"][b])
+        assert len(out["params"][b]) == int(g["nfit32"][b])
+        for k, (s, V, c) in enumerate(out["params"][b]):
+            assert rel_err(s, g["s32"][b, k]) < 1e-4
+            assert rel_err(c, g["c32"][b, k]) < 1e-4
+            assert axes_close(V.detach().numpy(), g["V32"][b, k], 1e-3)[0]
+    assert rel_err(out["loss"], g["loss32"]) < 1e-5
+    scale = max(np.abs(g["grad64"]).max(), 1e-12)
+    if int(g["n_attempt"].max()) > 1:          # with a single cluster the membership is constant: zero gradient
+        assert np.abs(out["grad_E"].numpy() - g["grad32"]).max() <= 1e-3 * scale
+    else:
+        assert np.abs(out["grad_E"].numpy()).max() < 1e-6   # rounding residue of e / sum(e) with one cluster
+
+
+def test_oracle_fp64_matches_reference_fp64(golden_dir):
+    g = _load(golden_dir, "planted_small")
+    E, P = torch.from_numpy(g["E"]).double(), torch.from_numpy(g["P"]).double()
+    np.random.seed(7)
+    out = R.fit_loss(E, P, float(g["quantile"]), int(g["iterations"]), int(g["max_num_clusters"]),
+                     noise=torch.from_numpy(g["noise"]).double())
+    assert rel_err(out["loss"], g["loss64"]) < 1e-10
+    assert rel_err(out["grad_E"], g["grad64"]) < 1e-7
