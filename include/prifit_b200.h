@@ -127,6 +127,12 @@ int prifit_sdf_loss_bwd(const float* Q, const float* s, const float* V, const fl
                         const int32_t* K, const int32_t* argmin, const float* gloss, int B, int M, int Kcap,
                         float* gs_out, float* gV_out, float* gc_out, float* gQ_out, void* stream);
 
+/* diagnostics -- hardware self-test of the tcgen05 / TMA descriptor encodings the tensor-core engine
+ *   uses: D[128,128] = A . B^T (mode 0: B K-major in shared memory) or A . B (mode 1: B MN-major), A staged
+ *   in tensor memory, B fetched by TMA with SWIZZLE_128B; lbo/sbo = descriptor byte offsets under test. */
+int prifit_debug_tc_probe(const float* A, const float* Bm, int mode, int lbo_bytes, int sbo_bytes,
+                          float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
