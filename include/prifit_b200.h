@@ -37,7 +37,7 @@ extern "C" {
 #define PRIFIT_E_NODEVICE (-4)   /* no sm_100 device / driver entry point missing */
 
 /* mean-shift forward engines */
-#define PRIFIT_MS_TF32_TCGEN05 0 /* tensor cores: tcgen05.mma kind::tf32, TMEM accumulators, TMA */
+#define PRIFIT_MS_TF32_TCGEN05 0 /* tensor cores: tcgen05.mma kind::f16 (10-bit mantissa operands like tf32), TMEM, TMA */
 #define PRIFIT_MS_FP32_SIMT    1 /* CUDA-core fp32, used to cross-check the tensor-core kernel */
 
 int prifit_version(void);
@@ -129,9 +129,10 @@ int prifit_sdf_loss_bwd(const float* Q, const float* s, const float* V, const fl
 
 /* diagnostics -- hardware self-test of the tcgen05 / TMA descriptor encodings the tensor-core engine
  *   uses: D[128,128] = A . B^T (mode 0: B K-major in shared memory) or A . B (mode 1: B MN-major), A staged
- *   in tensor memory, B fetched by TMA with SWIZZLE_128B; lbo/sbo = descriptor byte offsets under test. */
+ *   in tensor memory, B fetched by TMA with SWIZZLE_128B; lbo/sbo = descriptor byte offsets under test.
+ *   Operands are rounded to fp16 like the engine's; ws >= 33 KB of device scratch. */
 int prifit_debug_tc_probe(const float* A, const float* Bm, int mode, int lbo_bytes, int sbo_bytes,
-                          float* D, void* stream);
+                          float* D, void* ws, void* stream);
 
 #ifdef __cplusplus
 }

@@ -3,24 +3,30 @@
 //
 // One CTA owns 128 seed rows of one shape for ALL T iterations (rows are independent given X), so a
 // single launch covers the whole stage and the N x N kernel matrix only ever exists as 128 x 128
-// tiles in tensor memory.  Per key tile (128 keys x 128 d, one 64 KB TMA transaction, 3-stage ring):
+// tiles in tensor memory.  Per key tile (128 keys x 128 d fp16 = 32 KB, one TMA transaction, ring):
 //
-//   GEMM1  S[128 x 128]  = Q[128 x d] . Xtile^T      A = Q in TMEM (tf32), B = Xtile in smem, K-major
-//   softmax warps        : S -> P = exp2((S - 1) log2e / bw^2)  clamped at e^-13, tf32-rounded (RN),
+//   GEMM1  S[128 x 128]  = Q[128 x d] . Xtile^T      A = Q in TMEM (f16 pairs), B = Xtile in smem, K-major
+//   softmax warps        : S -> P = 2^10 exp2((S - 1) log2e / bw^2), clamped at e^-13, rounded to f16 and
 //                          written back over S in TMEM (thread = row, no shared-memory round trip)
 //   GEMM2  O[128 x d]   += P[128 x 128] . Xtile      A = P in TMEM, B = the SAME smem tile, MN-major
 //
 // and per iteration the epilogue renormalises O row-wise (y' = O / ||O||: the 1/rowsum factor of the
-// reference cancels in the normalisation) and stores it as the next Q in TMEM.  TMEM columns:
-// S0|P0 [0,128)  S1|P1 [128,256)  O [256,384)  Q [384,512).
+// reference and the 2^10 scale both cancel in the normalisation) and stores it as the next Q in TMEM.
+// TMEM columns: S0|P0 [0,128)  S1|P1 [128,256)  O [256,384)  Q [384,448).
+//
+// Why kind::f16 and not kind::tf32: fp16 carries the same 10-bit mantissa as tf32 and every operand
+// here lives in [6e-5, 2^10] (unit vectors, weights pre-scaled by 2^10), so the rounding is the same;
+// but MN-major tf32 operands only exist in the SW128_32B shared-memory layout, which K-major operands
+// cannot use, so one tf32 tile could not feed both GEMMs.  fp16 uses SWIZZLE_128B in both majors,
+// halves the tile bytes and doubles the MMA rate.
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-7 = softmax / epilogue (one thread per seed row, one warp per TMEM lane quarter).
 //
-// Precision: kind::tf32 (10-bit mantissa operands, fp32 accumulate); X is pre-rounded to tf32 with
-// round-to-nearest, P and Q are rounded RN when written to TMEM.  This pass only feeds the NMS
-// (discrete outcome); the K centres that carry gradient are recomputed in fp32 (meanshift_rows.cu).
+// This pass only feeds the NMS (discrete outcome); the K centres that carry gradient are recomputed in
+// fp32 (meanshift_rows.cu).
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -31,12 +37,13 @@ namespace {
 constexpr int TC_D = 128;
 constexpr int TC_BM = 128;                 // seed rows per CTA
 constexpr int TC_BN = 128;                 // keys per tile
-constexpr int TC_STAGES = 3;
-constexpr uint32_t TC_TILE_BYTES = TC_BN * TC_D * 4;      // 65536
-constexpr uint32_t TC_KBLOCK_BYTES = TC_BN * 128;          // one 32-column (128 B) K-block of the tile
+constexpr int TC_STAGES = 5;
+constexpr uint32_t TC_TILE_BYTES = TC_BN * TC_D * 2;      // 32768
+constexpr uint32_t TC_KBLOCK_BYTES = TC_BN * 128;          // one 64-column (128 B) block of the tile
 constexpr int TC_THREADS = 256;
 constexpr uint32_t COL_S0 = 0, COL_O = 256, COL_Q = 384;
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float P_SCALE_LOG2 = 10.0f;      // weights are stored as 2^10 * kappa (keeps e^-13 a normal f16)
 
 struct TcBarriers {
     uint64_t x_full[TC_STAGES];
@@ -50,18 +57,16 @@ struct TcBarriers {
 
 constexpr size_t TC_SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)TC_STAGES * TC_TILE_BYTES + sizeof(TcBarriers);
 
-__global__ void round_tf32_kernel(const float4* __restrict__ in, float4* __restrict__ out, size_t n4) {
+__global__ void to_half_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t n4) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        float4 v = in[i];
-        v.x = __uint_as_float(to_tf32_rna(v.x)); v.y = __uint_as_float(to_tf32_rna(v.y));
-        v.z = __uint_as_float(to_tf32_rna(v.z)); v.w = __uint_as_float(to_tf32_rna(v.w));
-        out[i] = v;
+        const float4 v = in[i];
+        out[i] = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
     }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
-    const __grid_constant__ CUtensorMap tmap, const float* __restrict__ Xq /*tf32-rounded X*/,
-    const float* __restrict__ bw, int N, int T, float* __restrict__ newX) {
+    const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ Xh, const float* __restrict__ bw,
+    int N, int T, float* __restrict__ newX) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;
@@ -95,25 +100,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
                     mbar_wait(&bars->x_empty[st], ph ^ 1);
                     mbar_arrive_expect_tx(&bars->x_full[st], TC_TILE_BYTES);
                     const uint32_t dst = smem_u32(tiles + (size_t)st * TC_TILE_BYTES);
-#pragma unroll
-                    for (int kb = 0; kb < 4; ++kb)
-                        tma_load_3d(dst + kb * TC_KBLOCK_BYTES, &tmap, &bars->x_full[st], 32 * kb, j * TC_BN, b);
+                    tma_load_3d(dst, &tmap, &bars->x_full[st], 0, j * TC_BN, b);
+                    tma_load_3d(dst + TC_KBLOCK_BYTES, &tmap, &bars->x_full[st], 64, j * TC_BN, b);
                 }
         }
     } else if (warp == 1) {
         // ================================= MMA issuer =================================
         if (lane == 0) {
-            constexpr uint32_t idesc1 = idesc_tf32(TC_BM, TC_BN, false);   // S = Q . X^T   (B K-major)
-            constexpr uint32_t idesc2 = idesc_tf32(TC_BM, TC_D, true);     // O += P . X    (B MN-major)
+            constexpr uint32_t idesc1 = idesc_f16(TC_BM, TC_BN, false);   // S = Q . X^T   (B K-major)
+            constexpr uint32_t idesc2 = idesc_f16(TC_BM, TC_D, true);     // O += P . X    (B MN-major)
             auto gemm2 = [&](uint32_t i, bool first_of_iter) {
                 const uint32_t st = i % TC_STAGES, buf = i & 1, ph = (i >> 1) & 1;
                 mbar_wait(&bars->p_full[buf], ph);
                 tc_fence_after();
                 const uint32_t base = smem_u32(tiles + (size_t)st * TC_TILE_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < TC_BN / 8; ++kk) {
-                    const uint64_t bd = smem_desc_sw128(base + kk * 1024, TC_KBLOCK_BYTES, 1024);
-                    mma_tf32_ts(tmem + COL_O, tmem + COL_S0 + buf * 128 + kk * 8, bd, idesc2, !(first_of_iter && kk == 0));
+                for (int kk = 0; kk < TC_BN / 16; ++kk) {      // 16 keys per MMA = two 8-row groups, 1024 B apart
+                    const uint64_t bd = smem_desc_sw128(base + kk * 2048, TC_KBLOCK_BYTES, 1024);
+                    mma_f16_ts(tmem + COL_O, tmem + COL_S0 + buf * 128 + kk * 8, bd, idesc2, !(first_of_iter && kk == 0));
                 }
                 mma_commit(&bars->x_empty[st]);
             };
@@ -127,11 +131,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
                     tc_fence_after();
                     const uint32_t base = smem_u32(tiles + (size_t)st * TC_TILE_BYTES);
 #pragma unroll
-                    for (int kb = 0; kb < 4; ++kb)
+                    for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
+                        for (int ks = 0; ks < 4; ++ks) {      // 16 d-elements (32 B) per MMA
                             const uint64_t bd = smem_desc_sw128(base + kb * TC_KBLOCK_BYTES + ks * 32, 16, 1024);
-                            mma_tf32_ts(tmem + COL_S0 + buf * 128, tmem + COL_Q + kb * 32 + ks * 8, bd, idesc1, (kb | ks) != 0);
+                            mma_f16_ts(tmem + COL_S0 + buf * 128, tmem + COL_Q + kb * 32 + ks * 8, bd, idesc1, (kb | ks) != 0);
                         }
                     mma_commit(&bars->s_full[buf]);
                     if (j > 0) gemm2(it - 1, j == 1);
@@ -146,19 +150,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
         const uint32_t lane_base = (uint32_t)(32 * (warp - 4)) << 16;
         const bool row_ok = r0 + row < N;
         const float bwv = bw[b];
-        const float c1 = LOG2E / (bwv * bwv), c0 = -c1, lo2 = PRIFIT_LO * LOG2E;
-        uint32_t v[32];
-        // Q^0 = this tile's own rows of X
-        const float4* xrow = reinterpret_cast<const float4*>(Xq + ((size_t)b * N + (row_ok ? r0 + row : 0)) * TC_D);
+        const float c1 = LOG2E / (bwv * bwv), c0 = P_SCALE_LOG2 - c1, lo2 = PRIFIT_LO * LOG2E + P_SCALE_LOG2;
+        uint32_t v[32], h[16];
+        // Q^0 = this tile's own rows of X (already fp16: 256 B per row = 64 packed columns)
+        const uint4* xrow = reinterpret_cast<const uint4*>(Xh + ((size_t)b * N + (row_ok ? r0 + row : 0)) * TC_D);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float4 f = row_ok ? xrow[c * 8 + e] : make_float4(0.f, 0.f, 0.f, 0.f);
-                v[4 * e] = __float_as_uint(f.x); v[4 * e + 1] = __float_as_uint(f.y);
-                v[4 * e + 2] = __float_as_uint(f.z); v[4 * e + 3] = __float_as_uint(f.w);
+            for (int e = 0; e < 4; ++e) {
+                const uint4 f = row_ok ? xrow[c * 4 + e] : make_uint4(0u, 0u, 0u, 0u);
+                h[4 * e] = f.x; h[4 * e + 1] = f.y; h[4 * e + 2] = f.z; h[4 * e + 3] = f.w;
             }
-            tmem_st32(tmem + lane_base + COL_Q + 32 * c, v);
+            tmem_st16(tmem + lane_base + COL_Q + 16 * c, h);
         }
         tmem_wait_st();
         tc_fence_before();
@@ -177,12 +180,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
                     tmem_ld32(sbase + 32 * c, v);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        float p = ex2_approx(fmaxf(fmaf(__uint_as_float(v[e]), c1, c0), lo2));   // exp(clamp((s-1)/bw^2, -13, .))
-                        if (key0 + 32 * c + e >= N) p = 0.f;                                      // padded keys weigh nothing
-                        v[e] = to_tf32_rna(p);
+                    for (int e = 0; e < 16; ++e) {
+                        // 2^10 exp(clamp((s-1)/bw^2, -13, .)); padded keys weigh nothing
+                        float p0 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[2 * e]), c1, c0), lo2));
+                        float p1 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[2 * e + 1]), c1, c0), lo2));
+                        if (key0 + 32 * c + 2 * e >= N) p0 = 0.f;
+                        if (key0 + 32 * c + 2 * e + 1 >= N) p1 = 0.f;
+                        h[e] = pack_f16x2(p0, p1);
                     }
-                    tmem_st32(sbase + 32 * c, v);
+                    tmem_st16(sbase + 16 * c, h);               // P (packed) aliases the S columns already consumed
                 }
                 tmem_wait_st();
                 tc_fence_before();
@@ -215,8 +221,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = to_tf32_rna(__uint_as_float(v[e]) * inv);
-                    tmem_st32(tmem + lane_base + COL_Q + 32 * c, v);
+                    for (int e = 0; e < 16; ++e)
+                        h[e] = pack_f16x2(__uint_as_float(v[2 * e]) * inv, __uint_as_float(v[2 * e + 1]) * inv);
+                    tmem_st16(tmem + lane_base + COL_Q + 16 * c, h);
                 }
             }
             if (!last) {
@@ -233,8 +240,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
 
 // --------------------------------------------------------------------------------------------------
 // Descriptor self-test: D[128 x 128] = A . B^T (mode 0, B K-major) or A . B (mode 1, B MN-major) with
-// A staged in TMEM and B fetched by TMA exactly like the kernel above.  lbo/sbo are runtime values so
-// the encodings can be verified on hardware (tests/test_gpu_stages.py::test_tcgen05_probe).
+// A staged in TMEM (packed f16 pairs) and B fetched by TMA exactly like the kernel above.  lbo/sbo are
+// runtime values so the encodings can be verified on hardware (tests/test_gpu_tcgen05_probe.py).
 // --------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const __grid_constant__ CUtensorMap tmap,
                                                            const float* __restrict__ A, int mode, uint32_t lbo, uint32_t sbo,
@@ -253,12 +260,13 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const __grid_constant_
     const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(&bars[0], TC_TILE_BYTES);
-        for (int kb = 0; kb < 4; ++kb) tma_load_3d(smem_u32(smem) + kb * TC_KBLOCK_BYTES, &tmap, &bars[0], 32 * kb, 0, 0);
+        tma_load_3d(smem_u32(smem), &tmap, &bars[0], 0, 0, 0);
+        tma_load_3d(smem_u32(smem) + TC_KBLOCK_BYTES, &tmap, &bars[0], 64, 0, 0);
     }
-    uint32_t v[32];
+    uint32_t h[16], v[32];
     for (int c = 0; c < 4; ++c) {
-        for (int e = 0; e < 32; ++e) v[e] = to_tf32_rna(A[row * 128 + 32 * c + e]);
-        tmem_st32(tmem + lane_base + 128 + 32 * c, v);         // A at columns [128,256)
+        for (int e = 0; e < 16; ++e) h[e] = pack_f16x2(A[row * 128 + 32 * c + 2 * e], A[row * 128 + 32 * c + 2 * e + 1]);
+        tmem_st16(tmem + lane_base + 128 + 16 * c, h);         // A (packed) at columns [128,192)
     }
     tmem_wait_st();
     tc_fence_before();
@@ -268,10 +276,10 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const __grid_constant_
         mbar_wait(&bars[0], 0);
         tc_fence_after();
         const uint32_t base = smem_u32(smem);
-        const uint32_t idesc = idesc_tf32(128, 128, mode == 1);
-        for (int kk = 0; kk < 16; ++kk) {
-            const uint32_t addr = mode == 0 ? base + (kk >> 2) * TC_KBLOCK_BYTES + (kk & 3) * 32 : base + kk * 1024;
-            mma_tf32_ts(tmem, tmem + 128 + kk * 8, smem_desc_sw128(addr, lbo, sbo), idesc, kk != 0);
+        const uint32_t idesc = idesc_f16(128, 128, mode == 1);
+        for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t addr = mode == 0 ? base + (kk >> 2) * TC_KBLOCK_BYTES + (kk & 3) * 32 : base + kk * 2048;
+            mma_f16_ts(tmem, tmem + 128 + kk * 8, smem_desc_sw128(addr, lbo, sbo), idesc, kk != 0);
         }
         mma_commit(&bars[1]);
     }
@@ -299,54 +307,63 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-// 3-D map over X[B][N][128] fp32: box = 32 columns (128 B, SWIZZLE_128B) x 128 rows x 1 shape;
+// 3-D map over Xh[B][N][128] fp16: box = 64 columns (128 B, SWIZZLE_128B) x 128 rows x 1 shape;
 // rows beyond N are zero-filled by the TMA unit.
-int make_tile_map(CUtensorMap* map, const float* X, int B, int N) {
+int make_tile_map(CUtensorMap* map, const __half* X, int B, int N) {
     PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
     if (!enc) { prifit_set_error("cuTensorMapEncodeTiled driver entry point not available"); return PRIFIT_E_NODEVICE; }
     cuuint64_t dims[3] = {(cuuint64_t)TC_D, (cuuint64_t)N, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)TC_D * 4, (cuuint64_t)N * TC_D * 4};
-    cuuint32_t box[3] = {32, (cuuint32_t)TC_BN, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)TC_D * 2, (cuuint64_t)N * TC_D * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)TC_BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(X), dims, strides, box, estr,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(X), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { prifit_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return PRIFIT_E_BADARG; }
     return 0;
 }
 
-}  // namespace
-
-size_t prifit_meanshift_tc_workspace_bytes(int B, int N) { return (size_t)B * N * TC_D * sizeof(float) + 256; }
-
-int prifit_meanshift_fwd_tc(const float* X, const float* bw, int B, int N, int T, float* newX,
-                            void* ws, size_t ws_bytes, cudaStream_t st) {
-    (void)ws_bytes;
-    float* Xq = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-    const size_t n4 = (size_t)B * N * TC_D / 4;
-    round_tf32_kernel<<<(unsigned)min((size_t)148 * 8, (n4 + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Xq), n4);
-    PF_LAUNCH_CHECK();
-    if (T == 0) {
-        PF_CUDA(cudaMemcpyAsync(newX, X, (size_t)B * N * TC_D * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        return 0;
-    }
-    CUtensorMap map;
-    int rc = make_tile_map(&map, Xq, B, N);
-    if (rc) return rc;
-    PF_CUDA(cudaFuncSetAttribute(meanshift_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    dim3 grid((N + TC_BM - 1) / TC_BM, B);
-    meanshift_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map, Xq, bw, N, T, newX);
+int convert_to_half(const float* X, __half* Xh, size_t n, cudaStream_t st) {
+    const size_t n4 = n / 4;
+    to_half_kernel<<<(unsigned)min((size_t)148 * 8, (n4 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(X), reinterpret_cast<uint2*>(Xh), n4);
     PF_LAUNCH_CHECK();
     return 0;
 }
 
-// diagnostics: see tc_probe_kernel.  A[128,128], Bm[128,128], D[128,128] device fp32.
-extern "C" int prifit_debug_tc_probe(const float* A, const float* Bm, int mode, int lbo_bytes, int sbo_bytes,
-                                     float* D, void* stream) {
-    PF_CHECK_ARG(A && Bm && D, PRIFIT_E_BADARG, "null pointer");
+}  // namespace
+
+size_t prifit_meanshift_tc_workspace_bytes(int B, int N) { return (size_t)B * N * TC_D * sizeof(__half) + 256; }
+
+int prifit_meanshift_fwd_tc(const float* X, const float* bw, int B, int N, int T, float* newX,
+                            void* ws, size_t ws_bytes, cudaStream_t st) {
+    (void)ws_bytes;
+    if (T == 0) {
+        PF_CUDA(cudaMemcpyAsync(newX, X, (size_t)B * N * TC_D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    __half* Xh = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    int rc = convert_to_half(X, Xh, (size_t)B * N * TC_D, st);
+    if (rc) return rc;
     CUtensorMap map;
-    int rc = make_tile_map(&map, Bm, 1, 128);
+    rc = make_tile_map(&map, Xh, B, N);
+    if (rc) return rc;
+    PF_CUDA(cudaFuncSetAttribute(meanshift_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    dim3 grid((N + TC_BM - 1) / TC_BM, B);
+    meanshift_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map, Xh, bw, N, T, newX);
+    PF_LAUNCH_CHECK();
+    return 0;
+}
+
+// diagnostics: see tc_probe_kernel.  A[128,128], Bm[128,128], D[128,128] device fp32; ws >= 64 KB + 256.
+extern "C" int prifit_debug_tc_probe(const float* A, const float* Bm, int mode, int lbo_bytes, int sbo_bytes,
+                                     float* D, void* ws, void* stream) {
+    PF_CHECK_ARG(A && Bm && D && ws, PRIFIT_E_BADARG, "null pointer");
+    __half* Bh = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    int rc = convert_to_half(Bm, Bh, 128 * 128, pf_stream(stream));
+    if (rc) return rc;
+    CUtensorMap map;
+    rc = make_tile_map(&map, Bh, 1, 128);
     if (rc) return rc;
     const size_t smem = 1024 + TC_TILE_BYTES + 64;
     PF_CUDA(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

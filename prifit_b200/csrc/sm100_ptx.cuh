@@ -94,6 +94,21 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+// two fp32 -> packed f16x2 (round to nearest even); `lo` lands in bits [0,16), `hi` in bits [16,32)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------- MMA
 // Shared-memory matrix descriptor (tcgen05 "version 1"), SWIZZLE_128B.  Addresses / offsets in bytes.
 //   K-major  operand: rows of 128 B along K; 8-row groups SBO bytes apart (LBO unused, encoded 1).
@@ -116,6 +131,22 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool b_mn_major)
          | ((b_mn_major ? 1u : 0u) << 16)
          | ((uint32_t)(N >> 3) << 17)
          | ((uint32_t)(M >> 4) << 24);
+}
+// Instruction descriptor for kind::f16 with fp16 operands, fp32 accumulate, A K-major.
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool b_mn_major) {
+    return (1u << 4)                  // D format f32;  A/B format fields 0 = f16
+         | ((b_mn_major ? 1u : 0u) << 16)
+         | ((uint32_t)(N >> 3) << 17)
+         | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem, packed f16 pairs] * B[smem desc]
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem desc]
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
