@@ -207,13 +207,14 @@ def test_cfg2_engines_agree_and_match_oracle(cuda):
     gscale = float(ref["grad_E"].abs().max())
     assert rel_err(a["loss"], ref["loss"]) < 1e-4
     assert float((a["grad_E"].cpu().double() - ref["grad_E"]).abs().max()) / gscale < 2e-3
-    try:
-        t = _run(E, P, cuda, 0.05, 10, 25, noise=noise, engine=ops.MS_TF32_TCGEN05)
-    except _lib.PrifitError as e:
-        if "not built" in str(e):
-            pytest.skip("tcgen05 engine not built yet")
-        raise
-    assert np.array_equal(t["cluster"].labels.cpu().numpy(), labels)
+    # the tensor-core engine may pick other representatives of the same modes (cluster numbering is
+    # rounding-noise dependent): same partition, noise re-matched, same loss and gradient
+    t0 = _run(E, P, cuda, 0.05, 10, 25, engine=ops.MS_TF32_TCGEN05)
+    labels_t = t0["cluster"].labels.cpu().numpy()
+    for b in range(2):
+        label_map(labels_t[b], labels[b])
+    noise_t, _ = _matched_noise(labels_t, ref_labels, ref_noise, 32)
+    t = _run(E, P, cuda, 0.05, 10, 25, noise=noise_t, engine=ops.MS_TF32_TCGEN05)
     assert rel_err(t["loss"], a["loss"]) < 1e-5
     assert rel_err(t["grad_E"], a["grad_E"]) < 1e-4
 
