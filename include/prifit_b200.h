@@ -41,6 +41,9 @@ extern "C" {
 #define PRIFIT_MS_FP32_SIMT    1 /* CUDA-core fp32, used to cross-check the tensor-core kernel */
 
 int prifit_version(void);
+/* Engine of the Gram-matrix passes inside prifit_bandwidth_fwd and prifit_nms_fwd (process-global):
+ * 0 = tensor cores (tcgen05, d == 128), 1 = fp32 CUDA cores (cross-check).  Returns the previous value. */
+int prifit_set_gram_engine(int engine);
 const char* prifit_last_error_string(void);
 /* 1 if the current device is compute capability 10.x, else 0 (or <0 on error) */
 int prifit_device_ok(void);

@@ -16,6 +16,7 @@ _sz = ctypes.c_size_t
 # name -> (restype, argtypes); mirrors include/prifit_b200.h one to one
 SIGNATURES = {
     "prifit_version": (_i, []),
+    "prifit_set_gram_engine": (_i, [_i]),
     "prifit_last_error_string": (ctypes.c_char_p, []),
     "prifit_device_ok": (_i, []),
     "prifit_normalize_fwd": (_i, [_p, _i64, _i, _p, _p]),
@@ -76,8 +77,8 @@ def check(rc, what):
 
 # kernels (and memset nodes) each entry point enqueues; bench.py reports the sum as `gpu_launches`
 LAUNCHES = {
-    "prifit_normalize_fwd": 1, "prifit_normalize_bwd": 1, "prifit_bandwidth_fwd": 2, "prifit_meanshift_fwd": 1,
-    "prifit_nms_fwd": 8, "prifit_meanshift_rows_fwd": 1, "prifit_meanshift_rows_bwd": 1,
+    "prifit_normalize_fwd": 1, "prifit_normalize_bwd": 1, "prifit_bandwidth_fwd": 6, "prifit_meanshift_fwd": 1,
+    "prifit_nms_fwd": 10, "prifit_meanshift_rows_fwd": 1, "prifit_meanshift_rows_bwd": 1,
     "prifit_membership_fwd": 2, "prifit_membership_bwd": 1, "prifit_fit_fwd": 1, "prifit_fit_bwd": 1,
     "prifit_sdf_loss_fwd": 2, "prifit_sdf_loss_bwd": 1,
 }

@@ -12,6 +12,14 @@ void prifit_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static int g_gram_engine = 0;
+int prifit_gram_engine() { return g_gram_engine; }
+extern "C" int prifit_set_gram_engine(int engine) {
+    const int prev = g_gram_engine;
+    g_gram_engine = engine ? 1 : 0;
+    return prev;
+}
+
 extern "C" int prifit_version(void) { return PRIFIT_VERSION; }
 extern "C" const char* prifit_last_error_string(void) { return g_err; }
 

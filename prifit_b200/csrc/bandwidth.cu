@@ -5,7 +5,12 @@
 // in shared memory while the key rows stream through a 64-key tile, so the n_s x n_s matrix never
 // reaches HBM.  The k-th order statistic is an exact 4 x 8-bit radix select on order-preserving
 // integer keys (one warp per row), so the result does not depend on any sort's tie handling.
+#include <cuda_fp16.h>
 #include "common.cuh"
+
+int prifit_tc_bandwidth_rows(const float* X, int B, int N, const int32_t* kth, __half* Xh_ws, int2* rowinfo_ws,
+                             float* rowval, int32_t* overflow, cudaStream_t st);
+int prifit_gram_engine();
 
 namespace {
 
@@ -15,8 +20,9 @@ constexpr int BW_TILE = 64;  // keys per tile
 template <int R>
 __global__ void __launch_bounds__(BW_THREADS) bandwidth_rows_kernel(
     const float* __restrict__ X, int N, int d, const int32_t* __restrict__ rows, int n_s,
-    const int32_t* __restrict__ kth, float* __restrict__ rowval /*[B,n_s]*/) {
+    const int32_t* __restrict__ kth, float* __restrict__ rowval /*[B,n_s]*/, const int32_t* __restrict__ only_if) {
     extern __shared__ __align__(16) float smem[];
+    if (only_if && *only_if == 0) return;     // exact fallback of the tensor-core path: runs only on overflow
     const int ld = d + 4;
     float* dist = smem;                       // [R][n_s]
     float* ys = dist + (size_t)R * n_s;       // [R][ld]
@@ -152,11 +158,11 @@ size_t bw_smem_bytes(int R, int n_s, int d) {
 
 template <int R>
 int launch_rows(const float* X, int B, int N, int d, const int32_t* rows, int n_s, const int32_t* kth,
-                float* rowval, cudaStream_t st) {
+                float* rowval, const int32_t* only_if, cudaStream_t st) {
     const size_t smem = bw_smem_bytes(R, n_s, d);
     PF_CUDA(cudaFuncSetAttribute(bandwidth_rows_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((n_s + R - 1) / R, B);
-    bandwidth_rows_kernel<R><<<grid, BW_THREADS, smem, st>>>(X, N, d, rows, n_s, kth, rowval);
+    bandwidth_rows_kernel<R><<<grid, BW_THREADS, smem, st>>>(X, N, d, rows, n_s, kth, rowval, only_if);
     PF_LAUNCH_CHECK();
     return 0;
 }
@@ -164,8 +170,8 @@ int launch_rows(const float* X, int B, int N, int d, const int32_t* rows, int n_
 }  // namespace
 
 extern "C" size_t prifit_bandwidth_workspace_bytes(int B, int N, int d, int n_s) {
-    (void)N; (void)d;
-    return (size_t)B * (size_t)n_s * sizeof(float);
+    // row values | overflow flag | (tensor-core path) per-row (bin, count) | fp16 rows
+    return (size_t)B * (size_t)n_s * sizeof(float) + 256 + (size_t)B * N * sizeof(int2) + 256 + (size_t)B * N * d * 2;
 }
 
 extern "C" int prifit_bandwidth_fwd(const float* X, int B, int N, int d, const int32_t* rows, int n_s,
@@ -179,9 +185,22 @@ extern "C" int prifit_bandwidth_fwd(const float* X, int B, int N, int d, const i
     float* rowval = static_cast<float*>(ws);
     cudaStream_t st = pf_stream(stream);
     int rc;
-    if (bw_smem_bytes(16, n_s, d) <= limit) rc = launch_rows<16>(X, B, N, d, rows, n_s, kth, rowval, st);
-    else if (bw_smem_bytes(8, n_s, d) <= limit) rc = launch_rows<8>(X, B, N, d, rows, n_s, kth, rowval, st);
-    else if (bw_smem_bytes(4, n_s, d) <= limit) rc = launch_rows<4>(X, B, N, d, rows, n_s, kth, rowval, st);
+    const int32_t* only_if = nullptr;
+    if (!rows && d == 128 && N < 65536 && prifit_gram_engine() == 0) {
+        // tensor-core path (gram_tc.cu): histogram pass + candidate pass with exact fp32 refinement
+        uint8_t* p = static_cast<uint8_t*>(ws) + (size_t)B * n_s * sizeof(float);
+        int32_t* overflow = reinterpret_cast<int32_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
+        int2* rowinfo = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(overflow) + 255) & ~(uintptr_t)255);
+        __half* Xh = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(rowinfo + (size_t)B * N) + 255) & ~(uintptr_t)255);
+        PF_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int32_t), st));
+        rc = prifit_tc_bandwidth_rows(X, B, N, kth, Xh, rowinfo, rowval, overflow, st);
+        if (rc) return rc;
+        only_if = overflow;      // the exact CUDA-core kernel below re-does the batch only if a candidate list overflowed
+    }
+    if (bw_smem_bytes(16, n_s, d) <= limit) rc = launch_rows<16>(X, B, N, d, rows, n_s, kth, rowval, only_if, st);
+    else if (bw_smem_bytes(8, n_s, d) <= limit) rc = launch_rows<8>(X, B, N, d, rows, n_s, kth, rowval, only_if, st);
+    else if (bw_smem_bytes(4, n_s, d) <= limit) rc = launch_rows<4>(X, B, N, d, rows, n_s, kth, rowval, only_if, st);
+    else if (only_if) rc = 0;
     else { prifit_set_error("prifit_bandwidth_fwd: n_s=%d too large for the shared-memory row block", n_s); return PRIFIT_E_SHAPE; }
     if (rc) return rc;
     bandwidth_mean_kernel<<<B, 256, 0, st>>>(rowval, n_s, bw_out);

@@ -333,6 +333,10 @@ int convert_to_half(const float* X, __half* Xh, size_t n, cudaStream_t st) {
 
 }  // namespace
 
+// shared with gram_tc.cu
+int prifit_tc_convert_to_half(const float* X, __half* Xh, size_t n, cudaStream_t st) { return convert_to_half(X, Xh, n, st); }
+int prifit_tc_make_tile_map(CUtensorMap* map, const __half* X, int B, int N) { return make_tile_map(map, X, B, N); }
+
 size_t prifit_meanshift_tc_workspace_bytes(int B, int N) { return (size_t)B * N * TC_D * sizeof(__half) + 256; }
 
 int prifit_meanshift_fwd_tc(const float* X, const float* bw, int B, int N, int T, float* newX,

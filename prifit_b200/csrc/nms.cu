@@ -9,7 +9,14 @@
 // The reference needs a D2H copy + numpy for step 2; here nothing leaves the GPU.
 //
 // fp32 CUDA-core Gram tiles (row groups of 32 against a resident 128-key tile).
+#include <cuda.h>
+#include <cuda_fp16.h>
 #include "rowgemm.cuh"
+
+int prifit_tc_nms_nearest(const float* newX, int B, int N, __half* Xh_ws, CUtensorMap* map_out, int32_t* nearest, cudaStream_t st);
+int prifit_tc_nms_best(const CUtensorMap* map, const __half* Xh, const float* bw, const int32_t* votes, int B, int N,
+                       int32_t* best, cudaStream_t st);
+int prifit_gram_engine();
 
 namespace {
 
@@ -218,12 +225,25 @@ int launch_nms(const float* newX, const float* bw, int B, int N, int Kcap, int32
     PF_CUDA(cudaFuncSetAttribute(nms_label_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PF_CUDA(cudaMemsetAsync(w.votes, 0, (2 * (size_t)B * N + (size_t)B * 64) * sizeof(int32_t), st));
     dim3 gt((N + RG_KEYS - 1) / RG_KEYS, B), ge((N + 255) / 256, B);
-    nms_gram_kernel<D, 0><<<gt, RG_THREADS, smem, st>>>(newX, bw, N, nullptr, w.nearest);
-    PF_LAUNCH_CHECK();
+    const bool tc = D == 128 && prifit_gram_engine() == 0;      // Gram passes on the tensor cores (gram_tc.cu)
+    __half* Xh = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(w.best + (size_t)B * N) + 255) & ~(uintptr_t)255);
+    CUtensorMap map;
+    if (tc) {
+        int rc = prifit_tc_nms_nearest(newX, B, N, Xh, &map, w.nearest, st);
+        if (rc) return rc;
+    } else {
+        nms_gram_kernel<D, 0><<<gt, RG_THREADS, smem, st>>>(newX, bw, N, nullptr, w.nearest);
+        PF_LAUNCH_CHECK();
+    }
     nms_vote_kernel<<<ge, 256, 0, st>>>(w.nearest, N, w.votes);
     PF_LAUNCH_CHECK();
-    nms_gram_kernel<D, 1><<<gt, RG_THREADS, smem, st>>>(newX, bw, N, w.votes, w.best);
-    PF_LAUNCH_CHECK();
+    if (tc) {
+        int rc = prifit_tc_nms_best(&map, Xh, bw, w.votes, B, N, w.best, st);
+        if (rc) return rc;
+    } else {
+        nms_gram_kernel<D, 1><<<gt, RG_THREADS, smem, st>>>(newX, bw, N, w.votes, w.best);
+        PF_LAUNCH_CHECK();
+    }
     nms_flag_kernel<<<ge, 256, 0, st>>>(w.votes, w.best, N, w.flags);
     PF_LAUNCH_CHECK();
     nms_compact_kernel<<<B, 1024, 0, st>>>(w.flags, N, Kcap, idx_out, K_out);
@@ -238,8 +258,7 @@ int launch_nms(const float* newX, const float* bw, int B, int N, int Kcap, int32
 }  // namespace
 
 extern "C" size_t prifit_nms_workspace_bytes(int B, int N, int d) {
-    (void)d;
-    return (4 * (size_t)B * N + (size_t)B * 64) * sizeof(int32_t);
+    return (4 * (size_t)B * N + (size_t)B * 64) * sizeof(int32_t) + 256 + (size_t)B * N * d * 2 /* fp16 rows for the tensor-core Gram */;
 }
 
 extern "C" int prifit_nms_fwd(const float* newX, const float* bw, int B, int N, int d, int Kcap,

@@ -391,3 +391,59 @@ def test_sdf_loss_no_ellipsoid(cuda):
     valid = torch.zeros(1, 32, dtype=torch.uint8, device=cuda)
     loss, argmin, _ = ops.sdf_fwd(Q, z3, z9, z3, valid, torch.tensor([0], dtype=torch.int32, device=cuda))
     assert float(loss[0]) == 0.0 and (argmin == -1).all()
+
+
+# ------------------------------------------------------- tensor-core Gram engine vs fp32 CUDA-core engine
+def _with_gram_engine(engine, fn):
+    from prifit_b200 import _lib
+
+    prev = _lib.load().prifit_set_gram_engine(engine)
+    try:
+        return fn()
+    finally:
+        _lib.load().prifit_set_gram_engine(prev)
+
+
+@pytest.mark.parametrize("n,q", [(2048, 0.05), (1000, 0.1), (320, 0.05), (10000, 0.05)])
+def test_bandwidth_tensor_core_is_exact(cuda, n, q):
+    """The tcgen05 histogram + candidate passes return the exact fp32 order statistic: bit-for-bit the
+    value of the CUDA-core kernel up to the summation order of the 128-term dot products (1e-6)."""
+    from prifit_b200 import ops, synthetic
+
+    E, _, _ = synthetic.planted_shapes(2, n_points=n, n_clusters=8, seed=91)
+    X = torch.cat([R.normalize_twice(E), _unit(n, 128, 92)[None]]).to(cuda)      # planted + random rows
+    k = torch.full((3,), int(q * n), dtype=torch.int32, device=cuda)
+    a = _with_gram_engine(1, lambda: ops.bandwidth(X, k))
+    b = _with_gram_engine(0, lambda: ops.bandwidth(X, k))
+    assert rel_err(b, a) < 1e-6
+    ref = [float(R.compute_bandwidth(X[i].cpu(), n, q, perm=np.arange(n))) for i in (0, 2)]
+    assert rel_err(b[[0, 2]], ref) < 2e-6
+
+
+def test_bandwidth_tensor_core_duplicates_fall_back(cuda):
+    """All points identical: every distance lands in one bin, the candidate lists overflow and the exact
+    CUDA-core kernel takes over on the device (no host round trip)."""
+    from prifit_b200 import ops
+
+    X = _unit(1, 128, 93).repeat(600, 1)[None].to(cuda)
+    k = torch.tensor([30], dtype=torch.int32, device=cuda)
+    a = _with_gram_engine(1, lambda: ops.bandwidth(X, k))
+    b = _with_gram_engine(0, lambda: ops.bandwidth(X, k))
+    assert torch.equal(a, b) and float(b[0]) == pytest.approx(1e-3, rel=1e-5)     # sqrt(clamp(~0, 1e-6))
+
+
+@pytest.mark.parametrize("n,kc", [(2048, 16), (1000, 7), (10000, 40)])
+def test_nms_tensor_core_matches_fp32(cuda, n, kc):
+    from prifit_b200 import ops, synthetic
+
+    E, _, planted = synthetic.planted_shapes(2, n_points=n, n_clusters=kc, seed=95)
+    X = R.normalize_twice(E).to(cuda)
+    q = 0.05 if kc <= 16 else 0.01
+    bw = ops.bandwidth(X, torch.full((2,), int(q * n), dtype=torch.int32, device=cuda))
+    newX = ops.meanshift(X, bw, 10, ops.MS_FP32_SIMT)
+    ia, Ka, la, na = _with_gram_engine(1, lambda: ops.nms(newX, bw, 64))
+    ib, Kb, lb, nb = _with_gram_engine(0, lambda: ops.nms(newX, bw, 64))
+    assert Ka.tolist() == Kb.tolist() == [kc, kc] and na.tolist() == nb.tolist()
+    for b in range(2):
+        label_map(lb[b].cpu().numpy(), la[b].cpu().numpy())
+        label_map(lb[b].cpu().numpy(), planted[b].numpy())

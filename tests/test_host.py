@@ -38,8 +38,9 @@ def test_bad_arguments_return_codes(lib):
     """Argument validation happens before any CUDA call, so it is testable without a GPU."""
     assert lib.prifit_normalize_fwd(None, 4, 128, None, None) == -1
     assert lib.prifit_meanshift_fwd(None, None, 1, 16, 128, 1, None, 0, None, 0, None) == -1
-    assert lib.prifit_bandwidth_workspace_bytes(2, 100, 128, 100) == 2 * 100 * 4
-    assert lib.prifit_nms_workspace_bytes(1, 10, 128) == (4 * 10 + 64) * 4
+    assert lib.prifit_bandwidth_workspace_bytes(2, 100, 128, 100) >= 2 * 100 * 4 + 2 * 100 * 128 * 2
+    assert lib.prifit_nms_workspace_bytes(1, 10, 128) >= (4 * 10 + 64) * 4 + 10 * 128 * 2
+    assert lib.prifit_set_gram_engine(1) == 0 and lib.prifit_set_gram_engine(0) == 1
     assert b"null pointer" in lib.prifit_last_error_string()
 
 
