@@ -171,7 +171,7 @@ int launch_rows(const float* X, int B, int N, int d, const int32_t* rows, int n_
 
 extern "C" size_t prifit_bandwidth_workspace_bytes(int B, int N, int d, int n_s) {
     // row values | overflow flag | (tensor-core path) per-row (bin, count) | fp16 rows
-    return (size_t)B * (size_t)n_s * sizeof(float) + 256 + (size_t)B * N * sizeof(int2) + 256 + (size_t)B * N * d * 2;
+    return (size_t)B * (size_t)n_s * sizeof(float) + 512 + (size_t)B * N * sizeof(int2) + 512 + (size_t)B * N * d * 2;
 }
 
 extern "C" int prifit_bandwidth_fwd(const float* X, int B, int N, int d, const int32_t* rows, int n_s,
@@ -190,7 +190,7 @@ extern "C" int prifit_bandwidth_fwd(const float* X, int B, int N, int d, const i
         // tensor-core path (gram_tc.cu): histogram pass + candidate pass with exact fp32 refinement
         uint8_t* p = static_cast<uint8_t*>(ws) + (size_t)B * n_s * sizeof(float);
         int32_t* overflow = reinterpret_cast<int32_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
-        int2* rowinfo = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(overflow) + 255) & ~(uintptr_t)255);
+        int2* rowinfo = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(overflow) + 16 + 255) & ~(uintptr_t)255);
         __half* Xh = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(rowinfo + (size_t)B * N) + 255) & ~(uintptr_t)255);
         PF_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int32_t), st));
         rc = prifit_tc_bandwidth_rows(X, B, N, kth, Xh, rowinfo, rowval, overflow, st);

@@ -160,7 +160,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
         uint16_t* cand = reinterpret_cast<uint16_t*>(scratch) + (size_t)row * CAND_CAP;  // COLLECT: own row
         float win_lo = 0.f, win_hi = 0.f;
         int below = 0, ncand = 0;
-        if (MODE == GM_BEST) bwv = a.bw[b];
+        float vnext = 0.f;
+        if (MODE == GM_BEST) {
+            bwv = a.bw[b];
+            vnext = row < N ? (float)a.votes[(size_t)b * N + row] : 0.f;
+        }
         if (MODE == GM_HIST) {
             uint32_t* hw = reinterpret_cast<uint32_t*>(hist);
             for (int q = 0; q < HIST_BINS / 2; ++q) hw[q] = 0u;
@@ -175,9 +179,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
             const uint32_t buf = j & 1, ph = (j >> 1) & 1;
             const int key0 = j * G_BN;
             if (MODE == GM_BEST) {
-                const int col = key0 + row;
-                vt[buf * 128 + row] = col < N ? (float)a.votes[(size_t)b * N + col] : 0.f;
+                vt[buf * 128 + row] = vnext;                  // votes of this tile's columns (prefetched)
                 epi_barrier();
+                const int col = key0 + G_BN + row;            // prefetch the next tile's votes
+                vnext = col < N ? (float)a.votes[(size_t)b * N + col] : 0.f;
             }
             mbar_wait(&bars->s_full[buf], ph);
             tc_fence_after();
@@ -190,15 +195,32 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                 for (int e = 0; e < 32; ++e) {
                     const int cl = 32 * c + e;
                     const float dist = fmaf(-2.0f, __uint_as_float(v[e]), 2.0f);        // 2.0 - 2.0 * s
-                    if (cl < ncols) {
+                    if (MODE == GM_HIST) {
+                        // groups of four counter updates with their loads in flight together; equal bins
+                        // inside a group are forwarded in registers (stores stay in program order)
+                        if ((e & 3) == 3) {
+                            int bn[4], inc[4], cnt[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float du = fmaf(-2.0f, __uint_as_float(v[e - 3 + u]), 2.0f);
+                                bn[u] = min(max((int)(du * HIST_SCALE), 0), HIST_BINS - 1);
+                                inc[u] = (cl - 3 + u) < ncols ? 1 : 0;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) cnt[u] = hist[bn[u]];
+                            cnt[0] += inc[0];
+                            cnt[1] = (bn[1] == bn[0] ? cnt[0] : cnt[1]) + inc[1];
+                            cnt[2] = (bn[2] == bn[1] ? cnt[1] : bn[2] == bn[0] ? cnt[0] : cnt[2]) + inc[2];
+                            cnt[3] = (bn[3] == bn[2] ? cnt[2] : bn[3] == bn[1] ? cnt[1] : bn[3] == bn[0] ? cnt[0] : cnt[3]) + inc[3];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) hist[bn[u]] = (uint16_t)cnt[u];
+                        }
+                    } else if (cl < ncols) {
                         if (MODE == GM_NEAREST) {
                             if (dist < best) { best = dist; besti = key0 + cl; }
                         } else if (MODE == GM_BEST) {
                             const float val = dist < bwv ? vt[buf * 128 + cl] : 0.f;
                             if (val > best) { best = val; besti = key0 + cl; }
-                        } else if (MODE == GM_HIST) {
-                            const int bin = min(max((int)(dist * HIST_SCALE), 0), HIST_BINS - 1);
-                            hist[bin] = (uint16_t)(hist[bin] + 1);
                         } else {
                             below += dist < win_lo ? 1 : 0;
                             if (dist >= win_lo && dist <= win_hi) {
@@ -244,18 +266,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                     if (lane == 0) { atomicExch(a.overflow, 1); a.rowval[(size_t)b * N + r0 + r] = 0.f; }
                     continue;
                 }
-                const float4* xr = reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + r0 + r) * G_D);
+                // the whole warp works on one candidate at a time: lane l owns dims 4l..4l+3, so every
+                // candidate row is one coalesced 512-byte request (4 candidates in flight per step)
+                const float4 xr = __ldg(reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + r0 + r) * G_D) + lane);
                 const uint16_t* cr = reinterpret_cast<const uint16_t*>(scratch) + (size_t)r * CAND_CAP;
-                for (int ci = lane; ci < nc; ci += 32) {
-                    const float4* xc = reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + cr[ci]) * G_D);
-                    float acc = 0.f;
-#pragma unroll 8
-                    for (int q = 0; q < G_D / 4; ++q) {
-                        const float4 p = __ldg(xr + q), w = __ldg(xc + q);
-                        acc = fmaf(p.x, w.x, acc); acc = fmaf(p.y, w.y, acc);
-                        acc = fmaf(p.z, w.z, acc); acc = fmaf(p.w, w.w, acc);
+                for (int c0 = 0; c0 < nc; c0 += 4) {
+                    float acc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ci = min(c0 + u, nc - 1);
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + cr[ci]) * G_D) + lane);
+                        acc[u] = fmaf(xr.x, w.x, fmaf(xr.y, w.y, fmaf(xr.z, w.z, xr.w * w.w)));
                     }
-                    vals[ci] = 2.0f - 2.0f * acc;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
+                    if (lane < 4 && c0 + lane < nc)
+                        vals[c0 + lane] = 2.0f - 2.0f * (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]);
                 }
                 __syncwarp();
                 float found = 0.f;

@@ -78,7 +78,20 @@ def bandwidth(X, kth, rows=None):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=X.device)
     bw = torch.empty(B, dtype=torch.float32, device=X.device)
     _lib.call("prifit_bandwidth_fwd", _ptr(X), B, N, d, _ptr(rows), n_s, _ptr(kth), _ptr(bw), _ptr(ws), nbytes, _stream())
+    global _last_bandwidth_ws
+    _last_bandwidth_ws = (ws, B * n_s * 4)
     return bw
+
+
+_last_bandwidth_ws = None
+
+
+def last_bandwidth_fell_back():
+    """Diagnostics for the tests: did the tensor-core candidate pass of the last bandwidth() call overflow
+    (and the exact CUDA-core kernel re-do the batch)?  Reads the flag word that follows the row values."""
+    ws, off = _last_bandwidth_ws
+    off = (ws.data_ptr() + off + 15) // 16 * 16 - ws.data_ptr()
+    return bool(ws[off:off + 4].view(torch.int32).item())
 
 
 def meanshift(X, bw, iterations, engine=None):
