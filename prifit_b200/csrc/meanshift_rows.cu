@@ -21,9 +21,7 @@ struct RowsSmem {
     static constexpr int LD = D + 4;
     static constexpr size_t fwd_floats = (size_t)RG_ROWS * LD        // ys
                                        + (size_t)RG_KEYS * LD        // xs
-                                       + (size_t)RG_ROWS * RG_LDP    // ps
-                                       + (size_t)RG_ROWS * D         // part_o
-                                       + (size_t)RG_ROWS * D         // urow
+                                       + (size_t)RG_ROWS * RG_LDP    // ps   (part_o and urow alias xs)
                                        + RG_ROWS                     // part_z
                                        + RG_THREADS;                 // red
     static constexpr size_t bwd_floats = (size_t)3 * RG_ROWS * LD    // ys, gms, gy
@@ -35,7 +33,7 @@ struct RowsSmem {
 
 // ------------------------------------------------------------------------------------------ forward
 template <int D>
-__global__ void __launch_bounds__(RG_THREADS) ms_rows_fwd_kernel(
+__global__ void __launch_bounds__(RG_THREADS, 2) ms_rows_fwd_kernel(
     const float* __restrict__ X, const float* __restrict__ bw, const int32_t* __restrict__ idx,
     const int32_t* __restrict__ K, int N, int T, int Kcap,
     float* __restrict__ traj, float* __restrict__ stat, float* __restrict__ C_out) {
@@ -70,9 +68,9 @@ __global__ void __launch_bounds__(RG_THREADS) ms_rows_fwd_kernel(
     float* ys = smem;
     float* xs = ys + RG_ROWS * LD;
     float* ps = xs + RG_KEYS * LD;
-    float* part_o = ps + RG_ROWS * RG_LDP;
-    float* urow = part_o + RG_ROWS * D;
-    float* part_z = urow + RG_ROWS * D;
+    float* part_o = xs;                       // the key tile is dead once the tile loop is done (2 CTAs / SM)
+    float* urow = xs + RG_ROWS * D;
+    float* part_z = ps + RG_ROWS * RG_LDP;
     float* red = part_z + RG_ROWS;
 
     const float* Xb = X + (size_t)b * N * D;
@@ -124,6 +122,7 @@ __global__ void __launch_bounds__(RG_THREADS) ms_rows_fwd_kernel(
             __syncthreads();
             rg_accum_rows<D>(ps, xs, o);
         }
+        __syncthreads();                              // every warp is done with xs before part_o overwrites it
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
 #pragma unroll
