@@ -137,6 +137,12 @@ int prifit_sdf_loss_bwd(const float* Q, const float* s, const float* V, const fl
 int prifit_debug_tc_probe(const float* A, const float* Bm, int mode, int lbo_bytes, int sbo_bytes,
                           float* D, void* ws, void* stream);
 
+/* diagnostics -- the distance matrix 2 - 2 X X^T exactly as the tensor-core Gram engine sees it
+ *   (split-fp16 operands, three tcgen05.mma per 16 elements, fp32 accumulate, clamped to [0, 4)):
+ *   dist_out[B,N,N]; d = 128; ws >= 4 * B * N * 128 + 256 bytes.  Used by the tests to bound the
+ *   engine's error against the margin of the bandwidth candidate pass. */
+int prifit_debug_tc_gram(const float* X, int B, int N, float* dist_out, void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ SIGNATURES = {
     "prifit_sdf_loss_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "prifit_sdf_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "prifit_debug_tc_probe": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "prifit_debug_tc_gram": (_i, [_p, _i, _i, _p, _p, _p]),
 }
 
 FIT_CTX = 48

@@ -8,8 +8,9 @@
 #include <cuda_fp16.h>
 #include "common.cuh"
 
-int prifit_tc_bandwidth_rows(const float* X, int B, int N, const int32_t* kth, __half* Xh_ws, int2* rowinfo_ws,
+int prifit_tc_bandwidth_rows(const float* X, int B, int N, const int32_t* kth, __half* Xs_ws, int2* rowinfo_ws,
                              float* rowval, int32_t* overflow, cudaStream_t st);
+size_t prifit_tc_gram_split_bytes(int B, int N);
 int prifit_gram_engine();
 
 namespace {
@@ -170,8 +171,9 @@ int launch_rows(const float* X, int B, int N, int d, const int32_t* rows, int n_
 }  // namespace
 
 extern "C" size_t prifit_bandwidth_workspace_bytes(int B, int N, int d, int n_s) {
-    // row values | overflow flag | (tensor-core path) per-row (bin, count) | fp16 rows
-    return (size_t)B * (size_t)n_s * sizeof(float) + 512 + (size_t)B * N * sizeof(int2) + 512 + (size_t)B * N * d * 2;
+    // row values | overflow flag | (tensor-core path) per-row (window, rank) | split fp16 rows (hi + lo)
+    return (size_t)B * (size_t)n_s * sizeof(float) + 512 + (size_t)B * N * sizeof(int2) + 512 +
+           (d == 128 ? prifit_tc_gram_split_bytes(B, N) : 0);
 }
 
 extern "C" int prifit_bandwidth_fwd(const float* X, int B, int N, int d, const int32_t* rows, int n_s,
@@ -187,7 +189,7 @@ extern "C" int prifit_bandwidth_fwd(const float* X, int B, int N, int d, const i
     int rc;
     const int32_t* only_if = nullptr;
     if (!rows && d == 128 && N < 65536 && prifit_gram_engine() == 0) {
-        // tensor-core path (gram_tc.cu): histogram pass + candidate pass with exact fp32 refinement
+        // tensor-core path (gram_tc.cu): two histogram passes + candidate pass with exact fp32 refinement
         uint8_t* p = static_cast<uint8_t*>(ws) + (size_t)B * n_s * sizeof(float);
         int32_t* overflow = reinterpret_cast<int32_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
         int2* rowinfo = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(overflow) + 16 + 255) & ~(uintptr_t)255);

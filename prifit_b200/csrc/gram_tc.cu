@@ -2,24 +2,37 @@
 //
 //   NEAREST  nearest[i] = argmin_j (2 - 2 <x_i, x_j>)                       NMS step 1, src/mean_shift.py:169-172
 //   BEST     best[i]    = argmax_j ([2 - 2 <x_i, x_j> < bw] * votes[j])     NMS step 3, src/mean_shift.py:187-194
-//   HIST     per-row 512-bin histogram of 2 - 2 <x_i, x_j>  -> bin holding the k-th smallest    } bandwidth,
-//   COLLECT  candidates inside that bin (+- a rigorous fp16 error margin), EXACT fp32 recompute  } src/mean_shift.py:153-158
-//            of just those, exact k-th order statistic, sqrt(max(., 1e-6))
+//            (only for the rows i that received votes -- the reference indexes nbrs[uniques] too)
+//   HIST     per-row 256-bin histogram of the distances inside the row's current window      } bandwidth,
+//            -> narrower window holding the k-th smallest (two levels: 1/64, then 1/16384)     } src/mean_shift.py:153-158
+//   COLLECT  candidates inside the final window (+- margin), EXACT fp32 recompute of just    }
+//            those, exact k-th order statistic, sqrt(max(., 1e-6))
+//   DUMP     the distance matrix itself (tests only)
 //
 // (the Gram matrix is symmetric and the products commute bit-for-bit, so the reference's column-wise
 // arg-reductions equal these row-wise ones, lowest index on ties.)
 //
-// Same skeleton as meanshift_tc.cu: a CTA owns 128 rows (A operand = its rows as packed f16 in TMEM),
-// streams every 128-key tile of the shape through a TMA ring (B operand, K-major, SWIZZLE_128B),
-// 8 x tcgen05.mma.kind::f16 (M128 N128 K16) per tile into a double-buffered S accumulator, and the
-// four epilogue warps (thread = row = TMEM lane) consume S straight from tensor memory.  The n x n
-// matrix never exists outside TMEM.
+// Precision.  fp16 operands alone would put an error of 2^-9 on every distance, which is what decides
+// threshold tests and the order statistic.  Every row is therefore split into two fp16 vectors,
+//      x * 2^8 = hi + lo,   hi = fp16(x * 2^8),   lo = fp16(x * 2^8 - hi)          (22 significant bits)
+// and the dot product is accumulated in fp32 by THREE tcgen05.mma.kind::f16 per 16 d-elements:
+//      2^16 <a, b>  ~=  lo_a.hi_b + hi_a.lo_b + hi_a.hi_b                           (|error| < ~1e-6 on <a,b>)
+// The 2^8 pre-scale keeps `lo` a normal fp16 for every element that matters.  The tensor pipe has so
+// much headroom here (the epilogues bound these kernels) that the 3x MMA work is free.
 //
-// Exactness of the bandwidth: fp16 operands bound the error of every distance by eps = 2^-9
-// (|d a.b| <= 2^-10 ||a|| ||b||).  HIST finds the bin of the k-th smallest fp16-distance; the true k-th
-// smallest lies within eps of it; COLLECT keeps every element within 2 eps of the bin, counts the
-// elements below, recomputes the kept ones in fp32 and ranks them -- so the result is the exact fp32
-// order statistic, independent of the fp16 rounding.
+// Skeleton: a CTA owns 128 rows (A operands = its rows' hi | lo halves as packed f16 in TMEM), streams
+// every 128-key tile of the shape through a TMA ring (B operands hi + lo, K-major, SWIZZLE_128B, 64 KB
+// per stage), 24 MMAs (M128 N128 K16) per tile into a double-buffered S accumulator, and EIGHT epilogue
+// warps (two per SM sub-partition: thread = (row, 64-column half)) consume S straight from tensor
+// memory.  The n x n matrix never exists outside TMEM.
+//
+// Exactness of the bandwidth.  The histogram levels partition the tensor-core distances exactly (the
+// MMA sequence is deterministic, bin edges are exact in fp32), so after two levels the k-th smallest
+// tensor-core distance is known to lie in a window of width 2^-14.  Its fp32 counterpart lies within
+// BW_MARGIN/2 of it; COLLECT keeps every element within BW_MARGIN of the window, counts the elements
+// below, recomputes the kept ones with fp32 FMAs and ranks them -- the result is the exact fp32 order
+// statistic, independent of the tensor-core rounding.  Rows with too many candidates (massive
+// duplicates) raise the overflow flag and the exact CUDA-core kernel (bandwidth.cu) redoes the batch.
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -27,69 +40,88 @@
 
 using namespace sm100;
 
-int prifit_tc_convert_to_half(const float* X, __half* Xh, size_t n, cudaStream_t st);
 int prifit_tc_make_tile_map(CUtensorMap* map, const __half* X, int B, int N);
 
 namespace {
 
-constexpr int G_D = 128, G_BM = 128, G_BN = 128, G_THREADS = 256;
-constexpr uint32_t G_TILE_BYTES = G_BN * G_D * 2;        // 32 KB
-constexpr uint32_t G_KBLOCK = G_BN * 128;
-constexpr uint32_t GCOL_Q = 256;
-enum { GM_NEAREST = 0, GM_BEST = 1, GM_HIST = 2, GM_COLLECT = 3 };
+constexpr int G_D = 128, G_BM = 128, G_BN = 128;
+constexpr int G_THREADS = 384;                           // warps 0-2: TMA / MMA / TMEM alloc; warps 4-11: epilogue
+constexpr int G_EPI = 256;                               // epilogue threads
+constexpr int G_STAGES = 2;
+constexpr uint32_t G_HALF_BYTES = G_BN * G_D * 2;        // one fp16 tile (hi or lo): 32 KB
+constexpr uint32_t G_STAGE_BYTES = 2 * G_HALF_BYTES;     // hi + lo
+constexpr uint32_t G_KBLOCK = G_BN * 128;                // one 64-column (128 B) block of a tile
+constexpr uint32_t GCOL_QHI = 256, GCOL_QLO = 320;
+constexpr float G_PRESCALE = 256.0f;                     // operands carry x * 2^8  ->  S = 2^16 <a, b>
+constexpr float G_DIST_MUL = -2.0f / 65536.0f;
+constexpr float G_DIST_MAX = 3.9999998f;                 // largest float below 4
+enum { GM_NEAREST = 0, GM_BEST = 1, GM_HIST = 2, GM_COLLECT = 3, GM_DUMP = 4 };
 
-constexpr int HIST_BINS = 512;                 // over [0, 4]: 128 bins per unit
-constexpr float HIST_SCALE = 128.0f;
-constexpr int HIST_STRIDE = HIST_BINS * 2 + 4; // bytes per row (odd number of words: conflict-free)
-constexpr float BW_MARGIN = 2.0f * 0.001953125f;   // 2 eps, eps = 2^-9
-constexpr int CAND_CAP = 256;
+constexpr int HIST_BINS = 256;
+constexpr int HIST_WORDS = HIST_BINS / 2 + 1;            // packed uint16 pairs; odd word stride: conflict-free rows
+constexpr float HIST_SCALE0 = 64.0f;                     // level 0: bins of 1/64 over [0, 4)
+constexpr float HIST_SCALE1 = 64.0f * 256.0f;            // level 1: bins of 2^-14 inside the level-0 bin
+constexpr float BW_MARGIN = 2.0e-5f;                     // >= 2 x the bound on |tensor-core - fp32| distance
+constexpr int CAND_HALF = 64;                            // candidates per (row, column half)
 
 template <int MODE> struct GCfg {
-    static constexpr int stages = MODE == GM_HIST ? 2 : 3;
-    static constexpr size_t scratch = MODE == GM_BEST ? 2 * 128 * sizeof(float)
-                                    : MODE == GM_HIST ? (size_t)G_BM * HIST_STRIDE
-                                    : MODE == GM_COLLECT ? (size_t)G_BM * CAND_CAP * 2 + 4 * CAND_CAP * sizeof(float) + 2 * G_BM * sizeof(int)
-                                    : 16;
-    static constexpr size_t smem = 1024 + (size_t)stages * G_TILE_BYTES + 256 + scratch;
+    static constexpr size_t scratch =
+        MODE == GM_NEAREST ? (size_t)G_BM * 8
+      : MODE == GM_BEST ? (size_t)G_BM * 8 + 2 * G_BN * sizeof(float)
+      : MODE == GM_HIST ? (size_t)G_BM * HIST_WORDS * 4
+      : MODE == GM_COLLECT ? (size_t)G_EPI * CAND_HALF * 2 + 8 * 2 * CAND_HALF * sizeof(float) + 2 * G_EPI * sizeof(int)
+      : 16;
+    static constexpr size_t smem = 1024 + (size_t)G_STAGES * G_STAGE_BYTES + 256 + scratch;
 };
 
 struct GBars {
-    uint64_t x_full[3], x_empty[3], s_full[2], s_free[2], q_full;
+    uint64_t x_full[G_STAGES], x_empty[G_STAGES], s_full[2], s_free[2], q_full;
     uint32_t tmem_base;
 };
 
 struct GramArgs {
-    const __half* Xh;        // [B,N,128] fp16 rows (A and B operands)
+    const __half* Xs;        // [2B,N,128] split rows: shapes [0,B) = hi, [B,2B) = lo   (A and B operands)
     const float* X32;        // [B,N,128] fp32 rows (COLLECT: exact recompute)
     const float* bw;         // [B]       (BEST)
     const int32_t* votes;    // [B,N]     (BEST)
+    const int32_t* rowsel;   // [B,N]     (BEST) compacted list of the rows to process, ascending
+    const int32_t* nrows;    // [B]       (BEST) length of that list
     const int32_t* kth;      // [B]       (HIST / COLLECT), 1-based rank
     int32_t* out_idx;        // [B,N]     (NEAREST / BEST)
-    int2* rowinfo;           // [B,N]     (HIST out, COLLECT in): (bin, count below the bin)
+    int2* rowinfo;           // [B,N]     (HIST in/out, COLLECT in): (window start as float bits, remaining rank)
     float* rowval;           // [B,N]     (COLLECT out)
     int32_t* overflow;       // [1]       (COLLECT out): candidate list overflow / window miss
-    int N;
+    float* dump;             // [B,N,N]   (DUMP out)
+    int N, B, level;
 };
 
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ float tc_dist(uint32_t sbits) {
+    // 2.0 - 2.0 * <a, b>, clamped to [0, 4): the same expression in every pass, so bins are consistent
+    return fminf(fmaxf(fmaf(__uint_as_float(sbits), G_DIST_MUL, 2.0f), 0.0f), G_DIST_MAX);
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
-    constexpr int STAGES = GCfg<MODE>::stages;
+    const int b = blockIdx.y, r0 = blockIdx.x * G_BM, N = a.N;
+    int nsel = N;                                              // rows this shape contributes (BEST: voted rows only)
+    if (MODE == GM_BEST) nsel = a.nrows[b];
+    if (r0 >= nsel) return;                                    // uniform over the CTA, before any barrier / allocation
+
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;
-    GBars* bars = reinterpret_cast<GBars*>(smem + (size_t)STAGES * G_TILE_BYTES);
-    uint8_t* scratch = smem + (size_t)STAGES * G_TILE_BYTES + 256;
+    GBars* bars = reinterpret_cast<GBars*>(smem + (size_t)G_STAGES * G_STAGE_BYTES);
+    uint8_t* scratch = smem + (size_t)G_STAGES * G_STAGE_BYTES + 256;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y, r0 = blockIdx.x * G_BM, N = a.N;
     const int nt = (N + G_BN - 1) / G_BN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->x_full[s], 1); mbar_init(&bars->x_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars->s_full[s], 1); mbar_init(&bars->s_free[s], 128); }
-        mbar_init(&bars->q_full, 128);
+        for (int s = 0; s < G_STAGES; ++s) { mbar_init(&bars->x_full[s], 1); mbar_init(&bars->x_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars->s_full[s], 1); mbar_init(&bars->s_free[s], G_EPI); }
+        mbar_init(&bars->q_full, G_EPI);
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) prefetch_tensormap(&tmap);
@@ -100,182 +132,225 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
     const uint32_t tmem = bars->tmem_base;
 
     if (warp == 0) {
+        // ================================ TMA producer ================================
         if (lane == 0) {
             for (int j = 0; j < nt; ++j) {
-                const uint32_t st = j % STAGES, ph = (j / STAGES) & 1;
+                const uint32_t st = j % G_STAGES, ph = (j / G_STAGES) & 1;
                 mbar_wait(&bars->x_empty[st], ph ^ 1);
-                mbar_arrive_expect_tx(&bars->x_full[st], G_TILE_BYTES);
-                const uint32_t dst = smem_u32(tiles + (size_t)st * G_TILE_BYTES);
+                mbar_arrive_expect_tx(&bars->x_full[st], G_STAGE_BYTES);
+                const uint32_t dst = smem_u32(tiles + (size_t)st * G_STAGE_BYTES);
                 tma_load_3d(dst, &tmap, &bars->x_full[st], 0, j * G_BN, b);
                 tma_load_3d(dst + G_KBLOCK, &tmap, &bars->x_full[st], 64, j * G_BN, b);
+                tma_load_3d(dst + G_HALF_BYTES, &tmap, &bars->x_full[st], 0, j * G_BN, a.B + b);
+                tma_load_3d(dst + G_HALF_BYTES + G_KBLOCK, &tmap, &bars->x_full[st], 64, j * G_BN, a.B + b);
             }
         }
     } else if (warp == 1) {
+        // ================================= MMA issuer =================================
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_f16(G_BM, G_BN, false);
             mbar_wait(&bars->q_full, 0);
             tc_fence_after();
             for (int j = 0; j < nt; ++j) {
-                const uint32_t st = j % STAGES, xph = (j / STAGES) & 1, buf = j & 1;
+                const uint32_t st = j % G_STAGES, xph = (j / G_STAGES) & 1, buf = j & 1;
                 mbar_wait(&bars->x_full[st], xph);
                 mbar_wait(&bars->s_free[buf], ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t base = smem_u32(tiles + (size_t)st * G_TILE_BYTES);
+                const uint32_t base = smem_u32(tiles + (size_t)st * G_STAGE_BYTES);
+                const uint32_t acc = tmem + buf * 128;
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_f16_ts(tmem + buf * 128, tmem + GCOL_Q + kb * 32 + ks * 8,
-                                   smem_desc_sw128(base + kb * G_KBLOCK + ks * 32, 16, 1024), idesc, (kb | ks) != 0);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t qo = kb * 32 + ks * 8;
+                        const uint64_t bhi = smem_desc_sw128(base + kb * G_KBLOCK + ks * 32, 16, 1024);
+                        const uint64_t blo = smem_desc_sw128(base + G_HALF_BYTES + kb * G_KBLOCK + ks * 32, 16, 1024);
+                        mma_f16_ts(acc, tmem + GCOL_QLO + qo, bhi, idesc, (kb | ks) != 0);
+                        mma_f16_ts(acc, tmem + GCOL_QHI + qo, blo, idesc, true);
+                        mma_f16_ts(acc, tmem + GCOL_QHI + qo, bhi, idesc, true);
+                    }
                 mma_commit(&bars->s_full[buf]);
                 mma_commit(&bars->x_empty[st]);
             }
         }
     } else if (warp >= 4) {
-        const int row = threadIdx.x - 128, ew = warp - 4;
-        const uint32_t lane_base = (uint32_t)(32 * ew) << 16;
-        const bool row_ok = r0 + row < N;
-        const size_t grow = (size_t)b * N + (row_ok ? r0 + row : 0);
-        uint32_t v[32], h[16];
-        const uint4* xrow = reinterpret_cast<const uint4*>(a.Xh + grow * G_D);
+        // ================================== epilogue ==================================
+        const int et = threadIdx.x - 128;                        // 0..255
+        const int ew = warp - 4;                                 // 0..7
+        const int half = ew >> 2;                                // column half of every tile this thread owns
+        const int row = 32 * (ew & 3) + lane;                    // TMEM lane == row within the CTA tile
+        const uint32_t lane_base = (uint32_t)(32 * (ew & 3)) << 16;
+        const bool row_ok = r0 + row < nsel;
+        int grow_i = row_ok ? r0 + row : 0;                      // row index inside the shape
+        if (MODE == GM_BEST) grow_i = row_ok ? a.rowsel[(size_t)b * N + r0 + row] : 0;
+        const size_t grow = (size_t)b * N + grow_i;
+
+        // ---- A operands: this thread's 64-element half of the row, hi and lo, into tensor memory
+        {
+            uint32_t h[16];
+            const uint4* xhi = reinterpret_cast<const uint4*>(a.Xs + grow * G_D) + 8 * half;
+            const uint4* xlo = reinterpret_cast<const uint4*>(a.Xs + ((size_t)a.B * N + grow) * G_D) + 8 * half;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+            for (int part = 0; part < 2; ++part) {
+                const uint4* src = part == 0 ? xhi : xlo;
+                const uint32_t col = (part == 0 ? GCOL_QHI : GCOL_QLO) + 32 * half;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const uint4 f = row_ok ? xrow[c * 4 + e] : make_uint4(0u, 0u, 0u, 0u);
-                h[4 * e] = f.x; h[4 * e + 1] = f.y; h[4 * e + 2] = f.z; h[4 * e + 3] = f.w;
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint4 f = row_ok ? src[c * 4 + e] : make_uint4(0u, 0u, 0u, 0u);
+                        h[4 * e] = f.x; h[4 * e + 1] = f.y; h[4 * e + 2] = f.z; h[4 * e + 3] = f.w;
+                    }
+                    tmem_st16(tmem + lane_base + col + 16 * c, h);
+                }
             }
-            tmem_st16(tmem + lane_base + GCOL_Q + 16 * c, h);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bars->q_full);
         }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&bars->q_full);
 
         // ---- per-mode state
         float best = MODE == GM_NEAREST ? INFINITY : -1.0f;
-        int besti = 0;
+        int besti = 0x7fffffff;
         float bwv = 0.f;
-        float* vt = reinterpret_cast<float*>(scratch);                                   // BEST: [2][128]
-        uint16_t* hist = reinterpret_cast<uint16_t*>(scratch + (size_t)row * HIST_STRIDE);   // HIST: own row
-        uint16_t* cand = reinterpret_cast<uint16_t*>(scratch) + (size_t)row * CAND_CAP;  // COLLECT: own row
-        float win_lo = 0.f, win_hi = 0.f;
-        int below = 0, ncand = 0;
+        float* cmb_v = reinterpret_cast<float*>(scratch);                                  // NEAREST/BEST: [128]
+        int* cmb_i = reinterpret_cast<int*>(scratch) + G_BM;                               //               [128]
+        float* vt = reinterpret_cast<float*>(scratch + (size_t)G_BM * 8);                  // BEST: [2][128]
+        uint32_t* hist = reinterpret_cast<uint32_t*>(scratch) + (size_t)row * HIST_WORDS;  // HIST: own row
+        uint16_t* cand = reinterpret_cast<uint16_t*>(scratch) + (size_t)(row * 2 + half) * CAND_HALF;   // COLLECT
+        float win_lo = 0.f, win_hi = 0.f, hscale = HIST_SCALE0;
+        int below = 0, ncand = 0, krem = 1;
         float vnext = 0.f;
         if (MODE == GM_BEST) {
             bwv = a.bw[b];
-            vnext = row < N ? (float)a.votes[(size_t)b * N + row] : 0.f;
+            vnext = et < G_BN && et < N ? (float)a.votes[(size_t)b * N + et] : 0.f;
         }
         if (MODE == GM_HIST) {
-            uint32_t* hw = reinterpret_cast<uint32_t*>(hist);
-            for (int q = 0; q < HIST_BINS / 2; ++q) hw[q] = 0u;
+            for (int q = half; q < HIST_WORDS; q += 2) hist[q] = 0u;
+            krem = max(1, min(a.kth[b], N));
+            if (a.level > 0 && row_ok) {
+                const int2 ri = a.rowinfo[grow];
+                win_lo = __int_as_float(ri.x);
+                krem = ri.y;
+                hscale = HIST_SCALE1;
+            }
+            epi_barrier();
         }
-        if (MODE == GM_COLLECT) {
-            const int2 ri = a.rowinfo[grow];
-            win_lo = (float)ri.x / HIST_SCALE - BW_MARGIN;
-            win_hi = (float)(ri.x + 1) / HIST_SCALE + BW_MARGIN;
+        if (MODE == GM_COLLECT && row_ok) {
+            const float lo2 = __int_as_float(a.rowinfo[grow].x);
+            win_lo = lo2 - BW_MARGIN;
+            win_hi = lo2 + 1.0f / HIST_SCALE1 + BW_MARGIN;
         }
 
         for (int j = 0; j < nt; ++j) {
             const uint32_t buf = j & 1, ph = (j >> 1) & 1;
             const int key0 = j * G_BN;
             if (MODE == GM_BEST) {
-                vt[buf * 128 + row] = vnext;                  // votes of this tile's columns (prefetched)
+                if (et < G_BN) vt[buf * G_BN + et] = vnext;          // votes of this tile's columns (prefetched)
                 epi_barrier();
-                const int col = key0 + G_BN + row;            // prefetch the next tile's votes
-                vnext = col < N ? (float)a.votes[(size_t)b * N + col] : 0.f;
+                const int col = key0 + G_BN + et;                    // prefetch the next tile's votes
+                vnext = et < G_BN && col < N ? (float)a.votes[(size_t)b * N + col] : 0.f;
             }
             mbar_wait(&bars->s_full[buf], ph);
             tc_fence_after();
-            const int ncols = min(G_BN, N - key0);
+            uint32_t v[2][32];
+            tmem_ld32(tmem + lane_base + buf * 128 + 64 * half, v[0]);
+            tmem_ld32(tmem + lane_base + buf * 128 + 64 * half + 32, v[1]);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(&bars->s_free[buf]);                         // S is in registers: the MMA warp may refill it
+            const int ncols = min(G_BN, N - key0) - 64 * half;       // valid columns among this thread's 64
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_ld32(tmem + lane_base + buf * 128 + 32 * c, v);
-                tmem_wait_ld();
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
-                    const int cl = 32 * c + e;
-                    const float dist = fmaf(-2.0f, __uint_as_float(v[e]), 2.0f);        // 2.0 - 2.0 * s
-                    if (MODE == GM_HIST) {
-                        // groups of four counter updates with their loads in flight together; equal bins
-                        // inside a group are forwarded in registers (stores stay in program order)
-                        if ((e & 3) == 3) {
-                            int bn[4], inc[4], cnt[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float du = fmaf(-2.0f, __uint_as_float(v[e - 3 + u]), 2.0f);
-                                bn[u] = min(max((int)(du * HIST_SCALE), 0), HIST_BINS - 1);
-                                inc[u] = (cl - 3 + u) < ncols ? 1 : 0;
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) cnt[u] = hist[bn[u]];
-                            cnt[0] += inc[0];
-                            cnt[1] = (bn[1] == bn[0] ? cnt[0] : cnt[1]) + inc[1];
-                            cnt[2] = (bn[2] == bn[1] ? cnt[1] : bn[2] == bn[0] ? cnt[0] : cnt[2]) + inc[2];
-                            cnt[3] = (bn[3] == bn[2] ? cnt[2] : bn[3] == bn[1] ? cnt[1] : bn[3] == bn[0] ? cnt[0] : cnt[3]) + inc[3];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) hist[bn[u]] = (uint16_t)cnt[u];
-                        }
-                    } else if (cl < ncols) {
+                    const int cl = 32 * c + e;                       // column within the half
+                    const float dist = tc_dist(v[c][e]);
+                    if (cl < ncols) {
+                        const int col = key0 + 64 * half + cl;
                         if (MODE == GM_NEAREST) {
-                            if (dist < best) { best = dist; besti = key0 + cl; }
+                            if (dist < best) { best = dist; besti = col; }
                         } else if (MODE == GM_BEST) {
-                            const float val = dist < bwv ? vt[buf * 128 + cl] : 0.f;
-                            if (val > best) { best = val; besti = key0 + cl; }
-                        } else {
+                            const float val = dist < bwv ? vt[buf * G_BN + 64 * half + cl] : 0.f;
+                            if (val > best) { best = val; besti = col; }
+                        } else if (MODE == GM_HIST) {
+                            const float t = (dist - win_lo) * hscale;
+                            if (t >= 0.f && t < (float)HIST_BINS) {
+                                const int bin = (int)t;
+                                atomicAdd(&hist[bin >> 1], (bin & 1) ? 65536u : 1u);
+                            }
+                        } else if (MODE == GM_COLLECT) {
                             below += dist < win_lo ? 1 : 0;
                             if (dist >= win_lo && dist <= win_hi) {
-                                if (ncand < CAND_CAP) cand[ncand] = (uint16_t)(key0 + cl);
+                                if (ncand < CAND_HALF) cand[ncand] = (uint16_t)col;
                                 ++ncand;
                             }
+                        } else if (row_ok) {
+                            a.dump[grow * N + col] = dist;
                         }
                     }
                 }
-            }
-            tc_fence_before();
-            mbar_arrive(&bars->s_free[buf]);
         }
 
         // ---- per-mode finalisation
         if (MODE == GM_NEAREST || MODE == GM_BEST) {
-            if (row_ok) a.out_idx[grow] = besti;
-        } else if (MODE == GM_HIST) {
-            if (row_ok) {
-                const int k = max(1, min(a.kth[b], N));
-                int cum = 0, bin = HIST_BINS - 1, before = 0;
-                for (int q = 0; q < HIST_BINS; ++q) {
-                    const int cnt = hist[q];
-                    if (cum + cnt >= k) { bin = q; before = cum; break; }
-                    cum += cnt;
-                }
-                a.rowinfo[grow] = make_int2(bin, before);
+            // combine the two column halves of every row: better value, then lower index
+            if (half == 1) { cmb_v[row] = best; cmb_i[row] = besti; }
+            epi_barrier();
+            if (half == 0 && row_ok) {
+                const float ov = cmb_v[row];
+                const int oi = cmb_i[row];
+                const bool take = MODE == GM_NEAREST ? (ov < best || (ov == best && oi < besti))
+                                                     : (ov > best || (ov == best && oi < besti));
+                a.out_idx[grow] = take ? oi : besti;
             }
-        } else {
-            // exact fp32 recompute of the candidates, one warp per row (lanes split the candidates)
-            float* vals = reinterpret_cast<float*>(scratch + (size_t)G_BM * CAND_CAP * 2) + ew * CAND_CAP;
-            int* below_s = reinterpret_cast<int*>(scratch + (size_t)G_BM * CAND_CAP * 2 + 4 * CAND_CAP * sizeof(float));
-            int* ncand_s = below_s + G_BM;
-            below_s[row] = below;
-            ncand_s[row] = ncand;
-            __syncwarp();
+        } else if (MODE == GM_HIST) {
+            epi_barrier();
+            if (half == 0 && row_ok) {
+                int cum = 0, bin = HIST_BINS - 1, before = 0;
+                bool found = false;
+                for (int q = 0; q < HIST_BINS / 2 && !found; ++q) {
+                    const uint32_t w = hist[q];
+                    const int c0 = (int)(w & 0xffffu), c1 = (int)(w >> 16);
+                    if (cum + c0 >= krem) { bin = 2 * q; before = cum; found = true; }
+                    else if (cum + c0 + c1 >= krem) { bin = 2 * q + 1; before = cum + c0; found = true; }
+                    cum += c0 + c1;
+                }
+                if (!found) before = max(0, krem - 1);          // cannot happen (bins partition the window)
+                const float lo_new = win_lo + (float)bin / hscale;   // exact: multiples of 2^-6 / 2^-14 below 4
+                a.rowinfo[grow] = make_int2(__float_as_int(lo_new), krem - before);
+            }
+        } else if (MODE == GM_COLLECT) {
+            // exact fp32 recompute of the candidates, one warp per row (16 rows per epilogue warp)
+            float* vals = reinterpret_cast<float*>(scratch + (size_t)G_EPI * CAND_HALF * 2) + ew * 2 * CAND_HALF;
+            int* below_s = reinterpret_cast<int*>(scratch + (size_t)G_EPI * CAND_HALF * 2 + 8 * 2 * CAND_HALF * sizeof(float));
+            int* ncand_s = below_s + G_EPI;
+            below_s[row * 2 + half] = below;
+            ncand_s[row * 2 + half] = ncand;
+            epi_barrier();
             const int k = max(1, min(a.kth[b], N));
-            for (int rr = 0; rr < 32; ++rr) {
-                const int r = 32 * ew + rr;
+            const uint16_t* call = reinterpret_cast<const uint16_t*>(scratch);
+            for (int rr = 0; rr < 16; ++rr) {
+                const int r = 16 * ew + rr;
                 if (r0 + r >= N) break;                                         // warp-uniform
-                const int nc = ncand_s[r], m = k - below_s[r];                 // m-th smallest candidate (1-based)
-                if (nc > CAND_CAP || m < 1 || m > nc) {
+                const int n0 = ncand_s[2 * r], n1 = ncand_s[2 * r + 1];
+                const int nc = n0 + n1, m = k - below_s[2 * r] - below_s[2 * r + 1];   // m-th smallest candidate (1-based)
+                if (n0 > CAND_HALF || n1 > CAND_HALF || m < 1 || m > nc) {
                     if (lane == 0) { atomicExch(a.overflow, 1); a.rowval[(size_t)b * N + r0 + r] = 0.f; }
                     continue;
                 }
                 // the whole warp works on one candidate at a time: lane l owns dims 4l..4l+3, so every
                 // candidate row is one coalesced 512-byte request (4 candidates in flight per step)
                 const float4 xr = __ldg(reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + r0 + r) * G_D) + lane);
-                const uint16_t* cr = reinterpret_cast<const uint16_t*>(scratch) + (size_t)r * CAND_CAP;
+                auto cand_of = [&](int ci) -> int {
+                    return ci < n0 ? call[(size_t)(2 * r) * CAND_HALF + ci] : call[(size_t)(2 * r + 1) * CAND_HALF + ci - n0];
+                };
                 for (int c0 = 0; c0 < nc; c0 += 4) {
                     float acc[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int ci = min(c0 + u, nc - 1);
-                        const float4 w = __ldg(reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + cr[ci]) * G_D) + lane);
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + cand_of(ci)) * G_D) + lane);
                         acc[u] = fmaf(xr.x, w.x, fmaf(xr.y, w.y, fmaf(xr.z, w.z, xr.w * w.w)));
                     }
 #pragma unroll
@@ -311,46 +386,87 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// x * 2^8 = hi + lo (both fp16, round to nearest); hi -> Xs[0 .. n), lo -> Xs[n .. 2n)
+__global__ void split_half_kernel(const float4* __restrict__ in, uint2* __restrict__ hi, uint2* __restrict__ lo, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = in[i];
+        const float s[4] = {v.x * G_PRESCALE, v.y * G_PRESCALE, v.z * G_PRESCALE, v.w * G_PRESCALE};
+        float r[4];
+        uint32_t hw[2], lw[2];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[e] = s[e] - __half2float(__float2half_rn(s[e]));
+        hw[0] = pack_f16x2(s[0], s[1]); hw[1] = pack_f16x2(s[2], s[3]);
+        lw[0] = pack_f16x2(r[0], r[1]); lw[1] = pack_f16x2(r[2], r[3]);
+        hi[i] = make_uint2(hw[0], hw[1]);
+        lo[i] = make_uint2(lw[0], lw[1]);
+    }
+}
+
 template <int MODE>
-int launch_gram(const CUtensorMap& map, const GramArgs& a, int B, cudaStream_t st) {
+int launch_gram(const CUtensorMap& map, const GramArgs& a, cudaStream_t st) {
     PF_CUDA(cudaFuncSetAttribute(gram_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GCfg<MODE>::smem));
-    dim3 grid((a.N + G_BM - 1) / G_BM, B);
+    dim3 grid((a.N + G_BM - 1) / G_BM, a.B);
     gram_tc_kernel<MODE><<<grid, G_THREADS, GCfg<MODE>::smem, st>>>(map, a);
     PF_LAUNCH_CHECK();
     return 0;
 }
 
-}  // namespace
-
-// ---- NMS steps 1 and 3 on the tensor cores (called from nms.cu).  Xh_ws: B*N*128 halves of scratch.
-int prifit_tc_nms_nearest(const float* newX, int B, int N, __half* Xh_ws, CUtensorMap* map_out, int32_t* nearest, cudaStream_t st) {
-    int rc = prifit_tc_convert_to_half(newX, Xh_ws, (size_t)B * N * G_D, st);
-    if (rc) return rc;
-    rc = prifit_tc_make_tile_map(map_out, Xh_ws, B, N);
-    if (rc) return rc;
-    GramArgs a = {};
-    a.Xh = Xh_ws; a.N = N; a.out_idx = nearest;
-    return launch_gram<GM_NEAREST>(*map_out, a, B, st);
+int split_rows(const float* X, __half* Xs, int B, int N, CUtensorMap* map, cudaStream_t st) {
+    const size_t n = (size_t)B * N * G_D, n4 = n / 4;
+    split_half_kernel<<<(unsigned)min((size_t)148 * 8, (n4 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(X), reinterpret_cast<uint2*>(Xs), reinterpret_cast<uint2*>(Xs + n), n4);
+    PF_LAUNCH_CHECK();
+    return prifit_tc_make_tile_map(map, Xs, 2 * B, N);
 }
 
-int prifit_tc_nms_best(const CUtensorMap* map, const __half* Xh, const float* bw, const int32_t* votes, int B, int N,
-                       int32_t* best, cudaStream_t st) {
+}  // namespace
+
+// Xs_ws scratch for every entry point below: 2 * B * N * 128 halves.
+size_t prifit_tc_gram_split_bytes(int B, int N) { return (size_t)2 * B * N * G_D * sizeof(__half); }
+
+// ---- NMS steps 1 and 3 on the tensor cores (called from nms.cu)
+int prifit_tc_nms_nearest(const float* newX, int B, int N, __half* Xs_ws, CUtensorMap* map_out, int32_t* nearest, cudaStream_t st) {
+    int rc = split_rows(newX, Xs_ws, B, N, map_out, st);
+    if (rc) return rc;
     GramArgs a = {};
-    a.Xh = Xh; a.N = N; a.bw = bw; a.votes = votes; a.out_idx = best;
-    return launch_gram<GM_BEST>(*map, a, B, st);
+    a.Xs = Xs_ws; a.N = N; a.B = B; a.out_idx = nearest;
+    return launch_gram<GM_NEAREST>(*map_out, a, st);
+}
+
+// best[b, i] is written only for the rows listed in rowsel[b, 0 .. nrows[b])
+int prifit_tc_nms_best(const CUtensorMap* map, const __half* Xs, const float* bw, const int32_t* votes,
+                       const int32_t* rowsel, const int32_t* nrows, int B, int N, int32_t* best, cudaStream_t st) {
+    GramArgs a = {};
+    a.Xs = Xs; a.N = N; a.B = B; a.bw = bw; a.votes = votes; a.rowsel = rowsel; a.nrows = nrows; a.out_idx = best;
+    return launch_gram<GM_BEST>(*map, a, st);
 }
 
 // ---- bandwidth order statistic on the tensor cores (called from bandwidth.cu)
-int prifit_tc_bandwidth_rows(const float* X, int B, int N, const int32_t* kth, __half* Xh_ws, int2* rowinfo_ws,
+int prifit_tc_bandwidth_rows(const float* X, int B, int N, const int32_t* kth, __half* Xs_ws, int2* rowinfo_ws,
                              float* rowval, int32_t* overflow, cudaStream_t st) {
-    int rc = prifit_tc_convert_to_half(X, Xh_ws, (size_t)B * N * G_D, st);
-    if (rc) return rc;
     CUtensorMap map;
-    rc = prifit_tc_make_tile_map(&map, Xh_ws, B, N);
+    int rc = split_rows(X, Xs_ws, B, N, &map, st);
     if (rc) return rc;
     GramArgs a = {};
-    a.Xh = Xh_ws; a.X32 = X; a.N = N; a.kth = kth; a.rowinfo = rowinfo_ws; a.rowval = rowval; a.overflow = overflow;
-    rc = launch_gram<GM_HIST>(map, a, B, st);
+    a.Xs = Xs_ws; a.X32 = X; a.N = N; a.B = B; a.kth = kth; a.rowinfo = rowinfo_ws; a.rowval = rowval; a.overflow = overflow;
+    a.level = 0;
+    rc = launch_gram<GM_HIST>(map, a, st);
     if (rc) return rc;
-    return launch_gram<GM_COLLECT>(map, a, B, st);
+    a.level = 1;
+    rc = launch_gram<GM_HIST>(map, a, st);
+    if (rc) return rc;
+    return launch_gram<GM_COLLECT>(map, a, st);
+}
+
+// diagnostics (tests): dist[B,N,N] = the tensor-core distance matrix.  ws >= prifit_tc_gram_split_bytes(B, N) + 256.
+extern "C" int prifit_debug_tc_gram(const float* X, int B, int N, float* dist_out, void* ws, void* stream) {
+    PF_CHECK_ARG(X && dist_out && ws, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(B > 0 && N > 0, PRIFIT_E_BADARG, "B, N > 0 required");
+    __half* Xs = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    CUtensorMap map;
+    int rc = split_rows(X, Xs, B, N, &map, pf_stream(stream));
+    if (rc) return rc;
+    GramArgs a = {};
+    a.Xs = Xs; a.N = N; a.B = B; a.dump = dist_out;
+    return launch_gram<GM_DUMP>(map, a, pf_stream(stream));
 }

@@ -20,8 +20,8 @@
 // cannot use, so one tf32 tile could not feed both GEMMs.  fp16 uses SWIZZLE_128B in both majors,
 // halves the tile bytes and doubles the MMA rate.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = softmax / epilogue (one thread per seed row, one warp per TMEM lane quarter).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-11 = softmax / epilogue (two warps per TMEM lane quarter: thread = seed row x 64-key half).
 //
 // This pass only feeds the NMS (discrete outcome); the K centres that carry gradient are recomputed in
 // fp32 (meanshift_rows.cu).
@@ -40,7 +40,8 @@ constexpr int TC_BN = 128;                 // keys per tile
 constexpr int TC_STAGES = 5;
 constexpr uint32_t TC_TILE_BYTES = TC_BN * TC_D * 2;      // 32768
 constexpr uint32_t TC_KBLOCK_BYTES = TC_BN * 128;          // one 64-column (128 B) block of the tile
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;             // warps 0-2: TMA / MMA / TMEM alloc, warps 4-11: softmax
+constexpr int TC_SOFTMAX = 256;             // softmax threads: (seed row, 64-key half of every tile)
 constexpr uint32_t COL_S0 = 0, COL_O = 256, COL_Q = 384;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float P_SCALE_LOG2 = 10.0f;      // weights are stored as 2^10 * kappa (keeps e^-13 a normal f16)
@@ -53,6 +54,7 @@ struct TcBarriers {
     uint64_t o_full;
     uint64_t q_full;
     uint32_t tmem_base;
+    float ssum[2][2][TC_BM];     // [iteration parity][column half][row] partial ||O||^2
 };
 
 constexpr size_t TC_SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)TC_STAGES * TC_TILE_BYTES + sizeof(TcBarriers);
@@ -78,9 +80,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bars->x_full[s], 1); mbar_init(&bars->x_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], TC_SOFTMAX); }
         mbar_init(&bars->o_full, 1);
-        mbar_init(&bars->q_full, 128);
+        mbar_init(&bars->q_full, TC_SOFTMAX);
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) prefetch_tensormap(&tmap);
@@ -117,7 +119,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
 #pragma unroll
                 for (int kk = 0; kk < TC_BN / 16; ++kk) {      // 16 keys per MMA = two 8-row groups, 1024 B apart
                     const uint64_t bd = smem_desc_sw128(base + kk * 2048, TC_KBLOCK_BYTES, 1024);
-                    mma_f16_ts(tmem + COL_O, tmem + COL_S0 + buf * 128 + kk * 8, bd, idesc2, !(first_of_iter && kk == 0));
+                    // P of keys [64h, 64h+64) sits packed in columns [64h, 64h+32) of the S buffer it replaces
+                    mma_f16_ts(tmem + COL_O, tmem + COL_S0 + buf * 128 + (kk >> 2) * 64 + (kk & 3) * 8, bd, idesc2,
+                               !(first_of_iter && kk == 0));
                 }
                 mma_commit(&bars->x_empty[st]);
             };
@@ -146,22 +150,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
         }
     } else if (warp >= 4) {
         // ============================= softmax / epilogue ==============================
-        const int row = threadIdx.x - 128;                       // TMEM lane == seed row within the tile
-        const uint32_t lane_base = (uint32_t)(32 * (warp - 4)) << 16;
+        // Two warps per SM sub-partition: thread = (seed row, 64-key half).  One warp alone cannot hide the
+        // tcgen05.ld -> ex2 -> tcgen05.st latency chain; two interleave and keep the MUFU pipe busy.
+        const int ew = warp - 4, half = ew >> 2;
+        const int row = 32 * (ew & 3) + lane;                    // TMEM lane == seed row within the tile
+        const uint32_t lane_base = (uint32_t)(32 * (ew & 3)) << 16;
         const bool row_ok = r0 + row < N;
         const float bwv = bw[b];
         const float c1 = LOG2E / (bwv * bwv), c0 = P_SCALE_LOG2 - c1, lo2 = PRIFIT_LO * LOG2E + P_SCALE_LOG2;
-        uint32_t v[32], h[16];
-        // Q^0 = this tile's own rows of X (already fp16: 256 B per row = 64 packed columns)
-        const uint4* xrow = reinterpret_cast<const uint4*>(Xh + ((size_t)b * N + (row_ok ? r0 + row : 0)) * TC_D);
+        uint32_t v[2][32], h[16];
+        // Q^0 = this tile's own rows of X (already fp16: 256 B per row = 64 packed columns, 32 per half)
+        const uint4* xrow = reinterpret_cast<const uint4*>(Xh + ((size_t)b * N + (row_ok ? r0 + row : 0)) * TC_D) + 8 * half;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const uint4 f = row_ok ? xrow[c * 4 + e] : make_uint4(0u, 0u, 0u, 0u);
                 h[4 * e] = f.x; h[4 * e + 1] = f.y; h[4 * e + 2] = f.z; h[4 * e + 3] = f.w;
             }
-            tmem_st16(tmem + lane_base + COL_Q + 16 * c, h);
+            tmem_st16(tmem + lane_base + COL_Q + 32 * half + 16 * c, h);
         }
         tmem_wait_st();
         tc_fence_before();
@@ -173,60 +180,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
                 const uint32_t buf = it & 1, ph = (it >> 1) & 1;
                 mbar_wait(&bars->s_full[buf], ph);
                 tc_fence_after();
-                const uint32_t sbase = tmem + lane_base + COL_S0 + buf * 128;
-                const int key0 = j * TC_BN;
+                const uint32_t sbase = tmem + lane_base + COL_S0 + buf * 128 + 64 * half;
+                const int key0 = j * TC_BN + 64 * half;
+                tmem_ld32(sbase, v[0]);
+                tmem_ld32(sbase + 32, v[1]);
+                tmem_wait_ld();
+                // P = 2^10 exp(clamp((s-1)/bw^2, -13, .)) packed as f16 pairs over the first 32 of this
+                // thread's own 64 S columns (already in registers); padded keys weigh nothing
+                if (key0 + 64 <= N) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    tmem_ld32(sbase + 32 * c, v);
-                    tmem_wait_ld();
+                    for (int c = 0; c < 2; ++c) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        // 2^10 exp(clamp((s-1)/bw^2, -13, .)); padded keys weigh nothing
-                        float p0 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[2 * e]), c1, c0), lo2));
-                        float p1 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[2 * e + 1]), c1, c0), lo2));
-                        if (key0 + 32 * c + 2 * e >= N) p0 = 0.f;
-                        if (key0 + 32 * c + 2 * e + 1 >= N) p1 = 0.f;
-                        h[e] = pack_f16x2(p0, p1);
+                        for (int e = 0; e < 16; ++e) {
+                            const float p0 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[c][2 * e]), c1, c0), lo2));
+                            const float p1 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[c][2 * e + 1]), c1, c0), lo2));
+                            h[e] = pack_f16x2(p0, p1);
+                        }
+                        tmem_st16(sbase + 16 * c, h);
                     }
-                    tmem_st16(sbase + 16 * c, h);               // P (packed) aliases the S columns already consumed
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float p0 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[c][2 * e]), c1, c0), lo2));
+                            float p1 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[c][2 * e + 1]), c1, c0), lo2));
+                            if (key0 + 32 * c + 2 * e >= N) p0 = 0.f;
+                            if (key0 + 32 * c + 2 * e + 1 >= N) p1 = 0.f;
+                            h[e] = pack_f16x2(p0, p1);
+                        }
+                        tmem_st16(sbase + 16 * c, h);
+                    }
                 }
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(&bars->p_full[buf]);
             }
-            // epilogue of iteration t: y' = O / ||O||
+            // epilogue of iteration t: y' = O / ||O||  (each thread owns 64 of the row's 128 columns)
             mbar_wait(&bars->o_full, t & 1);
             tc_fence_after();
+            tmem_ld32(tmem + lane_base + COL_O + 64 * half, v[0]);
+            tmem_ld32(tmem + lane_base + COL_O + 64 * half + 32, v[1]);
+            tmem_wait_ld();
             float ss = 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_ld32(tmem + lane_base + COL_O + 32 * c, v);
-                tmem_wait_ld();
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int e = 0; e < 32; ++e) ss = fmaf(__uint_as_float(v[e]), __uint_as_float(v[e]), ss);
-            }
-            const float inv = 1.0f / sqrtf(ss);
-            const bool last = t == T - 1;
-            float4* orow = reinterpret_cast<float4*>(newX + ((size_t)b * N + (row_ok ? r0 + row : 0)) * TC_D);
+                for (int e = 0; e < 32; ++e) ss = fmaf(__uint_as_float(v[c][e]), __uint_as_float(v[c][e]), ss);
+            bars->ssum[t & 1][half][row] = ss;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float inv = 1.0f / sqrtf(bars->ssum[t & 1][0][row] + bars->ssum[t & 1][1][row]);
+            if (t == T - 1) {
+                if (row_ok) {
+                    float4* orow = reinterpret_cast<float4*>(newX + ((size_t)b * N + r0 + row) * TC_D) + 16 * half;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_ld32(tmem + lane_base + COL_O + 32 * c, v);
-                tmem_wait_ld();
-                if (last) {
-                    if (row_ok) {
+                    for (int c = 0; c < 2; ++c)
 #pragma unroll
                         for (int e = 0; e < 8; ++e)
-                            orow[c * 8 + e] = make_float4(__uint_as_float(v[4 * e]) * inv, __uint_as_float(v[4 * e + 1]) * inv,
-                                                          __uint_as_float(v[4 * e + 2]) * inv, __uint_as_float(v[4 * e + 3]) * inv);
-                    }
-                } else {
+                            orow[c * 8 + e] = make_float4(__uint_as_float(v[c][4 * e]) * inv, __uint_as_float(v[c][4 * e + 1]) * inv,
+                                                          __uint_as_float(v[c][4 * e + 2]) * inv, __uint_as_float(v[c][4 * e + 3]) * inv);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
-                        h[e] = pack_f16x2(__uint_as_float(v[2 * e]) * inv, __uint_as_float(v[2 * e + 1]) * inv);
-                    tmem_st16(tmem + lane_base + COL_Q + 16 * c, h);
+                        h[e] = pack_f16x2(__uint_as_float(v[c][2 * e]) * inv, __uint_as_float(v[c][2 * e + 1]) * inv);
+                    tmem_st16(tmem + lane_base + COL_Q + 32 * half + 16 * c, h);
                 }
-            }
-            if (!last) {
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(&bars->q_full);

@@ -14,8 +14,9 @@
 #include "rowgemm.cuh"
 
 int prifit_tc_nms_nearest(const float* newX, int B, int N, __half* Xh_ws, CUtensorMap* map_out, int32_t* nearest, cudaStream_t st);
-int prifit_tc_nms_best(const CUtensorMap* map, const __half* Xh, const float* bw, const int32_t* votes, int B, int N,
-                       int32_t* best, cudaStream_t st);
+int prifit_tc_nms_best(const CUtensorMap* map, const __half* Xs, const float* bw, const int32_t* votes,
+                       const int32_t* rowsel, const int32_t* nrows, int B, int N, int32_t* best, cudaStream_t st);
+size_t prifit_tc_gram_split_bytes(int B, int N);
 int prifit_gram_engine();
 
 namespace {
@@ -200,7 +201,7 @@ __global__ void nms_nlabels_kernel(const int32_t* __restrict__ used, const int32
 }
 
 struct NmsWs {
-    int32_t *nearest, *votes, *best, *flags, *used;
+    int32_t *nearest, *votes, *best, *flags, *used, *rowsel, *nrows;
 };
 
 NmsWs carve(void* ws, int B, int N) {
@@ -212,6 +213,8 @@ NmsWs carve(void* ws, int B, int N) {
     w.used = p + 2 * bn;
     w.nearest = p + 2 * bn + (size_t)B * 64;
     w.best = w.nearest + bn;
+    w.rowsel = w.best + bn;
+    w.nrows = w.rowsel + bn;
     return w;
 }
 
@@ -226,7 +229,7 @@ int launch_nms(const float* newX, const float* bw, int B, int N, int Kcap, int32
     PF_CUDA(cudaMemsetAsync(w.votes, 0, (2 * (size_t)B * N + (size_t)B * 64) * sizeof(int32_t), st));
     dim3 gt((N + RG_KEYS - 1) / RG_KEYS, B), ge((N + 255) / 256, B);
     const bool tc = D == 128 && prifit_gram_engine() == 0;      // Gram passes on the tensor cores (gram_tc.cu)
-    __half* Xh = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(w.best + (size_t)B * N) + 255) & ~(uintptr_t)255);
+    __half* Xh = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(w.nrows + B) + 255) & ~(uintptr_t)255);
     CUtensorMap map;
     if (tc) {
         int rc = prifit_tc_nms_nearest(newX, B, N, Xh, &map, w.nearest, st);
@@ -238,7 +241,11 @@ int launch_nms(const float* newX, const float* bw, int B, int N, int Kcap, int32
     nms_vote_kernel<<<ge, 256, 0, st>>>(w.nearest, N, w.votes);
     PF_LAUNCH_CHECK();
     if (tc) {
-        int rc = prifit_tc_nms_best(&map, Xh, bw, w.votes, B, N, w.best, st);
+        // step 3 only concerns the rows that received votes (nbrs[uniques], src/mean_shift.py:192-194):
+        // compact them (ascending) and run the Gram pass over those rows alone
+        nms_compact_kernel<<<B, 1024, 0, st>>>(w.votes, N, N, w.rowsel, w.nrows);
+        PF_LAUNCH_CHECK();
+        int rc = prifit_tc_nms_best(&map, Xh, bw, w.votes, w.rowsel, w.nrows, B, N, w.best, st);
         if (rc) return rc;
     } else {
         nms_gram_kernel<D, 1><<<gt, RG_THREADS, smem, st>>>(newX, bw, N, w.votes, w.best);
@@ -258,7 +265,8 @@ int launch_nms(const float* newX, const float* bw, int B, int N, int Kcap, int32
 }  // namespace
 
 extern "C" size_t prifit_nms_workspace_bytes(int B, int N, int d) {
-    return (4 * (size_t)B * N + (size_t)B * 64) * sizeof(int32_t) + 256 + (size_t)B * N * d * 2 /* fp16 rows for the tensor-core Gram */;
+    // votes, flags, used, nearest, best, rowsel, nrows | split fp16 rows (hi + lo) for the tensor-core Gram
+    return (5 * (size_t)B * N + (size_t)B * 64 + B) * sizeof(int32_t) + 256 + (d == 128 ? prifit_tc_gram_split_bytes(B, N) : 0);
 }
 
 extern "C" int prifit_nms_fwd(const float* newX, const float* bw, int B, int N, int d, int Kcap,

@@ -447,3 +447,23 @@ def test_nms_tensor_core_matches_fp32(cuda, n, kc):
     for b in range(2):
         label_map(lb[b].cpu().numpy(), la[b].cpu().numpy())
         label_map(lb[b].cpu().numpy(), planted[b].numpy())
+
+
+@pytest.mark.parametrize("n", [128, 333, 1000])
+def test_tensor_core_gram_error_is_far_inside_the_candidate_margin(cuda, n):
+    """The split-fp16 (hi + lo, three MMAs) distance matrix of gram_tc.cu vs fp64: the bandwidth candidate
+    pass assumes |tensor-core - fp32| <= 1e-5 (BW_MARGIN / 2); measured error must stay 4x inside that."""
+    import ctypes
+
+    from prifit_b200 import _lib, synthetic
+
+    E, _, _ = synthetic.planted_shapes(1, n_points=n, n_clusters=4, seed=77)
+    X = torch.cat([R.normalize_twice(E), _unit(n, 128, 78)[None]]).to(cuda).contiguous()      # planted + random rows
+    dist = torch.empty(2, n, n, device=cuda)
+    ws = torch.empty(4 * 2 * n * 128 + 256, dtype=torch.uint8, device=cuda)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.call("prifit_debug_tc_gram", P(X), 2, n, P(dist), P(ws), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    Xd = X.double().cpu()
+    ref = (2.0 - 2.0 * Xd @ Xd.transpose(1, 2)).clamp(min=0.0)
+    err = float((dist.cpu().double() - ref).abs().max())
+    assert err < 2.5e-6, err
