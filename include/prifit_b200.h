@@ -78,17 +78,25 @@ int prifit_nms_fwd(const float* newX, const float* bw, int B, int N, int d, int 
                    int32_t* idx_out, int32_t* K_out, int32_t* labels_out, int32_t* n_labels_out,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* engines of the K-seed trajectory kernels */
+#define PRIFIT_ROWS_SPLIT_TCGEN05 0 /* tensor cores, split-fp16 (hi + lo) operands, 3 tcgen05.mma per product: fp32-class; d == 128 */
+#define PRIFIT_ROWS_FP32_SIMT     1 /* CUDA-core fp32 (cross-check; d in {64, 128, 256}) */
+
 /* k2 rows -- fp32 trajectories of the K selected seeds (center = new_X[indices],
  *   src/mean_shift.py:46): traj_out[B, T+1, Kcap, d] (y^0..y^T), stat_out[B, T, Kcap, 2] =
- *   (Z_t, ||u_t||), C_out[B,Kcap,d] = y^T.  Rows k >= K[b] are zero. */
+ *   (Z_t, ||u_t||), C_out[B,Kcap,d] = y^T.  Rows k >= K[b] are zero.  engine = PRIFIT_ROWS_*. */
+size_t prifit_meanshift_rows_workspace_bytes(int B, int N, int d, int engine);
 int prifit_meanshift_rows_fwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K,
                               int B, int N, int d, int T, int Kcap,
-                              float* traj_out, float* stat_out, float* C_out, void* stream);
+                              float* traj_out, float* stat_out, float* C_out,
+                              int engine, void* ws, size_t ws_bytes, void* stream);
 /* k2 backward -- autograd of mean_shift_ restricted to the K seeds that carry gradient (rows are
- *   independent given X).  gC[B,Kcap,d] = dL/d center; accumulates dL/dX into gX_inout[B,N,d]. */
+ *   independent given X).  gC[B,Kcap,d] = dL/d center; accumulates dL/dX into gX_inout[B,N,d].
+ *   traj / stat may come from either forward engine. */
 int prifit_meanshift_rows_bwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K,
                               const float* traj, const float* stat, const float* gC,
-                              int B, int N, int d, int T, int Kcap, float* gX_inout, void* stream);
+                              int B, int N, int d, int T, int Kcap, float* gX_inout,
+                              int engine, void* ws, size_t ws_bytes, void* stream);
 
 /* k4 -- soft membership.  src/mean_shift.py:230-247 (membership); W_out[B,Kcap,N] (cluster-major,
  *   i.e. the reference's [K,N] before the caller's transpose), smax_out[B] = the detached global max. */

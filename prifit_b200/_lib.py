@@ -27,8 +27,9 @@ SIGNATURES = {
     "prifit_meanshift_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _sz, _p]),
     "prifit_nms_workspace_bytes": (_sz, [_i, _i, _i]),
     "prifit_nms_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
-    "prifit_meanshift_rows_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
-    "prifit_meanshift_rows_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "prifit_meanshift_rows_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "prifit_meanshift_rows_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _sz, _p]),
+    "prifit_meanshift_rows_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _sz, _p]),
     "prifit_membership_workspace_bytes": (_sz, [_i, _i, _i]),
     "prifit_membership_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "prifit_membership_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
@@ -44,6 +45,8 @@ SIGNATURES = {
 FIT_CTX = 48
 MS_TF32_TCGEN05 = 0
 MS_FP32_SIMT = 1
+ROWS_SPLIT_TCGEN05 = 0
+ROWS_FP32_SIMT = 1
 
 _lib = None
 
@@ -79,7 +82,7 @@ def check(rc, what):
 # kernels (and memset nodes) each entry point enqueues; bench.py reports the sum as `gpu_launches`
 LAUNCHES = {
     "prifit_normalize_fwd": 1, "prifit_normalize_bwd": 1, "prifit_bandwidth_fwd": 6, "prifit_meanshift_fwd": 1,
-    "prifit_nms_fwd": 10, "prifit_meanshift_rows_fwd": 1, "prifit_meanshift_rows_bwd": 1,
+    "prifit_nms_fwd": 10, "prifit_meanshift_rows_fwd": 2, "prifit_meanshift_rows_bwd": 2,
     "prifit_membership_fwd": 2, "prifit_membership_bwd": 1, "prifit_fit_fwd": 1, "prifit_fit_bwd": 1,
     "prifit_sdf_loss_fwd": 2, "prifit_sdf_loss_bwd": 1,
 }

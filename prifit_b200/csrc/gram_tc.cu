@@ -421,6 +421,11 @@ int split_rows(const float* X, __half* Xs, int B, int N, CUtensorMap* map, cudaS
 
 }  // namespace
 
+// shared with meanshift_rows_tc.cu: x * 2^8 = hi + lo rows and the [2B][N][128] tile map over them
+int prifit_tc_split_rows(const float* X, __half* Xs, int B, int N, CUtensorMap* map, cudaStream_t st) {
+    return split_rows(X, Xs, B, N, map, st);
+}
+
 // Xs_ws scratch for every entry point below: 2 * B * N * 128 halves.
 size_t prifit_tc_gram_split_bytes(int B, int N) { return (size_t)2 * B * N * G_D * sizeof(__half); }
 

@@ -1,0 +1,863 @@
+// k2 rows, tensor-core engine -- trajectories of the K selected seeds (forward) and the reverse sweep
+// through them (backward) on tcgen05 / TMEM / TMA with fp32-class operands.
+//
+// reference: center = new_X[indices] (src/mean_shift.py:46) over mean_shift_ (src/mean_shift.py:50-84).
+// Same mathematics and the same saved tensors (traj, stat) as the CUDA-core kernels of
+// meanshift_rows.cu, which remain as the cross-check engine.
+//
+// Layout of the problem.  K <= 64 seeds against N keys is a "few rows x many keys" contraction, so
+// the MMAs run TRANSPOSED: keys are the M dimension (128 per tile = TMEM lanes), a group of 32 seeds
+// is the N dimension, and the KEYS of a shape are split over a thread-block cluster (<= 8 CTAs);
+// per-iteration partial sums (32 x d) are reduced through distributed shared memory in fixed rank
+// order.  One epilogue thread owns one key (and 16 of the 32 seeds).
+//
+//   forward, per key tile     S^T[128 keys x 32]  = Xtile . Y^T              (A smem K-major, B smem K-major)
+//                             P^T = exp(clamp(-(2 - 2 S)/b^2/2))             -> smem tile [key][seed]
+//                             O^T[d x 32]        += Xtile^T . P^T            (A smem MN-major, B smem MN-major)
+//   backward, per key tile    S1^T = Xtile . Y^T ,  S2^T = Xtile . Gm^T
+//                             ds, e1 (see meanshift_rows.cu)                  -> smem tile [key][ds | e1]
+//                             gy^T[d x 32]       += Xtile^T . ds^T
+//                             gX[128 keys x d]    = [ds | e1] . [Y ; Gm]     (A smem K-major, B smem MN-major)
+//
+// Precision.  Every operand is split into two fp16 numbers (hi + lo, 22 significant bits) after a
+// power-of-two pre-scale that keeps both halves normal, and every product is three tcgen05.mma
+// (lo.hi + hi.lo + hi.hi) accumulated in fp32 -- the same scheme as the Gram engine (gram_tc.cu),
+// |error| ~ 3e-7 on a dot product of unit vectors, i.e. fp32-class.  Scales:
+//   x, y      * 2^8                       (unit vectors)
+//   p         * 2^14                      (p in [e^-13, 1])
+//   gm        * SG  (power of two, max |gm| of the shape and iteration -> [2^7, 2^8))
+//   ds        * SD  (power of two from the bound |ds| <= 2 ||gm|| D / b^2 -> < 2^14)
+//   e1        * SE = SD 2^8 / SG          (so both halves of the K = 64 contraction share one scale)
+#include <cudaTypedefs.h>
+#include <cuda_fp16.h>
+#include <cooperative_groups.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace cg = cooperative_groups;
+using namespace sm100;
+
+int prifit_tc_make_tile_map(CUtensorMap* map, const __half* X, int B, int N);
+int prifit_tc_split_rows(const float* X, __half* Xs, int B, int N, CUtensorMap* map, cudaStream_t st);
+
+namespace {
+
+constexpr int RT_D = 128, RT_KEYS = 128, RT_SEEDS = 32;
+constexpr int RT_THREADS = 384;                            // warps 0-3: TMA / MMA / TMEM alloc / spare, warps 4-11: epilogue
+constexpr int RT_EPI = 256;
+constexpr int RT_STAGES = 2;
+constexpr uint32_t RT_HALF_BYTES = RT_KEYS * RT_D * 2;     // one fp16 key tile (hi or lo): 32 KB
+constexpr uint32_t RT_STAGE_BYTES = 2 * RT_HALF_BYTES;     // hi + lo
+constexpr uint32_t RT_KBLOCK = RT_KEYS * 128;              // one 64-column (128 B) block of a key tile
+constexpr uint32_t RT_PPART = RT_KEYS * 128;               // coefficient tile [128 keys][128 B], one part (hi or lo)
+constexpr float RT_XSCALE = 256.0f;                        // x, y pre-scale (matches split_half_kernel of gram_tc.cu)
+constexpr float RT_PSCALE = 16384.0f;                      // p pre-scale
+constexpr int RT_MAXC = 8;
+
+// ---- shared-memory plans (offsets from a 1024-aligned base; every MMA tile is 1024-aligned)
+struct FwdPlan {
+    static constexpr uint32_t Y_KB = RT_SEEDS * 128;                         // [32 rows][128 B] per 64-column block
+    static constexpr uint32_t Y_PART = 2 * Y_KB;                             // 8 KB (hi or lo)
+    static constexpr uint32_t x = 0;
+    static constexpr uint32_t y = x + RT_STAGES * RT_STAGE_BYTES;            // Y tile hi | lo
+    static constexpr uint32_t p = y + 2 * Y_PART;                            // P tile hi | lo
+    static constexpr uint32_t ys = p + 2 * RT_PPART;                         // fp32 [32][128] current seeds
+    static constexpr uint32_t misc = ys + RT_SEEDS * RT_D * 4;
+    static constexpr uint32_t total = misc + 4096;
+    // aliases inside the coefficient tile (dead between the tile loop and the next one)
+    static constexpr uint32_t part_o = p;                                    // fp32 [32][128] partial numerators
+    static constexpr uint32_t urow = p + RT_PPART;                           // fp32 [32][128] owned rows being finished
+};
+struct BwdPlan {
+    static constexpr uint32_t YG_KB = 2 * RT_SEEDS * 128;                    // [Y rows 0-31 | Gm rows 32-63][128 B]: 8 KB
+    static constexpr uint32_t YG_PART = 2 * YG_KB;                           // 16 KB (hi or lo)
+    static constexpr uint32_t x = 0;
+    static constexpr uint32_t yg = x + RT_STAGES * RT_STAGE_BYTES;
+    static constexpr uint32_t de = yg + 2 * YG_PART;                         // [128 keys][ds 64 B | e1 64 B] hi | lo
+    static constexpr uint32_t gy = de + 2 * RT_PPART;                        // fp32 [32][128] dL/dy^{t+1}
+    static constexpr uint32_t misc = gy + RT_SEEDS * RT_D * 4;
+    static constexpr uint32_t total = misc + 4096;
+    // aliases inside the coefficient tile (dead between the tile loop and the next one)
+    static constexpr uint32_t part_o = de;                                   // fp32 [32][128]
+    static constexpr uint32_t gms = de + RT_PPART;                           // fp32 [32][128]
+};
+
+struct RtMisc {
+    uint64_t x_full[RT_STAGES], x_empty[RT_STAGES];
+    uint64_t s_full[2], s_free[2];
+    uint64_t c_full, c_free;             // coefficient tile (P / ds|e1) written / consumed
+    uint64_t gx_full[2], gx_free[2];     // backward: gX accumulator of a tile complete / flushed
+    uint64_t o_full, y_full;
+    uint32_t tmem_base;
+    float part_z[RT_SEEDS];
+    float zwarp[8][16];
+    float red[RT_EPI];
+    float gmm[RT_SEEDS], dinv[RT_SEEDS], gmax[RT_SEEDS], gbound[RT_SEEDS];
+    float scal[4];                        // backward: SG, SD, SE
+};
+static_assert(sizeof(RtMisc) <= 4096, "misc block");
+
+__host__ __device__ constexpr uint32_t idesc_f16_mm(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// (a, b) -> packed f16 pairs hi, lo with a = hi.x + lo.x (22 significant bits), likewise b
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// three MMAs of one 16-element K step: D (+)= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi
+__device__ __forceinline__ void mma3(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc, bool acc) {
+    mma_f16_ss(d, a_lo, b_hi, idesc, acc);
+    mma_f16_ss(d, a_hi, b_lo, idesc, true);
+    mma_f16_ss(d, a_hi, b_hi, idesc, true);
+}
+
+// Sum 16 per-lane values over the 32 lanes of a warp; lane l ends up with the total of value index (l >> 1) & 15.
+__device__ __forceinline__ float warp_transpose_sum16(const float (&v)[16], int lane) {
+    float w8[8], w4[4], w2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = b4 ? v[i] : v[i + 8], keep = b4 ? v[i + 8] : v[i];
+        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b3 ? w8[i] : w8[i + 4], keep = b3 ? w8[i + 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b2 ? w4[i] : w4[i + 2], keep = b2 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const float send = b1 ? w2[0] : w2[1], keep = b1 ? w2[1] : w2[0];
+    float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
+// write 8 consecutive fp32 (pre-scaled) of row `r`, 16-byte chunk `chunk` (0..7) of a [rows][128 B] SWIZZLE_128B
+// block as hi / lo fp16
+__device__ __forceinline__ void store_chunk_hilo(uint8_t* hi_blk, uint8_t* lo_blk, int r, int chunk, const float (&f)[8]) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split2(f[2 * e], f[2 * e + 1], h[e], l[e]);
+    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(hi_blk + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_blk + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// power of two 2^e with v * 2^e in [2^(top-1), 2^top)   (v > 0, finite)
+__device__ __forceinline__ float pow2_scale_to(float v, int top) {
+    int ex;
+    frexpf(v, &ex);                   // v = m 2^ex, m in [0.5, 1)
+    return ldexpf(1.0f, top - ex);
+}
+
+struct RowsArgs {
+    const float* X; const float* bw; const int32_t* idx; const int32_t* K;
+    int N, B, T, Kcap;
+    // forward
+    float* traj; float* stat; float* C_out;
+    // backward
+    const float* traj_in; const float* stat_in; const float* gC; float* gX;
+};
+
+// key tiles of this CTA: [j0, j0 + ntl)
+__device__ __forceinline__ void my_tiles(int N, int csize, int rank, int& j0, int& ntl) {
+    const int nt = (N + RT_KEYS - 1) / RT_KEYS, tpc = (nt + csize - 1) / csize;
+    j0 = rank * tpc;
+    ntl = max(0, min(nt, j0 + tpc) - j0);
+}
+
+__device__ __forceinline__ void produce_tile(uint8_t* smem, RtMisc* m, const CUtensorMap* tmap, uint32_t st, int row0, int b, int B) {
+    mbar_arrive_expect_tx(&m->x_full[st], RT_STAGE_BYTES);
+    const uint32_t dst = smem_u32(smem + (size_t)st * RT_STAGE_BYTES);
+    tma_load_3d(dst, tmap, &m->x_full[st], 0, row0, b);
+    tma_load_3d(dst + RT_KBLOCK, tmap, &m->x_full[st], 64, row0, b);
+    tma_load_3d(dst + RT_HALF_BYTES, tmap, &m->x_full[st], 0, row0, B + b);
+    tma_load_3d(dst + RT_HALF_BYTES + RT_KBLOCK, tmap, &m->x_full[st], 64, row0, B + b);
+}
+
+// =========================================================================================== forward
+__global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const RowsArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int b = blockIdx.z, k0 = blockIdx.y * RT_SEEDS;
+    const int N = a.N, T = a.T, Kcap = a.Kcap;
+    const int Kb = min(a.K[b], Kcap);
+    const int nrows = max(0, min(RT_SEEDS, Kb - k0));
+    const int krows = min(RT_SEEDS, Kcap - k0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    float* traj_b = a.traj + (size_t)b * (T + 1) * Kcap * RT_D;
+    float* stat_b = a.stat + (size_t)b * T * Kcap * 2;
+
+    // padded rows of this seed group are defined as zero
+    for (int t = rank; t <= T; t += csize) {
+        for (int e = tid; e < (krows - nrows) * RT_D; e += RT_THREADS) {
+            const int r = nrows + e / RT_D, c = e % RT_D;
+            traj_b[((size_t)t * Kcap + k0 + r) * RT_D + c] = 0.f;
+            if (t == T) a.C_out[((size_t)b * Kcap + k0 + r) * RT_D + c] = 0.f;
+        }
+        if (t < T)
+            for (int e = tid; e < (krows - nrows) * 2; e += RT_THREADS) stat_b[((size_t)t * Kcap + k0 + nrows) * 2 + e] = 0.f;
+    }
+    if (nrows == 0) return;   // uniform over the cluster, before any barrier / allocation
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    RtMisc* m = reinterpret_cast<RtMisc*>(smem + FwdPlan::misc);
+    float* ys = reinterpret_cast<float*>(smem + FwdPlan::ys);
+    float* part_o = reinterpret_cast<float*>(smem + FwdPlan::part_o);
+    float* urow = reinterpret_cast<float*>(smem + FwdPlan::urow);
+
+    int j0, ntl;
+    my_tiles(N, csize, rank, j0, ntl);
+    const bool resident = ntl <= RT_STAGES;       // the CTA's key slice stays in shared memory for all T iterations
+
+    if (tid == 0) {
+        for (int s = 0; s < RT_STAGES; ++s) { mbar_init(&m->x_full[s], 1); mbar_init(&m->x_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&m->s_full[s], 1); mbar_init(&m->s_free[s], RT_EPI); }
+        mbar_init(&m->c_full, RT_EPI); mbar_init(&m->c_free, 1);
+        mbar_init(&m->o_full, 1); mbar_init(&m->y_full, RT_EPI);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) prefetch_tensormap(&tmap);
+    if (warp == 2) { tmem_alloc(&m->tmem_base, 128); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = m->tmem_base;
+    constexpr uint32_t COL_S = 0, COL_O = 64;
+
+    const float* Xb = a.X + (size_t)b * N * RT_D;
+    const int32_t* idx_b = a.idx + (size_t)b * Kcap + k0;
+    const float bwv = a.bw[b];
+    const float b2 = bwv * bwv;
+
+    // epilogue-thread coordinates (valid for warps >= 4)
+    const int et = tid - 128, ew = warp - 4, half = (ew >> 2) & 1;
+    const int row = 32 * (ew & 3) + lane;                          // TMEM lane: key within the tile / column d of O^T
+    const uint32_t lane_base = (uint32_t)(32 * (ew & 3)) << 16;
+    // reduce-phase ownership: this CTA finishes seeds [rank * rpc, rank * rpc + rpc)
+    const int rpc = (RT_SEEDS + csize - 1) / csize, tpr = RT_EPI / rpc;
+    const int rr = et / tpr, tc = et - rr * tpr;
+    const int myrow = rank * rpc + rr;
+    const bool owner = warp >= 4 && rr < rpc && myrow < RT_SEEDS;
+
+    auto write_y_tile = [&]() {      // ys (fp32) -> Y tile hi | lo, K-major SWIZZLE_128B, rows = seeds
+        for (int q = et; q < RT_SEEDS * 16; q += RT_EPI) {
+            const int r = q >> 4, c8 = q & 15;                 // 8 columns [8 c8, 8 c8 + 8)
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = ys[r * RT_D + 8 * c8 + e] * RT_XSCALE;
+            uint8_t* hi_blk = smem + FwdPlan::y + (c8 >> 3) * FwdPlan::Y_KB;
+            store_chunk_hilo(hi_blk, hi_blk + FwdPlan::Y_PART, r, c8 & 7, f);
+        }
+        fence_proxy_async();
+        mbar_arrive(&m->y_full);
+    };
+
+    if (warp >= 4) {
+        for (int q = et; q < RT_SEEDS * (RT_D / 4); q += RT_EPI) {
+            const int r = q / (RT_D / 4), c = q % (RT_D / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrows) v = reinterpret_cast<const float4*>(Xb + (size_t)idx_b[r] * RT_D)[c];
+            reinterpret_cast<float4*>(ys + r * RT_D)[c] = v;
+            if (rank == 0 && r < nrows) reinterpret_cast<float4*>(traj_b + ((size_t)k0 + r) * RT_D)[c] = v;
+            if (T == 0 && rank == 0 && r < nrows) reinterpret_cast<float4*>(a.C_out + ((size_t)b * Kcap + k0 + r) * RT_D)[c] = v;
+        }
+        epi_bar();
+        write_y_tile();
+    }
+
+    uint32_t it = 0;                       // tiles processed so far (every role counts alike)
+    for (int t = 0; t < T; ++t) {
+        if (warp == 0) {
+            // ================================ TMA producer ================================
+            if (lane == 0 && (!resident || t == 0)) {
+                uint32_t pit = it;
+                for (int jl = 0; jl < ntl; ++jl, ++pit) {
+                    const uint32_t st = resident ? (uint32_t)jl : pit % RT_STAGES, ph = (pit / RT_STAGES) & 1;
+                    if (!resident) mbar_wait(&m->x_empty[st], ph ^ 1);
+                    produce_tile(smem, m, &tmap, st, (j0 + jl) * RT_KEYS, b, a.B);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            // ================================= MMA issuer =================================
+            if (lane == 0) {
+                constexpr uint32_t id1 = idesc_f16_mm(RT_KEYS, RT_SEEDS, false, false);   // S^T = X . Y^T
+                constexpr uint32_t id2 = idesc_f16_mm(RT_D, RT_SEEDS, true, true);        // O^T += X^T . P^T
+                const uint32_t ybase = smem_u32(smem + FwdPlan::y), pbase = smem_u32(smem + FwdPlan::p);
+                auto gemm2 = [&](uint32_t i, int jl, bool first) {
+                    const uint32_t st = resident ? (uint32_t)jl : i % RT_STAGES;
+                    mbar_wait(&m->c_full, i & 1);
+                    tc_fence_after();
+                    const uint32_t xb = smem_u32(smem + (size_t)st * RT_STAGE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < RT_KEYS / 16; ++kk) {        // 16 keys per MMA
+                        const uint64_t a_hi = smem_desc_sw128(xb + kk * 2048, RT_KBLOCK, 1024);
+                        const uint64_t a_lo = smem_desc_sw128(xb + RT_HALF_BYTES + kk * 2048, RT_KBLOCK, 1024);
+                        const uint64_t b_hi = smem_desc_sw128(pbase + kk * 2048, RT_KBLOCK, 1024);
+                        const uint64_t b_lo = smem_desc_sw128(pbase + RT_PPART + kk * 2048, RT_KBLOCK, 1024);
+                        mma3(tmem + COL_O, a_hi, a_lo, b_hi, b_lo, id2, !(first && kk == 0));
+                    }
+                    if (!resident) mma_commit(&m->x_empty[st]);
+                    mma_commit(&m->c_free);
+                };
+                mbar_wait(&m->y_full, t & 1);
+                tc_fence_after();
+                uint32_t mit = it;
+                for (int jl = 0; jl < ntl; ++jl, ++mit) {
+                    const uint32_t st = resident ? (uint32_t)jl : mit % RT_STAGES, buf = mit & 1;
+                    if (!resident) mbar_wait(&m->x_full[st], (mit / RT_STAGES) & 1);
+                    else if (t == 0) mbar_wait(&m->x_full[st], 0);
+                    mbar_wait(&m->s_free[buf], ((mit >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t xb = smem_u32(smem + (size_t)st * RT_STAGE_BYTES);
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {               // 16 d-elements (32 B) per MMA
+                            const uint32_t xo = kb * RT_KBLOCK + ks * 32, yo = kb * FwdPlan::Y_KB + ks * 32;
+                            const uint64_t a_hi = smem_desc_sw128(xb + xo, 16, 1024);
+                            const uint64_t a_lo = smem_desc_sw128(xb + RT_HALF_BYTES + xo, 16, 1024);
+                            const uint64_t b_hi = smem_desc_sw128(ybase + yo, 16, 1024);
+                            const uint64_t b_lo = smem_desc_sw128(ybase + FwdPlan::Y_PART + yo, 16, 1024);
+                            mma3(tmem + COL_S + buf * 32, a_hi, a_lo, b_hi, b_lo, id1, (kb | ks) != 0);
+                        }
+                    mma_commit(&m->s_full[buf]);
+                    if (jl > 0) gemm2(mit - 1, jl - 1, jl == 1);
+                }
+                if (ntl > 0) { gemm2(mit - 1, ntl - 1, ntl == 1); mma_commit(&m->o_full); }
+            }
+            __syncwarp();
+        } else if (warp >= 4) {
+            // ============================= coefficients (thread = key) ==============================
+            float zlane = 0.f;
+            uint32_t eit = it;
+            for (int jl = 0; jl < ntl; ++jl, ++eit) {
+                const uint32_t buf = eit & 1;
+                mbar_wait(&m->s_full[buf], (eit >> 1) & 1);
+                tc_fence_after();
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + COL_S + buf * 32 + 16 * half, v);
+                tmem_wait_ld();
+                tc_fence_before();
+                mbar_arrive(&m->s_free[buf]);
+                const bool kvalid = (j0 + jl) * RT_KEYS + row < N;
+                float p[16];
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    const float dot = __uint_as_float(v[s]) * (1.0f / (RT_XSCALE * RT_XSCALE));
+                    const float dist = 2.0f - 2.0f * dot;                       // src/mean_shift.py:65
+                    const float pv = guard_expf((-dist / b2) * 0.5f);            // :68
+                    p[s] = kvalid ? pv : 0.f;
+                }
+                zlane += warp_transpose_sum16(p, lane);
+                uint32_t h[8], l[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split2(p[2 * e] * RT_PSCALE, p[2 * e + 1] * RT_PSCALE, h[e], l[e]);
+                mbar_wait(&m->c_free, (eit & 1) ^ 1);                           // GEMM2 of the previous tile is done with the tile
+                uint8_t* prow = smem + FwdPlan::p + (uint32_t)row * 128u;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t off = (uint32_t)(((2 * half + c) ^ (row & 7)) << 4);
+                    *reinterpret_cast<uint4*>(prow + off) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+                    *reinterpret_cast<uint4*>(prow + RT_PPART + off) = make_uint4(l[4 * c], l[4 * c + 1], l[4 * c + 2], l[4 * c + 3]);
+                }
+                fence_proxy_async();
+                mbar_arrive(&m->c_full);
+            }
+            // partial numerators O^T (lane = column d) and denominators of this CTA's key slice
+            uint32_t v[16];
+            if (ntl > 0) {
+                mbar_wait(&m->o_full, t & 1);
+                tc_fence_after();
+                tmem_ld16(tmem + lane_base + COL_O + 16 * half, v);
+                tmem_wait_ld();
+                tc_fence_before();
+            } else {
+#pragma unroll
+                for (int s = 0; s < 16; ++s) v[s] = 0u;
+            }
+#pragma unroll
+            for (int s = 0; s < 16; ++s)
+                part_o[(16 * half + s) * RT_D + row] = __uint_as_float(v[s]) * (1.0f / (RT_XSCALE * RT_PSCALE));
+            if ((lane & 1) == 0) m->zwarp[ew][lane >> 1] = zlane;
+            epi_bar();
+            if (et < RT_SEEDS) {
+                const int hz = et >> 4, sz = et & 15;
+                m->part_z[et] = (m->zwarp[4 * hz][sz] + m->zwarp[4 * hz + 1][sz]) + (m->zwarp[4 * hz + 2][sz] + m->zwarp[4 * hz + 3][sz]);
+            }
+        }
+        it += ntl;
+        cluster.sync();
+        // ---- reduce over the cluster in fixed rank order; finish the owned seeds (src/mean_shift.py:75-82)
+        float nrm = 0.f, zsum = 0.f;
+        if (owner) {
+            for (int q = 0; q < csize; ++q) zsum += cluster.map_shared_rank(m->part_z, q)[myrow];
+            const float dinv = 1.0f / zsum;
+            float n2 = 0.f;
+            for (int col = tc; col < RT_D; col += tpr) {
+                float s = 0.f;
+                for (int q = 0; q < csize; ++q) s += cluster.map_shared_rank(part_o, q)[myrow * RT_D + col];
+                const float y = ys[myrow * RT_D + col];
+                const float mm = s * dinv - y;
+                const float u = y + mm;
+                urow[rr * RT_D + col] = u;
+                n2 = fmaf(u, u, n2);
+            }
+            m->red[et] = n2;
+        }
+        if (warp >= 4) epi_bar();
+        if (owner) {
+            for (int q = 0; q < tpr; ++q) nrm += m->red[rr * tpr + q];
+            nrm = sqrtf(nrm);
+            const bool live = myrow < nrows;
+            for (int col = tc; col < RT_D; col += tpr) {
+                const float ynew = urow[rr * RT_D + col] / nrm;
+                for (int q = 0; q < csize; ++q) cluster.map_shared_rank(ys, q)[myrow * RT_D + col] = ynew;
+                if (live) {
+                    traj_b[((size_t)(t + 1) * Kcap + k0 + myrow) * RT_D + col] = ynew;
+                    if (t == T - 1) a.C_out[((size_t)b * Kcap + k0 + myrow) * RT_D + col] = ynew;
+                }
+            }
+            if (live && tc == 0) {
+                stat_b[((size_t)t * Kcap + k0 + myrow) * 2 + 0] = zsum;
+                stat_b[((size_t)t * Kcap + k0 + myrow) * 2 + 1] = nrm;
+            }
+        }
+        cluster.sync();
+        if (warp >= 4 && t + 1 < T) write_y_tile();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+}
+
+// ========================================================================================== backward
+// One reverse step t for seed r with g = dL/dy^{t+1} -- the formulas of meanshift_rows.cu:
+//   g_m = (g - (g.y^{t+1}) y^{t+1}) / ||u||,  dkappa_j = (g_m.x_j - g_m.m) D,  ds_j = kappa_j dkappa_j [lo<=a_j<=hi] / b^2,
+//   dL/dy^t = sum_j ds_j x_j,   dL/dx_j += ds_j y^t + kappa_j D g_m
+__global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const RowsArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int b = blockIdx.z;
+    const int N = a.N, T = a.T, Kcap = a.Kcap;
+    const int Kb = min(a.K[b], Kcap);
+    if (Kb <= 0 || T <= 0) {
+        // T == 0: center = X[idx]; the gradient lands on the seeds' own rows
+        if (T <= 0 && Kb > 0 && rank == 0)
+            for (int e = threadIdx.x; e < Kb * RT_D; e += RT_THREADS) {
+                const int r = e / RT_D, c = e % RT_D;
+                atomicAdd(a.gX + ((size_t)b * N + a.idx[(size_t)b * Kcap + r]) * RT_D + c, a.gC[((size_t)b * Kcap + r) * RT_D + c]);
+            }
+        return;       // uniform over the cluster
+    }
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    RtMisc* m = reinterpret_cast<RtMisc*>(smem + BwdPlan::misc);
+    float* gy = reinterpret_cast<float*>(smem + BwdPlan::gy);
+    float* part_o = reinterpret_cast<float*>(smem + BwdPlan::part_o);
+    float* gms = reinterpret_cast<float*>(smem + BwdPlan::gms);
+
+    int j0, ntl;
+    my_tiles(N, csize, rank, j0, ntl);
+    const bool resident = ntl <= RT_STAGES;
+
+    if (tid == 0) {
+        for (int s = 0; s < RT_STAGES; ++s) { mbar_init(&m->x_full[s], 1); mbar_init(&m->x_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&m->s_full[s], 1); mbar_init(&m->s_free[s], RT_EPI);
+            mbar_init(&m->gx_full[s], 1); mbar_init(&m->gx_free[s], RT_EPI);
+        }
+        mbar_init(&m->c_full, RT_EPI); mbar_init(&m->c_free, 1);
+        mbar_init(&m->o_full, 1); mbar_init(&m->y_full, RT_EPI);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) prefetch_tensormap(&tmap);
+    if (warp == 2) { tmem_alloc(&m->tmem_base, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = m->tmem_base;
+    constexpr uint32_t COL_S = 0 /* [buf][S1 32 | S2 32] */, COL_GY = 128, COL_GX = 256 /* [buf][128] */;
+
+    const float* Xb = a.X + (size_t)b * N * RT_D;
+    float* gXb = a.gX + (size_t)b * N * RT_D;
+    const float* traj_b = a.traj_in + (size_t)b * (T + 1) * Kcap * RT_D;
+    const float* stat_b = a.stat_in + (size_t)b * T * Kcap * 2;
+    const float bwv = a.bw[b];
+    const float b2 = bwv * bwv;
+
+    const int et = tid - 128, ew = warp - 4, half = (ew >> 2) & 1;
+    const int row = 32 * (ew & 3) + lane;
+    const uint32_t lane_base = (uint32_t)(32 * (ew & 3)) << 16;
+    const int rpc = (RT_SEEDS + csize - 1) / csize, tpr = RT_EPI / rpc;
+    const int rr = et / tpr, tc = et - rr * tpr;
+    const int myrow = rank * rpc + rr;
+    const bool owner = warp >= 4 && rr < rpc && myrow < RT_SEEDS;
+
+    uint32_t it = 0, itn = 0;              // tiles / iterations processed so far
+    bool x_loaded = false;
+    for (int k0 = 0; k0 < Kb; k0 += RT_SEEDS) {
+        const int nrows = min(RT_SEEDS, Kb - k0);
+        if (warp >= 4) {
+            const float* gC_b = a.gC + ((size_t)b * Kcap + k0) * RT_D;
+            for (int q = et; q < RT_SEEDS * (RT_D / 4); q += RT_EPI) {
+                const int r = q / (RT_D / 4), c = q % (RT_D / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < nrows) v = reinterpret_cast<const float4*>(gC_b + (size_t)r * RT_D)[c];
+                reinterpret_cast<float4*>(gy + r * RT_D)[c] = v;
+            }
+            epi_bar();
+        }
+        for (int t = T - 1; t >= 0; --t, ++itn) {
+            float sg = 1.f, sd = 1.f, se = 1.f;
+            if (warp == 0) {
+                if (lane == 0 && (!resident || !x_loaded)) {
+                    uint32_t pit = it;
+                    for (int jl = 0; jl < ntl; ++jl, ++pit) {
+                        const uint32_t st = resident ? (uint32_t)jl : pit % RT_STAGES, ph = (pit / RT_STAGES) & 1;
+                        if (!resident) mbar_wait(&m->x_empty[st], ph ^ 1);
+                        produce_tile(smem, m, &tmap, st, (j0 + jl) * RT_KEYS, b, a.B);
+                    }
+                }
+                __syncwarp();
+            } else if (warp == 1) {
+                if (lane == 0) {
+                    constexpr uint32_t id1 = idesc_f16_mm(RT_KEYS, RT_SEEDS, false, false);   // S1^T, S2^T
+                    constexpr uint32_t id2 = idesc_f16_mm(RT_D, RT_SEEDS, true, true);        // gy^T += X^T . ds^T
+                    constexpr uint32_t id3 = idesc_f16_mm(RT_KEYS, RT_D, false, true);        // gX = [ds|e1] . [Y;Gm]
+                    const uint32_t ygbase = smem_u32(smem + BwdPlan::yg), cbase = smem_u32(smem + BwdPlan::de);
+                    auto gemm_g = [&](uint32_t i, int jl, bool first) {
+                        const uint32_t st = resident ? (uint32_t)jl : i % RT_STAGES, buf = i & 1;
+                        mbar_wait(&m->c_full, i & 1);
+                        mbar_wait(&m->gx_free[buf], ((i >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t xb = smem_u32(smem + (size_t)st * RT_STAGE_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < RT_KEYS / 16; ++kk) {
+                            const uint64_t a_hi = smem_desc_sw128(xb + kk * 2048, RT_KBLOCK, 1024);
+                            const uint64_t a_lo = smem_desc_sw128(xb + RT_HALF_BYTES + kk * 2048, RT_KBLOCK, 1024);
+                            const uint64_t b_hi = smem_desc_sw128(cbase + kk * 2048, RT_KBLOCK, 1024);
+                            const uint64_t b_lo = smem_desc_sw128(cbase + RT_PPART + kk * 2048, RT_KBLOCK, 1024);
+                            mma3(tmem + COL_GY, a_hi, a_lo, b_hi, b_lo, id2, !(first && kk == 0));
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {               // K = 64: seeds of ds (0,1), seeds of e1 (2,3)
+                            const uint64_t a_hi = smem_desc_sw128(cbase + ks * 32, 16, 1024);
+                            const uint64_t a_lo = smem_desc_sw128(cbase + RT_PPART + ks * 32, 16, 1024);
+                            const uint64_t b_hi = smem_desc_sw128(ygbase + ks * 2048, BwdPlan::YG_KB, 1024);
+                            const uint64_t b_lo = smem_desc_sw128(ygbase + BwdPlan::YG_PART + ks * 2048, BwdPlan::YG_KB, 1024);
+                            mma3(tmem + COL_GX + buf * 128, a_hi, a_lo, b_hi, b_lo, id3, ks != 0);
+                        }
+                        if (!resident) mma_commit(&m->x_empty[st]);
+                        mma_commit(&m->c_free);
+                        mma_commit(&m->gx_full[buf]);
+                    };
+                    mbar_wait(&m->y_full, itn & 1);
+                    tc_fence_after();
+                    uint32_t mit = it;
+                    for (int jl = 0; jl < ntl; ++jl, ++mit) {
+                        const uint32_t st = resident ? (uint32_t)jl : mit % RT_STAGES, buf = mit & 1;
+                        if (!resident) mbar_wait(&m->x_full[st], (mit / RT_STAGES) & 1);
+                        else if (!x_loaded) mbar_wait(&m->x_full[st], 0);
+                        mbar_wait(&m->s_free[buf], ((mit >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t xb = smem_u32(smem + (size_t)st * RT_STAGE_BYTES);
+#pragma unroll
+                        for (int which = 0; which < 2; ++which)        // 0: y^t rows, 1: g_m rows of the stacked tile
+#pragma unroll
+                            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint32_t xo = kb * RT_KBLOCK + ks * 32;
+                                    const uint32_t yo = kb * BwdPlan::YG_KB + which * (RT_SEEDS * 128) + ks * 32;
+                                    const uint64_t a_hi = smem_desc_sw128(xb + xo, 16, 1024);
+                                    const uint64_t a_lo = smem_desc_sw128(xb + RT_HALF_BYTES + xo, 16, 1024);
+                                    const uint64_t b_hi = smem_desc_sw128(ygbase + yo, 16, 1024);
+                                    const uint64_t b_lo = smem_desc_sw128(ygbase + BwdPlan::YG_PART + yo, 16, 1024);
+                                    mma3(tmem + COL_S + buf * 64 + which * 32, a_hi, a_lo, b_hi, b_lo, id1, (kb | ks) != 0);
+                                }
+                        mma_commit(&m->s_full[buf]);
+                        if (jl > 0) gemm_g(mit - 1, jl - 1, jl == 1);
+                    }
+                    if (ntl > 0) { gemm_g(mit - 1, ntl - 1, ntl == 1); mma_commit(&m->o_full); }
+                }
+                __syncwarp();
+            } else if (warp >= 4) {
+                // ---- per-seed preparation: one warp per seed, 4 seeds per warp
+                for (int q = 0; q < 4; ++q) {
+                    const int r = ew * 4 + q;
+                    float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float gmm = 0.f, dinv = 0.f, gmx = 0.f, gbound = 0.f;
+                    if (r < nrows) {
+                        const float4 yn = reinterpret_cast<const float4*>(traj_b + ((size_t)(t + 1) * Kcap + k0 + r) * RT_D)[lane];
+                        const float zt = stat_b[((size_t)t * Kcap + k0 + r) * 2 + 0];
+                        const float nrm = stat_b[((size_t)t * Kcap + k0 + r) * 2 + 1];
+                        const float4 g = reinterpret_cast<const float4*>(gy + r * RT_D)[lane];
+                        const float gdot = warp_sum(g.x * yn.x + g.y * yn.y + g.z * yn.z + g.w * yn.w);
+                        gm.x = (g.x - gdot * yn.x) / nrm; gm.y = (g.y - gdot * yn.y) / nrm;
+                        gm.z = (g.z - gdot * yn.z) / nrm; gm.w = (g.w - gdot * yn.w) / nrm;
+                        gmm = warp_sum(gm.x * (yn.x * nrm) + gm.y * (yn.y * nrm) + gm.z * (yn.z * nrm) + gm.w * (yn.w * nrm));
+                        const float g2 = warp_sum(gm.x * gm.x + gm.y * gm.y + gm.z * gm.z + gm.w * gm.w);
+                        gmx = warp_max(fmaxf(fmaxf(fabsf(gm.x), fabsf(gm.y)), fmaxf(fabsf(gm.z), fabsf(gm.w))));
+                        dinv = 1.0f / zt;
+                        gbound = 2.0f * sqrtf(g2) * dinv / b2;
+                    }
+                    reinterpret_cast<float4*>(gms + r * RT_D)[lane] = gm;
+                    if (lane == 0) { m->gmm[r] = gmm; m->dinv[r] = dinv; m->gmax[r] = gmx; m->gbound[r] = gbound; }
+                }
+                epi_bar();
+                // ---- scales of this step (identical in every thread and every CTA of the cluster)
+                {
+                    float gmx = 0.f, bnd = 0.f, dmx = 0.f;
+                    for (int r = 0; r < RT_SEEDS; ++r) { gmx = fmaxf(gmx, m->gmax[r]); bnd = fmaxf(bnd, m->gbound[r]); dmx = fmaxf(dmx, m->dinv[r]); }
+                    const bool ok = gmx > 0.f && bnd > 0.f && isfinite(gmx) && isfinite(bnd);
+                    sg = ok ? pow2_scale_to(gmx, 8) : 1.0f;
+                    sd = ok ? pow2_scale_to(bnd, 14) : 1.0f;
+                    se = sd * RT_XSCALE / sg;
+                    if (ok && dmx * se > 32768.0f) {                   // keep e1 inside fp16: give up bits of ds instead
+                        const float shrink = pow2_scale_to(dmx * se, 15);
+                        sd *= shrink;
+                        se *= shrink;
+                    }
+                }
+                // ---- stacked operand tile [y^t rows | g_m rows], hi | lo
+                for (int q = et; q < 2 * RT_SEEDS * 16; q += RT_EPI) {
+                    const int which = q >> 9, r = (q >> 4) & 31, c8 = q & 15;
+                    float f[8];
+                    if (which == 0) {
+                        if (r < nrows) {
+                            const float4* src = reinterpret_cast<const float4*>(traj_b + ((size_t)t * Kcap + k0 + r) * RT_D + 8 * c8);
+                            const float4 u = src[0], w = src[1];
+                            f[0] = u.x * RT_XSCALE; f[1] = u.y * RT_XSCALE; f[2] = u.z * RT_XSCALE; f[3] = u.w * RT_XSCALE;
+                            f[4] = w.x * RT_XSCALE; f[5] = w.y * RT_XSCALE; f[6] = w.z * RT_XSCALE; f[7] = w.w * RT_XSCALE;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = gms[r * RT_D + 8 * c8 + e] * sg;
+                    }
+                    uint8_t* hi_blk = smem + BwdPlan::yg + (c8 >> 3) * BwdPlan::YG_KB + which * (RT_SEEDS * 128);
+                    store_chunk_hilo(hi_blk, hi_blk + BwdPlan::YG_PART, r, c8 & 7, f);
+                }
+                float gmm_r[16], dinv_r[16];
+#pragma unroll
+                for (int s = 0; s < 16; ++s) { gmm_r[s] = m->gmm[16 * half + s]; dinv_r[s] = m->dinv[16 * half + s]; }
+                epi_bar();                                             // gms (aliases the coefficient tile) is consumed
+                fence_proxy_async();
+                mbar_arrive(&m->y_full);
+
+                const float s1_mul = 1.0f / (RT_XSCALE * RT_XSCALE), s2_mul = 1.0f / (RT_XSCALE * sg);
+                const float gx_mul = 1.0f / (sd * RT_XSCALE);
+                auto flush = [&](uint32_t i, int jl) {                 // gX accumulator of tile i -> global (rows owned by this CTA)
+                    const uint32_t buf = i & 1;
+                    mbar_wait(&m->gx_full[buf], (i >> 1) & 1);
+                    tc_fence_after();
+                    uint32_t g0[32], g1[32];
+                    tmem_ld32(tmem + lane_base + COL_GX + buf * 128 + 64 * half, g0);
+                    tmem_ld32(tmem + lane_base + COL_GX + buf * 128 + 64 * half + 32, g1);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(&m->gx_free[buf]);
+                    const int key = (j0 + jl) * RT_KEYS + row;
+                    if (key < N) {
+                        float4* dst = reinterpret_cast<float4*>(gXb + (size_t)key * RT_D + 64 * half);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float4 o = __ldcg(dst + e);
+                            o.x = fmaf(__uint_as_float(g0[4 * e]), gx_mul, o.x); o.y = fmaf(__uint_as_float(g0[4 * e + 1]), gx_mul, o.y);
+                            o.z = fmaf(__uint_as_float(g0[4 * e + 2]), gx_mul, o.z); o.w = fmaf(__uint_as_float(g0[4 * e + 3]), gx_mul, o.w);
+                            dst[e] = o;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float4 o = __ldcg(dst + 8 + e);
+                            o.x = fmaf(__uint_as_float(g1[4 * e]), gx_mul, o.x); o.y = fmaf(__uint_as_float(g1[4 * e + 1]), gx_mul, o.y);
+                            o.z = fmaf(__uint_as_float(g1[4 * e + 2]), gx_mul, o.z); o.w = fmaf(__uint_as_float(g1[4 * e + 3]), gx_mul, o.w);
+                            dst[8 + e] = o;
+                        }
+                    }
+                };
+
+                uint32_t eit = it;
+                for (int jl = 0; jl < ntl; ++jl, ++eit) {
+                    const uint32_t buf = eit & 1;
+                    mbar_wait(&m->s_full[buf], (eit >> 1) & 1);
+                    tc_fence_after();
+                    uint32_t v1[16], v2[16];
+                    tmem_ld16(tmem + lane_base + COL_S + buf * 64 + 16 * half, v1);
+                    tmem_ld16(tmem + lane_base + COL_S + buf * 64 + 32 + 16 * half, v2);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(&m->s_free[buf]);
+                    const bool kvalid = (j0 + jl) * RT_KEYS + row < N;
+                    uint32_t dh[8], dl[8], eh[8], el[8];
+#pragma unroll
+                    for (int s2i = 0; s2i < 8; ++s2i) {
+                        float dsv[2], e1v[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int s = 2 * s2i + u;
+                            const float dot = __uint_as_float(v1[s]) * s1_mul;
+                            const float dist = 2.0f - 2.0f * dot;
+                            const float av = (-dist / b2) * 0.5f;
+                            const float kap = guard_expf(av);
+                            const bool inr = (av >= PRIFIT_LO) && (av <= PRIFIT_HI);
+                            const float dk = (__uint_as_float(v2[s]) * s2_mul - gmm_r[s]) * dinv_r[s];
+                            dsv[u] = (inr && kvalid) ? ((kap * dk) / b2) * sd : 0.f;
+                            e1v[u] = kvalid ? (kap * dinv_r[s]) * se : 0.f;
+                        }
+                        split2(dsv[0], dsv[1], dh[s2i], dl[s2i]);
+                        split2(e1v[0], e1v[1], eh[s2i], el[s2i]);
+                    }
+                    mbar_wait(&m->c_free, (eit & 1) ^ 1);
+                    uint8_t* crow = smem + BwdPlan::de + (uint32_t)row * 128u;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint32_t od = (uint32_t)(((2 * half + c) ^ (row & 7)) << 4);          // ds: seeds 16 half + 8 c ..
+                        const uint32_t oe = (uint32_t)(((4 + 2 * half + c) ^ (row & 7)) << 4);      // e1: K index 32 + ..
+                        *reinterpret_cast<uint4*>(crow + od) = make_uint4(dh[4 * c], dh[4 * c + 1], dh[4 * c + 2], dh[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(crow + RT_PPART + od) = make_uint4(dl[4 * c], dl[4 * c + 1], dl[4 * c + 2], dl[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(crow + oe) = make_uint4(eh[4 * c], eh[4 * c + 1], eh[4 * c + 2], eh[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(crow + RT_PPART + oe) = make_uint4(el[4 * c], el[4 * c + 1], el[4 * c + 2], el[4 * c + 3]);
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(&m->c_full);
+                    if (jl > 0) flush(eit - 1, jl - 1);
+                }
+                if (ntl > 0) flush(eit - 1, ntl - 1);
+                // partial dL/dy^t of this CTA's keys (lane = column d); the coefficient tile is dead now
+                uint32_t v[16];
+                if (ntl > 0) {
+                    mbar_wait(&m->o_full, itn & 1);
+                    tc_fence_after();
+                    tmem_ld16(tmem + lane_base + COL_GY + 16 * half, v);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 16; ++s) v[s] = 0u;
+                }
+                epi_bar();                                             // all flush() loads of this CTA are done with TMEM
+#pragma unroll
+                for (int s = 0; s < 16; ++s) part_o[(16 * half + s) * RT_D + row] = __uint_as_float(v[s]) * gx_mul;
+            }
+            it += ntl;
+            x_loaded = true;
+            cluster.sync();
+            if (owner) {
+                for (int col = tc; col < RT_D; col += tpr) {
+                    float s = 0.f;
+                    for (int q = 0; q < csize; ++q) s += cluster.map_shared_rank(part_o, q)[myrow * RT_D + col];
+                    for (int q = 0; q < csize; ++q) cluster.map_shared_rank(gy, q)[myrow * RT_D + col] = s;
+                }
+            }
+            cluster.sync();
+        }
+        // dL/dy^0 lands on the seed's own row of X (new_X = X.clone(), gather by idx)
+        __threadfence();
+        cluster.sync();
+        if (owner && myrow < nrows) {
+            const int src = a.idx[(size_t)b * Kcap + k0 + myrow];
+            for (int col = tc; col < RT_D; col += tpr) atomicAdd(gXb + (size_t)src * RT_D + col, gy[myrow * RT_D + col]);
+        }
+        __threadfence();
+        cluster.sync();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+int pick_cluster(int N) {
+    const int nt = (N + RT_KEYS - 1) / RT_KEYS;
+    int csize = RT_MAXC;
+    if (const char* e = getenv("PRIFIT_ROWS_CLUSTER")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= RT_MAXC) csize = v;
+    }
+    while (csize > 1 && nt < csize) --csize;
+    return csize;
+}
+
+template <typename Kern>
+int launch_rows_tc(Kern kern, size_t smem, int csize, dim3 grid, const CUtensorMap& map, const RowsArgs& a, cudaStream_t st) {
+    PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(RT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    PF_CUDA(cudaLaunchKernelEx(&cfg, kern, map, a));
+    return 0;
+}
+
+}  // namespace
+
+size_t prifit_rows_tc_workspace_bytes(int B, int N) { return (size_t)2 * B * N * RT_D * sizeof(__half) + 256; }
+
+int prifit_rows_tc_fwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K, int B, int N, int T, int Kcap,
+                       float* traj, float* stat, float* C_out, void* ws, cudaStream_t st) {
+    __half* Xs = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    CUtensorMap map;
+    int rc = prifit_tc_split_rows(X, Xs, B, N, &map, st);
+    if (rc) return rc;
+    RowsArgs a = {};
+    a.X = X; a.bw = bw; a.idx = idx; a.K = K; a.N = N; a.B = B; a.T = T; a.Kcap = Kcap;
+    a.traj = traj; a.stat = stat; a.C_out = C_out;
+    const int csize = pick_cluster(N);
+    return launch_rows_tc(rows_tc_fwd_kernel, 1024 + FwdPlan::total, csize, dim3(csize, (Kcap + RT_SEEDS - 1) / RT_SEEDS, B), map, a, st);
+}
+
+int prifit_rows_tc_bwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K, const float* traj,
+                       const float* stat, const float* gC, int B, int N, int T, int Kcap, float* gX, void* ws, cudaStream_t st) {
+    __half* Xs = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    CUtensorMap map;
+    int rc = prifit_tc_split_rows(X, Xs, B, N, &map, st);
+    if (rc) return rc;
+    RowsArgs a = {};
+    a.X = X; a.bw = bw; a.idx = idx; a.K = K; a.N = N; a.B = B; a.T = T; a.Kcap = Kcap;
+    a.traj_in = traj; a.stat_in = stat; a.gC = gC; a.gX = gX;
+    const int csize = pick_cluster(N);
+    return launch_rows_tc(rows_tc_bwd_kernel, 1024 + BwdPlan::total, csize, dim3(csize, 1, B), map, a, st);
+}

@@ -12,6 +12,7 @@ torch is used for device memory, streams and autograd plumbing only; every compu
 hand-written kernel behind `_lib.call`.
 """
 import ctypes
+import os
 
 import torch
 
@@ -22,6 +23,12 @@ MS_FP32_SIMT = _lib.MS_FP32_SIMT
 
 # default mean-shift engine for the full N-seed pass (the K differentiable seeds are always fp32)
 DEFAULT_ENGINE = MS_TF32_TCGEN05
+
+# engine of the K differentiable seeds' trajectories (forward and backward): split-fp16 tensor cores
+# (fp32-class) or fp32 CUDA cores.  PRIFIT_ROWS_ENGINE=1 in the environment selects the latter.
+ROWS_SPLIT_TCGEN05 = _lib.ROWS_SPLIT_TCGEN05
+ROWS_FP32_SIMT = _lib.ROWS_FP32_SIMT
+DEFAULT_ROWS_ENGINE = int(os.environ.get("PRIFIT_ROWS_ENGINE", ROWS_SPLIT_TCGEN05))
 
 # bench.py sets this to a list to collect (start, end) CUDA events around the all-seed mean-shift kernel
 TIMING = None
@@ -128,22 +135,35 @@ def nms(newX, bw, kcap):
     return idx, K, labels, nlab
 
 
-def rows_fwd(X, bw, idx, K, iterations, kcap):
+def _rows_engine(engine, d):
+    engine = DEFAULT_ROWS_ENGINE if engine is None else engine
+    if engine == ROWS_SPLIT_TCGEN05 and d != 128:
+        engine = ROWS_FP32_SIMT        # the tensor-core kernels are specialised for d = 128
+    return engine
+
+
+def rows_fwd(X, bw, idx, K, iterations, kcap, engine=None):
     B, N, d = X.shape
     dev = X.device
     T = int(iterations)
+    engine = _rows_engine(engine, d)
+    nbytes = _lib.load().prifit_meanshift_rows_workspace_bytes(B, N, d, engine)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     traj = torch.empty(B, T + 1, kcap, d, dtype=torch.float32, device=dev)
     stat = torch.empty(B, max(T, 1), kcap, 2, dtype=torch.float32, device=dev)
     C = torch.empty(B, kcap, d, dtype=torch.float32, device=dev)
     _lib.call("prifit_meanshift_rows_fwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), B, N, d, T, kcap,
-              _ptr(traj), _ptr(stat), _ptr(C), _stream())
+              _ptr(traj), _ptr(stat), _ptr(C), engine, _ptr(ws), nbytes, _stream())
     return traj, stat, C
 
 
-def rows_bwd(X, bw, idx, K, traj, stat, gC, gX_inout, iterations, kcap):
+def rows_bwd(X, bw, idx, K, traj, stat, gC, gX_inout, iterations, kcap, engine=None):
     B, N, d = X.shape
+    engine = _rows_engine(engine, d)
+    nbytes = _lib.load().prifit_meanshift_rows_workspace_bytes(B, N, d, engine)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=X.device)
     _lib.call("prifit_meanshift_rows_bwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), _ptr(traj), _ptr(stat), _ptr(gC),
-              B, N, d, int(iterations), kcap, _ptr(gX_inout), _stream())
+              B, N, d, int(iterations), kcap, _ptr(gX_inout), engine, _ptr(ws), nbytes, _stream())
 
 
 def membership_fwd(C, X, bw, K):
@@ -236,20 +256,20 @@ class SeedCentres(torch.autograd.Function):
     Backward = autograd through the T iterations of mean_shift_ restricted to those rows."""
 
     @staticmethod
-    def forward(ctx, X, bw, idx, K, iterations):
+    def forward(ctx, X, bw, idx, K, iterations, engine=None):
         X = _chk(X)
         kcap = idx.shape[1]
-        traj, stat, C = rows_fwd(X, bw, idx, K, iterations, kcap)
+        traj, stat, C = rows_fwd(X, bw, idx, K, iterations, kcap, engine)
         ctx.save_for_backward(X, bw, idx, K, traj, stat)
-        ctx.iterations, ctx.kcap = int(iterations), kcap
+        ctx.iterations, ctx.kcap, ctx.engine = int(iterations), kcap, engine
         return C
 
     @staticmethod
     def backward(ctx, gC):
         X, bw, idx, K, traj, stat = ctx.saved_tensors
         gX = torch.zeros_like(X)
-        rows_bwd(X, bw, idx, K, traj, stat, gC.contiguous(), gX, ctx.iterations, ctx.kcap)
-        return gX, None, None, None, None
+        rows_bwd(X, bw, idx, K, traj, stat, gC.contiguous(), gX, ctx.iterations, ctx.kcap, ctx.engine)
+        return gX, None, None, None, None, None
 
 
 class Membership(torch.autograd.Function):

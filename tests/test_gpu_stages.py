@@ -170,7 +170,11 @@ def test_nms_many_modes_reports_count(cuda):
 
 
 # --------------------------------------------------------------------------- K-row trajectories fwd/bwd
-def test_rows_fwd_golden(cuda, golden_dir):
+ROWS_ENGINES = [0, 1]     # PRIFIT_ROWS_SPLIT_TCGEN05, PRIFIT_ROWS_FP32_SIMT
+
+
+@pytest.mark.parametrize("engine", ROWS_ENGINES)
+def test_rows_fwd_golden(cuda, golden_dir, engine):
     from prifit_b200 import ops
 
     g = _g(golden_dir, "stages")
@@ -180,14 +184,15 @@ def test_rows_fwd_golden(cuda, golden_dir):
     idx = torch.full((1, 32), -1, dtype=torch.int32, device=cuda)
     idx[0, :k] = torch.from_numpy(g["ids"]).to(cuda)
     K = torch.tensor([k], dtype=torch.int32, device=cuda)
-    traj, stat, C = ops.rows_fwd(X, bw, idx, K, 6, 32)
+    traj, stat, C = ops.rows_fwd(X, bw, idx, K, 6, 32, engine)
     assert rel_err(C[0, :k], g["newX"][g["ids"]]) < 1e-5
     assert float(C[0, k:].abs().max()) == 0.0
     assert rel_err(traj[0, 0, :k], g["X"][g["ids"]]) == 0.0
 
 
-@pytest.mark.parametrize("n,k,T,kcap", [(300, 5, 3, 32), (1100, 40, 2, 64), (128, 1, 4, 32)])
-def test_rows_fwd_bwd_vs_oracle_autograd(cuda, n, k, T, kcap):
+@pytest.mark.parametrize("engine", ROWS_ENGINES)
+@pytest.mark.parametrize("n,k,T,kcap", [(300, 5, 3, 32), (1100, 40, 2, 64), (128, 1, 4, 32), (700, 33, 3, 64)])
+def test_rows_fwd_bwd_vs_oracle_autograd(cuda, n, k, T, kcap, engine):
     """dL/dX of L = sum(gC * new_X[idx]) through T dense iterations (fp64 autograd of the oracle)."""
     from prifit_b200 import ops
 
@@ -207,12 +212,35 @@ def test_rows_fwd_bwd_vs_oracle_autograd(cuda, n, k, T, kcap):
     idx = torch.full((2, kcap), -1, dtype=torch.int32)
     idx[:, :k] = ids.int()
     Xc = X.to(cuda).requires_grad_(True)
-    C = ops.SeedCentres.apply(Xc, bw.to(cuda), idx.to(cuda), torch.tensor([k, k], dtype=torch.int32, device=cuda), T)
+    C = ops.SeedCentres.apply(Xc, bw.to(cuda), idx.to(cuda), torch.tensor([k, k], dtype=torch.int32, device=cuda), T, engine)
     gpad = torch.zeros(2, kcap, 128)
     gpad[:, :k] = gC
     (C * gpad.to(cuda)).sum().backward()
     assert rel_err(C[:, :k], ref_C) < 1e-5
     assert rel_err(Xc.grad, Xd.grad) < 1e-4
+
+
+@pytest.mark.parametrize("n,kc,T", [(2048, 16, 10), (1500, 9, 10), (10000, 40, 10)])
+def test_rows_engines_agree_on_planted_shapes(cuda, n, kc, T):
+    """cfg2 / cfg4-like planted shapes: tensor-core (split-fp16) trajectories and their backward against the
+    fp32 CUDA-core engine, at the narrow bandwidths real shapes have (1/b^2 amplifies dot-product error)."""
+    from prifit_b200 import ops, pipeline, synthetic
+
+    E, _, _ = synthetic.planted_shapes(2, n_points=n, n_clusters=kc, seed=5)
+    X = ops.normalize_fwd(E.to(cuda))
+    res = pipeline.cluster_batch(X, n, 0.05 if n < 5000 else 0.01, T, 50)
+    kcap = res.kcap
+    g = torch.Generator().manual_seed(2)
+    gC = torch.randn(2, kcap, 128, generator=g).to(cuda)
+    outs = []
+    for engine in ROWS_ENGINES:
+        Xc = X.clone().requires_grad_(True)
+        C = ops.SeedCentres.apply(Xc, res.bw, res.idx, res.K, T, engine)
+        (C * gC).sum().backward()
+        outs.append((C.detach(), Xc.grad))
+    assert min(res.K_host) >= 2
+    assert rel_err(outs[0][0], outs[1][0]) < 2e-6
+    assert rel_err(outs[0][1], outs[1][1]) < 1e-4
 
 
 # ----------------------------------------------------------------------------------------- membership
