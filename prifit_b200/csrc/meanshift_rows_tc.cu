@@ -54,6 +54,7 @@ constexpr uint32_t RT_PPART = RT_KEYS * 128;               // coefficient tile [
 constexpr float RT_XSCALE = 256.0f;                        // x, y pre-scale (matches split_half_kernel of gram_tc.cu)
 constexpr float RT_PSCALE = 16384.0f;                      // p pre-scale
 constexpr int RT_MAXC = 8;
+constexpr float RT_LOG2E = 1.4426950408889634f;
 
 // ---- shared-memory plans (offsets from a 1024-aligned base; every MMA tile is 1024-aligned)
 struct FwdPlan {
@@ -119,6 +120,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // (a, b) -> packed f16 pairs hi, lo with a = hi.x + lo.x (22 significant bits), likewise b
@@ -173,12 +177,32 @@ __device__ __forceinline__ void store_chunk_hilo(uint8_t* hi_blk, uint8_t* lo_bl
     *reinterpret_cast<uint4*>(lo_blk + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+__device__ __forceinline__ void warp_sum4(float (&v)[4]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+}
+__device__ __forceinline__ void warp_max4(float (&v)[4]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = fmaxf(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
+}
+
 // power of two 2^e with v * 2^e in [2^(top-1), 2^top)   (v > 0, finite)
 __device__ __forceinline__ float pow2_scale_to(float v, int top) {
     int ex;
     frexpf(v, &ex);                   // v = m 2^ex, m in [0.5, 1)
     return ldexpf(1.0f, top - ex);
 }
+
+// Optional phase timeline (diagnostics): epilogue thread 0 of CTA (0, 0, 0) records (phase id, clock64).
+__device__ long long g_rt_dbg[8192];
+__device__ int g_rt_dbg_n;
+#define RT_MARK(id)                                                                        \
+    do { if (a.dbg && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 128) {          \
+             const int n__ = g_rt_dbg_n; if (n__ < 4090) { g_rt_dbg[2 * n__] = (id); g_rt_dbg[2 * n__ + 1] = clock64(); g_rt_dbg_n = n__ + 1; } } } while (0)
 
 struct RowsArgs {
     const float* X; const float* bw; const int32_t* idx; const int32_t* K;
@@ -187,6 +211,7 @@ struct RowsArgs {
     float* traj; float* stat; float* C_out;
     // backward
     const float* traj_in; const float* stat_in; const float* gC; float* gX;
+    int dbg;
 };
 
 // key tiles of this CTA: [j0, j0 + ntl)
@@ -261,9 +286,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
     const int32_t* idx_b = a.idx + (size_t)b * Kcap + k0;
     const float bwv = a.bw[b];
     const float b2 = bwv * bwv;
+    const float a_mul = (1.0f / b2) * (1.0f / (RT_XSCALE * RT_XSCALE));
 
     // epilogue-thread coordinates (valid for warps >= 4)
     const int et = tid - 128, ew = warp - 4, half = (ew >> 2) & 1;
+    const bool seeds_live = 16 * half < nrows;                     // any real seed among this thread's 16 columns
     const int row = 32 * (ew & 3) + lane;                          // TMEM lane: key within the tile / column d of O^T
     const uint32_t lane_base = (uint32_t)(32 * (ew & 3)) << 16;
     // reduce-phase ownership: this CTA finishes seeds [rank * rpc, rank * rpc + rpc)
@@ -367,6 +394,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
             for (int jl = 0; jl < ntl; ++jl, ++eit) {
                 const uint32_t buf = eit & 1;
                 mbar_wait(&m->s_full[buf], (eit >> 1) & 1);
+                RT_MARK(4);
                 tc_fence_after();
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + COL_S + buf * 32 + 16 * half, v);
@@ -375,18 +403,24 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                 mbar_arrive(&m->s_free[buf]);
                 const bool kvalid = (j0 + jl) * RT_KEYS + row < N;
                 float p[16];
+                if (kvalid && seeds_live) {
 #pragma unroll
-                for (int s = 0; s < 16; ++s) {
-                    const float dot = __uint_as_float(v[s]) * (1.0f / (RT_XSCALE * RT_XSCALE));
-                    const float dist = 2.0f - 2.0f * dot;                       // src/mean_shift.py:65
-                    const float pv = guard_expf((-dist / b2) * 0.5f);            // :68
-                    p[s] = kvalid ? pv : 0.f;
+                    for (int s = 0; s < 16; ++s) {
+                        // a = -(2 - 2 dot) / b^2 / 2 = (dot - 1) / b^2 with dot = S 2^-16   (src/mean_shift.py:65,68)
+                        const float av = (__uint_as_float(v[s]) - RT_XSCALE * RT_XSCALE) * a_mul;
+                        p[s] = ex2_approx(fminf(fmaxf(av, PRIFIT_LO), PRIFIT_HI) * RT_LOG2E);
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 16; ++s) p[s] = 0.f;
                 }
                 zlane += warp_transpose_sum16(p, lane);
                 uint32_t h[8], l[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) split2(p[2 * e] * RT_PSCALE, p[2 * e + 1] * RT_PSCALE, h[e], l[e]);
+                RT_MARK(5);
                 mbar_wait(&m->c_free, (eit & 1) ^ 1);                           // GEMM2 of the previous tile is done with the tile
+                RT_MARK(6);
                 uint8_t* prow = smem + FwdPlan::p + (uint32_t)row * 128u;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
@@ -396,6 +430,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                 }
                 fence_proxy_async();
                 mbar_arrive(&m->c_full);
+                RT_MARK(7);
             }
             // partial numerators O^T (lane = column d) and denominators of this CTA's key slice
             uint32_t v[16];
@@ -418,18 +453,27 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                 const int hz = et >> 4, sz = et & 15;
                 m->part_z[et] = (m->zwarp[4 * hz][sz] + m->zwarp[4 * hz + 1][sz]) + (m->zwarp[4 * hz + 2][sz] + m->zwarp[4 * hz + 3][sz]);
             }
+            RT_MARK(11);
         }
         it += ntl;
         cluster.sync();
+        RT_MARK(12);
         // ---- reduce over the cluster in fixed rank order; finish the owned seeds (src/mean_shift.py:75-82)
         float nrm = 0.f, zsum = 0.f;
         if (owner) {
-            for (int q = 0; q < csize; ++q) zsum += cluster.map_shared_rank(m->part_z, q)[myrow];
+            float zq[RT_MAXC];
+#pragma unroll
+            for (int q = 0; q < RT_MAXC; ++q) zq[q] = q < csize ? cluster.map_shared_rank(m->part_z, q)[myrow] : 0.f;
+#pragma unroll
+            for (int q = 0; q < RT_MAXC; ++q) zsum += zq[q];
             const float dinv = 1.0f / zsum;
             float n2 = 0.f;
             for (int col = tc; col < RT_D; col += tpr) {
-                float s = 0.f;
-                for (int q = 0; q < csize; ++q) s += cluster.map_shared_rank(part_o, q)[myrow * RT_D + col];
+                float oq[RT_MAXC], s = 0.f;
+#pragma unroll
+                for (int q = 0; q < RT_MAXC; ++q) oq[q] = q < csize ? cluster.map_shared_rank(part_o, q)[myrow * RT_D + col] : 0.f;
+#pragma unroll
+                for (int q = 0; q < RT_MAXC; ++q) s += oq[q];
                 const float y = ys[myrow * RT_D + col];
                 const float mm = s * dinv - y;
                 const float u = y + mm;
@@ -456,8 +500,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                 stat_b[((size_t)t * Kcap + k0 + myrow) * 2 + 1] = nrm;
             }
         }
+        RT_MARK(13);
         cluster.sync();
+        RT_MARK(14);
         if (warp >= 4 && t + 1 < T) write_y_tile();
+        RT_MARK(3);
     }
     tc_fence_before();
     __syncthreads();
@@ -520,6 +567,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
     const float* stat_b = a.stat_in + (size_t)b * T * Kcap * 2;
     const float bwv = a.bw[b];
     const float b2 = bwv * bwv;
+    const float a_mul = (1.0f / b2) * (1.0f / (RT_XSCALE * RT_XSCALE));
 
     const int et = tid - 128, ew = warp - 4, half = (ew >> 2) & 1;
     const int row = 32 * (ew & 3) + lane;
@@ -618,29 +666,65 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                 }
                 __syncwarp();
             } else if (warp >= 4) {
-                // ---- per-seed preparation: one warp per seed, 4 seeds per warp
+                RT_MARK(1);
+                // ---- per-seed preparation: one warp per seed, 4 seeds per warp; every global load of the step is
+                //      issued before the first dependent instruction
+                float4 yn[4], g4[4], gm[4];
+                float zt[4], nr[4];
+#pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int r = ew * 4 + q;
-                    float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float gmm = 0.f, dinv = 0.f, gmx = 0.f, gbound = 0.f;
+                    yn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    zt[q] = 1.f; nr[q] = 1.f;
                     if (r < nrows) {
-                        const float4 yn = reinterpret_cast<const float4*>(traj_b + ((size_t)(t + 1) * Kcap + k0 + r) * RT_D)[lane];
-                        const float zt = stat_b[((size_t)t * Kcap + k0 + r) * 2 + 0];
-                        const float nrm = stat_b[((size_t)t * Kcap + k0 + r) * 2 + 1];
-                        const float4 g = reinterpret_cast<const float4*>(gy + r * RT_D)[lane];
-                        const float gdot = warp_sum(g.x * yn.x + g.y * yn.y + g.z * yn.z + g.w * yn.w);
-                        gm.x = (g.x - gdot * yn.x) / nrm; gm.y = (g.y - gdot * yn.y) / nrm;
-                        gm.z = (g.z - gdot * yn.z) / nrm; gm.w = (g.w - gdot * yn.w) / nrm;
-                        gmm = warp_sum(gm.x * (yn.x * nrm) + gm.y * (yn.y * nrm) + gm.z * (yn.z * nrm) + gm.w * (yn.w * nrm));
-                        const float g2 = warp_sum(gm.x * gm.x + gm.y * gm.y + gm.z * gm.z + gm.w * gm.w);
-                        gmx = warp_max(fmaxf(fmaxf(fabsf(gm.x), fabsf(gm.y)), fmaxf(fabsf(gm.z), fabsf(gm.w))));
-                        dinv = 1.0f / zt;
-                        gbound = 2.0f * sqrtf(g2) * dinv / b2;
+                        yn[q] = __ldg(reinterpret_cast<const float4*>(traj_b + ((size_t)(t + 1) * Kcap + k0 + r) * RT_D) + lane);
+                        const float2 st2 = __ldg(reinterpret_cast<const float2*>(stat_b + ((size_t)t * Kcap + k0 + r) * 2));
+                        zt[q] = st2.x; nr[q] = st2.y;
                     }
-                    reinterpret_cast<float4*>(gms + r * RT_D)[lane] = gm;
-                    if (lane == 0) { m->gmm[r] = gmm; m->dinv[r] = dinv; m->gmax[r] = gmx; m->gbound[r] = gbound; }
+                }
+                float4 ytile[2][2];                                    // this thread's two chunks of the y^t rows
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int q = et + RT_EPI * i, r = (q >> 4) & 31, c8 = q & 15;
+                    ytile[i][0] = ytile[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < nrows) {
+                        const float4* src = reinterpret_cast<const float4*>(traj_b + ((size_t)t * Kcap + k0 + r) * RT_D + 8 * c8);
+                        ytile[i][0] = __ldg(src); ytile[i][1] = __ldg(src + 1);
+                    }
+                }
+                float red4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    g4[q] = reinterpret_cast<const float4*>(gy + (ew * 4 + q) * RT_D)[lane];
+                    red4[q] = g4[q].x * yn[q].x + g4[q].y * yn[q].y + g4[q].z * yn[q].z + g4[q].w * yn[q].w;
+                }
+                warp_sum4(red4);
+                float gmm4[4], g24[4], gmx4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float gdot = red4[q], nrm = nr[q];
+                    gm[q].x = (g4[q].x - gdot * yn[q].x) / nrm; gm[q].y = (g4[q].y - gdot * yn[q].y) / nrm;
+                    gm[q].z = (g4[q].z - gdot * yn[q].z) / nrm; gm[q].w = (g4[q].w - gdot * yn[q].w) / nrm;
+                    gmm4[q] = gm[q].x * (yn[q].x * nrm) + gm[q].y * (yn[q].y * nrm) + gm[q].z * (yn[q].z * nrm) + gm[q].w * (yn[q].w * nrm);
+                    g24[q] = gm[q].x * gm[q].x + gm[q].y * gm[q].y + gm[q].z * gm[q].z + gm[q].w * gm[q].w;
+                    gmx4[q] = fmaxf(fmaxf(fabsf(gm[q].x), fabsf(gm[q].y)), fmaxf(fabsf(gm[q].z), fabsf(gm[q].w)));
+                }
+                warp_sum4(gmm4);
+                warp_sum4(g24);
+                warp_max4(gmx4);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = ew * 4 + q;
+                    const bool rl = r < nrows;
+                    reinterpret_cast<float4*>(gms + r * RT_D)[lane] = rl ? gm[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lane == 0) {
+                        const float dinv = rl ? 1.0f / zt[q] : 0.f;
+                        m->gmm[r] = rl ? gmm4[q] : 0.f; m->dinv[r] = dinv; m->gmax[r] = rl ? gmx4[q] : 0.f;
+                        m->gbound[r] = rl ? 2.0f * sqrtf(g24[q]) * dinv / b2 : 0.f;
+                    }
                 }
                 epi_bar();
+                RT_MARK(2);
                 // ---- scales of this step (identical in every thread and every CTA of the cluster)
                 {
                     float gmx = 0.f, bnd = 0.f, dmx = 0.f;
@@ -656,19 +740,15 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                     }
                 }
                 // ---- stacked operand tile [y^t rows | g_m rows], hi | lo
-                for (int q = et; q < 2 * RT_SEEDS * 16; q += RT_EPI) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = et + RT_EPI * i;
                     const int which = q >> 9, r = (q >> 4) & 31, c8 = q & 15;
                     float f[8];
-                    if (which == 0) {
-                        if (r < nrows) {
-                            const float4* src = reinterpret_cast<const float4*>(traj_b + ((size_t)t * Kcap + k0 + r) * RT_D + 8 * c8);
-                            const float4 u = src[0], w = src[1];
-                            f[0] = u.x * RT_XSCALE; f[1] = u.y * RT_XSCALE; f[2] = u.z * RT_XSCALE; f[3] = u.w * RT_XSCALE;
-                            f[4] = w.x * RT_XSCALE; f[5] = w.y * RT_XSCALE; f[6] = w.z * RT_XSCALE; f[7] = w.w * RT_XSCALE;
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = 0.f;
-                        }
+                    if (i < 2) {
+                        const float4 u = ytile[i & 1][0], w = ytile[i & 1][1];
+                        f[0] = u.x * RT_XSCALE; f[1] = u.y * RT_XSCALE; f[2] = u.z * RT_XSCALE; f[3] = u.w * RT_XSCALE;
+                        f[4] = w.x * RT_XSCALE; f[5] = w.y * RT_XSCALE; f[6] = w.z * RT_XSCALE; f[7] = w.w * RT_XSCALE;
                     } else {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] = gms[r * RT_D + 8 * c8 + e] * sg;
@@ -682,8 +762,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                 epi_bar();                                             // gms (aliases the coefficient tile) is consumed
                 fence_proxy_async();
                 mbar_arrive(&m->y_full);
+                RT_MARK(3);
 
-                const float s1_mul = 1.0f / (RT_XSCALE * RT_XSCALE), s2_mul = 1.0f / (RT_XSCALE * sg);
+                const float s2_mul = 1.0f / (RT_XSCALE * sg), ds_mul = sd / b2;
                 const float gx_mul = 1.0f / (sd * RT_XSCALE);
                 auto flush = [&](uint32_t i, int jl) {                 // gX accumulator of tile i -> global (rows owned by this CTA)
                     const uint32_t buf = i & 1;
@@ -697,21 +778,16 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                     mbar_arrive(&m->gx_free[buf]);
                     const int key = (j0 + jl) * RT_KEYS + row;
                     if (key < N) {
-                        float4* dst = reinterpret_cast<float4*>(gXb + (size_t)key * RT_D + 64 * half);
+                        // fire-and-forget vector reductions: no read round trip on the critical path
+                        float* dst = gXb + (size_t)key * RT_D + 64 * half;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float4 o = __ldcg(dst + e);
-                            o.x = fmaf(__uint_as_float(g0[4 * e]), gx_mul, o.x); o.y = fmaf(__uint_as_float(g0[4 * e + 1]), gx_mul, o.y);
-                            o.z = fmaf(__uint_as_float(g0[4 * e + 2]), gx_mul, o.z); o.w = fmaf(__uint_as_float(g0[4 * e + 3]), gx_mul, o.w);
-                            dst[e] = o;
-                        }
+                        for (int e = 0; e < 8; ++e)
+                            red_add_v4(dst + 4 * e, __uint_as_float(g0[4 * e]) * gx_mul, __uint_as_float(g0[4 * e + 1]) * gx_mul,
+                                       __uint_as_float(g0[4 * e + 2]) * gx_mul, __uint_as_float(g0[4 * e + 3]) * gx_mul);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float4 o = __ldcg(dst + 8 + e);
-                            o.x = fmaf(__uint_as_float(g1[4 * e]), gx_mul, o.x); o.y = fmaf(__uint_as_float(g1[4 * e + 1]), gx_mul, o.y);
-                            o.z = fmaf(__uint_as_float(g1[4 * e + 2]), gx_mul, o.z); o.w = fmaf(__uint_as_float(g1[4 * e + 3]), gx_mul, o.w);
-                            dst[8 + e] = o;
-                        }
+                        for (int e = 0; e < 8; ++e)
+                            red_add_v4(dst + 32 + 4 * e, __uint_as_float(g1[4 * e]) * gx_mul, __uint_as_float(g1[4 * e + 1]) * gx_mul,
+                                       __uint_as_float(g1[4 * e + 2]) * gx_mul, __uint_as_float(g1[4 * e + 3]) * gx_mul);
                     }
                 };
 
@@ -719,6 +795,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                 for (int jl = 0; jl < ntl; ++jl, ++eit) {
                     const uint32_t buf = eit & 1;
                     mbar_wait(&m->s_full[buf], (eit >> 1) & 1);
+                    RT_MARK(4);
                     tc_fence_after();
                     uint32_t v1[16], v2[16];
                     tmem_ld16(tmem + lane_base + COL_S + buf * 64 + 16 * half, v1);
@@ -726,7 +803,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                     tmem_wait_ld();
                     tc_fence_before();
                     mbar_arrive(&m->s_free[buf]);
-                    const bool kvalid = (j0 + jl) * RT_KEYS + row < N;
+                    const bool live = (j0 + jl) * RT_KEYS + row < N && 16 * half < nrows;
                     uint32_t dh[8], dl[8], eh[8], el[8];
 #pragma unroll
                     for (int s2i = 0; s2i < 8; ++s2i) {
@@ -734,19 +811,19 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
                             const int s = 2 * s2i + u;
-                            const float dot = __uint_as_float(v1[s]) * s1_mul;
-                            const float dist = 2.0f - 2.0f * dot;
-                            const float av = (-dist / b2) * 0.5f;
-                            const float kap = guard_expf(av);
+                            const float av = (__uint_as_float(v1[s]) - RT_XSCALE * RT_XSCALE) * a_mul;    // (dot - 1) / b^2
+                            const float kap = ex2_approx(fminf(fmaxf(av, PRIFIT_LO), PRIFIT_HI) * RT_LOG2E);
                             const bool inr = (av >= PRIFIT_LO) && (av <= PRIFIT_HI);
                             const float dk = (__uint_as_float(v2[s]) * s2_mul - gmm_r[s]) * dinv_r[s];
-                            dsv[u] = (inr && kvalid) ? ((kap * dk) / b2) * sd : 0.f;
-                            e1v[u] = kvalid ? (kap * dinv_r[s]) * se : 0.f;
+                            dsv[u] = (inr && live) ? (kap * dk) * ds_mul : 0.f;
+                            e1v[u] = live ? (kap * dinv_r[s]) * se : 0.f;
                         }
                         split2(dsv[0], dsv[1], dh[s2i], dl[s2i]);
                         split2(e1v[0], e1v[1], eh[s2i], el[s2i]);
                     }
+                    RT_MARK(5);
                     mbar_wait(&m->c_free, (eit & 1) ^ 1);
+                    RT_MARK(6);
                     uint8_t* crow = smem + BwdPlan::de + (uint32_t)row * 128u;
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -759,9 +836,12 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                     }
                     fence_proxy_async();
                     mbar_arrive(&m->c_full);
+                    RT_MARK(7);
                     if (jl > 0) flush(eit - 1, jl - 1);
+                    RT_MARK(8);
                 }
                 if (ntl > 0) flush(eit - 1, ntl - 1);
+                RT_MARK(9);
                 // partial dL/dy^t of this CTA's keys (lane = column d); the coefficient tile is dead now
                 uint32_t v[16];
                 if (ntl > 0) {
@@ -774,21 +854,29 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
 #pragma unroll
                     for (int s = 0; s < 16; ++s) v[s] = 0u;
                 }
+                RT_MARK(10);
                 epi_bar();                                             // all flush() loads of this CTA are done with TMEM
 #pragma unroll
                 for (int s = 0; s < 16; ++s) part_o[(16 * half + s) * RT_D + row] = __uint_as_float(v[s]) * gx_mul;
+                RT_MARK(11);
             }
             it += ntl;
             x_loaded = true;
             cluster.sync();
+            RT_MARK(12);
             if (owner) {
                 for (int col = tc; col < RT_D; col += tpr) {
-                    float s = 0.f;
-                    for (int q = 0; q < csize; ++q) s += cluster.map_shared_rank(part_o, q)[myrow * RT_D + col];
+                    float oq[RT_MAXC], s = 0.f;
+#pragma unroll
+                    for (int q = 0; q < RT_MAXC; ++q) oq[q] = q < csize ? cluster.map_shared_rank(part_o, q)[myrow * RT_D + col] : 0.f;
+#pragma unroll
+                    for (int q = 0; q < RT_MAXC; ++q) s += oq[q];
                     for (int q = 0; q < csize; ++q) cluster.map_shared_rank(gy, q)[myrow * RT_D + col] = s;
                 }
             }
+            RT_MARK(13);
             cluster.sync();
+            RT_MARK(14);
         }
         // dL/dy^0 lands on the seed's own row of X (new_X = X.clone(), gather by idx)
         __threadfence();
@@ -805,9 +893,18 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-int pick_cluster(int N) {
+// Keys of a shape are split over `csize` CTAs.  One CTA per SM (shared memory), so when 8-CTA clusters would
+// need a second, mostly empty wave but 4-CTA clusters fit in one, the smaller cluster wins (measured on
+// cfg2: 24 shapes -> 192 vs 96 CTAs on 148 SMs, 420 vs 308 us backward).  PRIFIT_ROWS_CLUSTER overrides.
+int pick_cluster(int N, int nclusters) {
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 148;
+    }
     const int nt = (N + RT_KEYS - 1) / RT_KEYS;
     int csize = RT_MAXC;
+    if (nclusters * 8 > n_sm && nclusters * 4 <= n_sm) csize = 4;
     if (const char* e = getenv("PRIFIT_ROWS_CLUSTER")) {
         const int v = atoi(e);
         if (v >= 1 && v <= RT_MAXC) csize = v;
@@ -834,6 +931,23 @@ int launch_rows_tc(Kern kern, size_t smem, int csize, dim3 grid, const CUtensorM
 
 }  // namespace
 
+// diagnostics: copy the phase timeline recorded by the last launch made with PRIFIT_ROWS_TIMELINE=1
+extern "C" int prifit_debug_rows_timeline(long long* host_pairs, int max_pairs) {
+    int n = 0;
+    if (cudaMemcpyFromSymbol(&n, g_rt_dbg_n, sizeof(int)) != cudaSuccess) return -1;
+    n = n < max_pairs ? n : max_pairs;
+    if (n > 0 && cudaMemcpyFromSymbol(host_pairs, g_rt_dbg, (size_t)n * 2 * sizeof(long long)) != cudaSuccess) return -1;
+    return n;
+}
+
+static int rows_dbg_begin() {
+    const char* e = getenv("PRIFIT_ROWS_TIMELINE");
+    if (!e || atoi(e) == 0) return 0;
+    int zero = 0;
+    cudaMemcpyToSymbol(g_rt_dbg_n, &zero, sizeof(int));
+    return 1;
+}
+
 size_t prifit_rows_tc_workspace_bytes(int B, int N) { return (size_t)2 * B * N * RT_D * sizeof(__half) + 256; }
 
 int prifit_rows_tc_fwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K, int B, int N, int T, int Kcap,
@@ -845,7 +959,8 @@ int prifit_rows_tc_fwd(const float* X, const float* bw, const int32_t* idx, cons
     RowsArgs a = {};
     a.X = X; a.bw = bw; a.idx = idx; a.K = K; a.N = N; a.B = B; a.T = T; a.Kcap = Kcap;
     a.traj = traj; a.stat = stat; a.C_out = C_out;
-    const int csize = pick_cluster(N);
+    a.dbg = rows_dbg_begin();
+    const int csize = pick_cluster(N, B * ((Kcap + RT_SEEDS - 1) / RT_SEEDS));
     return launch_rows_tc(rows_tc_fwd_kernel, 1024 + FwdPlan::total, csize, dim3(csize, (Kcap + RT_SEEDS - 1) / RT_SEEDS, B), map, a, st);
 }
 
@@ -858,6 +973,7 @@ int prifit_rows_tc_bwd(const float* X, const float* bw, const int32_t* idx, cons
     RowsArgs a = {};
     a.X = X; a.bw = bw; a.idx = idx; a.K = K; a.N = N; a.B = B; a.T = T; a.Kcap = Kcap;
     a.traj_in = traj; a.stat_in = stat; a.gC = gC; a.gX = gX;
-    const int csize = pick_cluster(N);
+    a.dbg = rows_dbg_begin();
+    const int csize = pick_cluster(N, B);
     return launch_rows_tc(rows_tc_bwd_kernel, 1024 + BwdPlan::total, csize, dim3(csize, 1, B), map, a, st);
 }
