@@ -103,14 +103,6 @@ __host__ __device__ constexpr uint32_t idesc_f16_mm(int M, int N, bool a_mn, boo
     return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -893,18 +885,13 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-// Keys of a shape are split over `csize` CTAs.  One CTA per SM (shared memory), so when 8-CTA clusters would
-// need a second, mostly empty wave but 4-CTA clusters fit in one, the smaller cluster wins (measured on
-// cfg2: 24 shapes -> 192 vs 96 CTAs on 148 SMs, 420 vs 308 us backward).  PRIFIT_ROWS_CLUSTER overrides.
-int pick_cluster(int N, int nclusters) {
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 148;
-    }
+// Keys of a shape are split over `csize` CTAs (one CTA per SM: shared memory).  The split is independent of
+// the batch size so that a shape's result does not depend on how the batch is sharded (fixed summation
+// order).  4 beats 8 on cfg2 (24 shapes: 96 CTAs in one wave vs 192 in two; 308 vs 420 us backward) and
+// loses little elsewhere.  PRIFIT_ROWS_CLUSTER overrides (diagnostics).
+int pick_cluster(int N) {
     const int nt = (N + RT_KEYS - 1) / RT_KEYS;
-    int csize = RT_MAXC;
-    if (nclusters * 8 > n_sm && nclusters * 4 <= n_sm) csize = 4;
+    int csize = 4;
     if (const char* e = getenv("PRIFIT_ROWS_CLUSTER")) {
         const int v = atoi(e);
         if (v >= 1 && v <= RT_MAXC) csize = v;
@@ -960,7 +947,7 @@ int prifit_rows_tc_fwd(const float* X, const float* bw, const int32_t* idx, cons
     a.X = X; a.bw = bw; a.idx = idx; a.K = K; a.N = N; a.B = B; a.T = T; a.Kcap = Kcap;
     a.traj = traj; a.stat = stat; a.C_out = C_out;
     a.dbg = rows_dbg_begin();
-    const int csize = pick_cluster(N, B * ((Kcap + RT_SEEDS - 1) / RT_SEEDS));
+    const int csize = pick_cluster(N);
     return launch_rows_tc(rows_tc_fwd_kernel, 1024 + FwdPlan::total, csize, dim3(csize, (Kcap + RT_SEEDS - 1) / RT_SEEDS, B), map, a, st);
 }
 
@@ -974,6 +961,6 @@ int prifit_rows_tc_bwd(const float* X, const float* bw, const int32_t* idx, cons
     a.X = X; a.bw = bw; a.idx = idx; a.K = K; a.N = N; a.B = B; a.T = T; a.Kcap = Kcap;
     a.traj_in = traj; a.stat_in = stat; a.gC = gC; a.gX = gX;
     a.dbg = rows_dbg_begin();
-    const int csize = pick_cluster(N, B);
+    const int csize = pick_cluster(N);
     return launch_rows_tc(rows_tc_bwd_kernel, 1024 + BwdPlan::total, csize, dim3(csize, 1, B), map, a, st);
 }

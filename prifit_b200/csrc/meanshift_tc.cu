@@ -5,14 +5,20 @@
 // single launch covers the whole stage and the N x N kernel matrix only ever exists as 128 x 128
 // tiles in tensor memory.  Per key tile (128 keys x 128 d fp16 = 32 KB, one TMA transaction, ring):
 //
-//   GEMM1  S[128 x 128]  = Q[128 x d] . Xtile^T      A = Q in TMEM (f16 pairs), B = Xtile in smem, K-major
+//   GEMM1  S[128 x 128]  = Q[128 x d] . Xtile^T      A = Q in smem (K-major, rewritten once per iteration), B = Xtile in smem, K-major
 //   softmax warps        : S -> P = 2^10 exp2((S - 1) log2e / bw^2), clamped at e^-13, rounded to f16 and
 //                          written back over S in TMEM (thread = row, no shared-memory round trip)
 //   GEMM2  O[128 x d]   += P[128 x 128] . Xtile      A = P in TMEM, B = the SAME smem tile, MN-major
 //
 // and per iteration the epilogue renormalises O row-wise (y' = O / ||O||: the 1/rowsum factor of the
-// reference and the 2^10 scale both cancel in the normalisation) and stores it as the next Q in TMEM.
-// TMEM columns: S0|P0 [0,128)  S1|P1 [128,256)  O [256,384)  Q [384,448).
+// reference and the 2^10 scale both cancel in the normalisation) and stores it as the next Q (fp16,
+// SWIZZLE_128B, K-major) in shared memory.  TMEM columns: S0|P0 [0,128)  S1|P1 [128,256)  O [256,384).
+//
+// What bounds it.  tcgen05.ld and the A-operand fetch of a TMEM-sourced MMA share a tensor-memory read
+// path of ~64 B/clk/SM: per tile the softmax must read S (64 KB) and GEMM2 reads P (32 KB) -> 1536 clk,
+// against 1024 clk of MMA work and 1024 clk of MUFU work.  An earlier version also kept Q in tensor
+// memory (another 32 KB per tile): 2048 clk per tile, measured 2016.  Q therefore lives in shared
+// memory (128 B/clk, otherwise idle) and only P -- produced in registers right next to it -- stays in TMEM.
 //
 // Why kind::f16 and not kind::tf32: fp16 carries the same 10-bit mantissa as tf32 and every operand
 // here lives in [6e-5, 2^10] (unit vectors, weights pre-scaled by 2^10), so the rounding is the same;
@@ -27,6 +33,7 @@
 // fp32 (meanshift_rows.cu).
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -42,7 +49,8 @@ constexpr uint32_t TC_TILE_BYTES = TC_BN * TC_D * 2;      // 32768
 constexpr uint32_t TC_KBLOCK_BYTES = TC_BN * 128;          // one 64-column (128 B) block of the tile
 constexpr int TC_THREADS = 384;             // warps 0-2: TMA / MMA / TMEM alloc, warps 4-11: softmax
 constexpr int TC_SOFTMAX = 256;             // softmax threads: (seed row, 64-key half of every tile)
-constexpr uint32_t COL_S0 = 0, COL_O = 256, COL_Q = 384;
+constexpr uint32_t COL_S0 = 0, COL_O = 256;
+constexpr uint32_t TC_Q_BYTES = TC_BM * TC_D * 2;            // Q tile: two 64-column blocks of [128 rows][128 B]
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float P_SCALE_LOG2 = 10.0f;      // weights are stored as 2^10 * kappa (keeps e^-13 a normal f16)
 
@@ -57,7 +65,7 @@ struct TcBarriers {
     float ssum[2][2][TC_BM];     // [iteration parity][column half][row] partial ||O||^2
 };
 
-constexpr size_t TC_SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)TC_STAGES * TC_TILE_BYTES + sizeof(TcBarriers);
+constexpr size_t TC_SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)TC_STAGES * TC_TILE_BYTES + TC_Q_BYTES + sizeof(TcBarriers);
 
 __global__ void to_half_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t n4) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -66,13 +74,17 @@ __global__ void to_half_kernel(const float4* __restrict__ in, uint2* __restrict_
     }
 }
 
+// DBG (timing experiments only, results are meaningless for DBG != 0): 1 = no ex2, 2 = no tcgen05.ld of S,
+// 3 = no tcgen05.ld / ex2 / tcgen05.st at all (the softmax warps only relay the barriers).
+template <int DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
     const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ Xh, const float* __restrict__ bw,
     int N, int T, float* __restrict__ newX) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;
-    TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + (size_t)TC_STAGES * TC_TILE_BYTES);
+    uint8_t* qtile = smem + (size_t)TC_STAGES * TC_TILE_BYTES;
+    TcBarriers* bars = reinterpret_cast<TcBarriers*>(qtile + TC_Q_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y, r0 = blockIdx.x * TC_BM;
@@ -133,13 +145,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
                     const uint32_t st = it % TC_STAGES, xph = (it / TC_STAGES) & 1, buf = it & 1;
                     mbar_wait(&bars->x_full[st], xph);
                     tc_fence_after();
-                    const uint32_t base = smem_u32(tiles + (size_t)st * TC_TILE_BYTES);
+                    const uint32_t base = smem_u32(tiles + (size_t)st * TC_TILE_BYTES), qbase = smem_u32(qtile);
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {      // 16 d-elements (32 B) per MMA
+                            const uint64_t ad = smem_desc_sw128(qbase + kb * TC_KBLOCK_BYTES + ks * 32, 16, 1024);
                             const uint64_t bd = smem_desc_sw128(base + kb * TC_KBLOCK_BYTES + ks * 32, 16, 1024);
-                            mma_f16_ts(tmem + COL_S0 + buf * 128, tmem + COL_Q + kb * 32 + ks * 8, bd, idesc1, (kb | ks) != 0);
+                            mma_f16_ss(tmem + COL_S0 + buf * 128, ad, bd, idesc1, (kb | ks) != 0);
                         }
                     mma_commit(&bars->s_full[buf]);
                     if (j > 0) gemm2(it - 1, j == 1);
@@ -160,18 +173,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
         const float c1 = LOG2E / (bwv * bwv), c0 = P_SCALE_LOG2 - c1, lo2 = PRIFIT_LO * LOG2E + P_SCALE_LOG2;
         uint32_t v[2][32], h[16];
         // Q^0 = this tile's own rows of X (already fp16: 256 B per row = 64 packed columns, 32 per half)
+        // (row, half) owns row `row` of 64-column block `half` of the Q tile: eight 16-byte chunks, chunk c at c ^ (row & 7)
+        uint8_t* qrow = qtile + (size_t)half * TC_KBLOCK_BYTES + (size_t)row * 128;
         const uint4* xrow = reinterpret_cast<const uint4*>(Xh + ((size_t)b * N + (row_ok ? r0 + row : 0)) * TC_D) + 8 * half;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const uint4 f = row_ok ? xrow[c * 4 + e] : make_uint4(0u, 0u, 0u, 0u);
-                h[4 * e] = f.x; h[4 * e + 1] = f.y; h[4 * e + 2] = f.z; h[4 * e + 3] = f.w;
-            }
-            tmem_st16(tmem + lane_base + COL_Q + 32 * half + 16 * c, h);
-        }
-        tmem_wait_st();
-        tc_fence_before();
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(qrow + ((c ^ (row & 7)) << 4)) = row_ok ? xrow[c] : make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
         mbar_arrive(&bars->q_full);
 
         uint32_t it = 0;
@@ -182,18 +190,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
                 tc_fence_after();
                 const uint32_t sbase = tmem + lane_base + COL_S0 + buf * 128 + 64 * half;
                 const int key0 = j * TC_BN + 64 * half;
-                tmem_ld32(sbase, v[0]);
-                tmem_ld32(sbase + 32, v[1]);
-                tmem_wait_ld();
+                if (DBG < 2) {
+                    tmem_ld32(sbase, v[0]);
+                    tmem_ld32(sbase + 32, v[1]);
+                    tmem_wait_ld();
+                }
                 // P = 2^10 exp(clamp((s-1)/bw^2, -13, .)) packed as f16 pairs over the first 32 of this
                 // thread's own 64 S columns (already in registers); padded keys weigh nothing
-                if (key0 + 64 <= N) {
+                if (DBG == 3) {
+                } else if (key0 + 64 <= N) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
-                            const float p0 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[c][2 * e]), c1, c0), lo2));
-                            const float p1 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[c][2 * e + 1]), c1, c0), lo2));
+                            const float x0 = fmaxf(fmaf(__uint_as_float(v[c][2 * e]), c1, c0), lo2);
+                            const float x1 = fmaxf(fmaf(__uint_as_float(v[c][2 * e + 1]), c1, c0), lo2);
+                            const float p0 = DBG == 1 ? x0 : ex2_approx(x0);
+                            const float p1 = DBG == 1 ? x1 : ex2_approx(x1);
                             h[e] = pack_f16x2(p0, p1);
                         }
                         tmem_st16(sbase + 16 * c, h);
@@ -246,10 +259,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
                         h[e] = pack_f16x2(__uint_as_float(v[c][2 * e]) * inv, __uint_as_float(v[c][2 * e + 1]) * inv);
-                    tmem_st16(tmem + lane_base + COL_Q + 32 * half + 16 * c, h);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)        // columns [32 c + 8 q, +8) of this half = chunk 4 c + q
+                        *reinterpret_cast<uint4*>(qrow + (((4 * c + q) ^ (row & 7)) << 4)) = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
                 }
-                tmem_wait_st();
-                tc_fence_before();
+                fence_proxy_async();
                 mbar_arrive(&bars->q_full);
             }
         }
@@ -373,9 +387,14 @@ int prifit_meanshift_fwd_tc(const float* X, const float* bw, int B, int N, int T
     CUtensorMap map;
     rc = make_tile_map(&map, Xh, B, N);
     if (rc) return rc;
-    PF_CUDA(cudaFuncSetAttribute(meanshift_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     dim3 grid((N + TC_BM - 1) / TC_BM, B);
-    meanshift_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map, Xh, bw, N, T, newX);
+    const char* e = getenv("PRIFIT_MS_DEBUG");
+    const int dbg = e ? atoi(e) : 0;
+#define MS_LAUNCH(D)                                                                                                          \
+    do { PF_CUDA(cudaFuncSetAttribute(meanshift_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES)); \
+         meanshift_tc_kernel<D><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map, Xh, bw, N, T, newX); } while (0)
+    if (dbg == 1) MS_LAUNCH(1); else if (dbg == 2) MS_LAUNCH(2); else if (dbg == 3) MS_LAUNCH(3); else MS_LAUNCH(0);
+#undef MS_LAUNCH
     PF_LAUNCH_CHECK();
     return 0;
 }

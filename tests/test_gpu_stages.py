@@ -239,7 +239,7 @@ def test_rows_engines_agree_on_planted_shapes(cuda, n, kc, T):
         (C * gC).sum().backward()
         outs.append((C.detach(), Xc.grad))
     assert min(res.K_host) >= 2
-    assert rel_err(outs[0][0], outs[1][0]) < 2e-6
+    assert rel_err(outs[0][0], outs[1][0]) < 1e-5      # 1/b^2 (up to ~100) amplifies fp32-level dot differences
     assert rel_err(outs[0][1], outs[1][1]) < 1e-4
 
 
