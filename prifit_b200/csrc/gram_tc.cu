@@ -22,8 +22,8 @@
 //
 // Skeleton: a CTA owns 128 rows (A operands = its rows' hi | lo halves as packed f16 in TMEM), streams
 // every 128-key tile of the shape through a TMA ring (B operands hi + lo, K-major, SWIZZLE_128B, 64 KB
-// per stage), 24 MMAs (M128 N128 K16) per tile into a double-buffered S accumulator, and EIGHT epilogue
-// warps (two per SM sub-partition: thread = (row, 64-column half)) consume S straight from tensor
+// per stage), 24 MMAs (M128 N128 K16) per tile into a double-buffered S accumulator, and SIXTEEN epilogue
+// warps (four per SM sub-partition: thread = (row, 32-column quarter)) consume S straight from tensor
 // memory.  The n x n matrix never exists outside TMEM.
 //
 // Exactness of the bandwidth.  The histogram levels partition the tensor-core distances exactly (the
@@ -45,8 +45,8 @@ int prifit_tc_make_tile_map(CUtensorMap* map, const __half* X, int B, int N);
 namespace {
 
 constexpr int G_D = 128, G_BM = 128, G_BN = 128;
-constexpr int G_THREADS = 384;                           // warps 0-2: TMA / MMA / TMEM alloc; warps 4-11: epilogue
-constexpr int G_EPI = 256;                               // epilogue threads
+constexpr int G_THREADS = 640;                           // warps 0-2: TMA / MMA / TMEM alloc; warps 4-19: epilogue
+constexpr int G_EPI = 512;                               // epilogue threads: (row, 32-column quarter of every tile)
 constexpr int G_STAGES = 2;
 constexpr uint32_t G_HALF_BYTES = G_BN * G_D * 2;        // one fp16 tile (hi or lo): 32 KB
 constexpr uint32_t G_STAGE_BYTES = 2 * G_HALF_BYTES;     // hi + lo
@@ -62,14 +62,14 @@ constexpr int HIST_WORDS = HIST_BINS / 2 + 1;            // packed uint16 pairs;
 constexpr float HIST_SCALE0 = 64.0f;                     // level 0: bins of 1/64 over [0, 4)
 constexpr float HIST_SCALE1 = 64.0f * 256.0f;            // level 1: bins of 2^-14 inside the level-0 bin
 constexpr float BW_MARGIN = 2.0e-5f;                     // >= 2 x the bound on |tensor-core - fp32| distance
-constexpr int CAND_HALF = 64;                            // candidates per (row, column half)
+constexpr int CAND_Q = 32;                               // candidates per (row, column quarter)
 
 template <int MODE> struct GCfg {
     static constexpr size_t scratch =
-        MODE == GM_NEAREST ? (size_t)G_BM * 8
-      : MODE == GM_BEST ? (size_t)G_BM * 8 + 2 * G_BN * sizeof(float)
+        MODE == GM_NEAREST ? (size_t)3 * G_BM * 8
+      : MODE == GM_BEST ? (size_t)3 * G_BM * 8 + 2 * G_BN * sizeof(float)
       : MODE == GM_HIST ? (size_t)G_BM * HIST_WORDS * 4
-      : MODE == GM_COLLECT ? (size_t)G_EPI * CAND_HALF * 2 + 8 * 2 * CAND_HALF * sizeof(float) + 2 * G_EPI * sizeof(int)
+      : MODE == GM_COLLECT ? (size_t)G_EPI * CAND_Q * 2 + 16 * 4 * CAND_Q * sizeof(float) + 2 * G_EPI * sizeof(int)
       : 16;
     static constexpr size_t smem = 1024 + (size_t)G_STAGES * G_STAGE_BYTES + 256 + scratch;
 };
@@ -95,7 +95,7 @@ struct GramArgs {
     int N, B, level;
 };
 
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __device__ __forceinline__ float tc_dist(uint32_t sbits) {
     // 2.0 - 2.0 * <a, b>, clamped to [0, 4): the same expression in every pass, so bins are consistent
@@ -175,9 +175,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
         }
     } else if (warp >= 4) {
         // ================================== epilogue ==================================
-        const int et = threadIdx.x - 128;                        // 0..255
-        const int ew = warp - 4;                                 // 0..7
-        const int half = ew >> 2;                                // column half of every tile this thread owns
+        // Four warps per SM sub-partition (thread = row x 32-column quarter): the per-element work is a short
+        // dependent ALU chain, so latency hiding comes from warps, not from ILP.
+        const int et = threadIdx.x - 128;                        // 0..511
+        const int ew = warp - 4;                                 // 0..15
+        const int qt = ew >> 2;                                  // column quarter of every tile this thread owns
         const int row = 32 * (ew & 3) + lane;                    // TMEM lane == row within the CTA tile
         const uint32_t lane_base = (uint32_t)(32 * (ew & 3)) << 16;
         const bool row_ok = r0 + row < nsel;
@@ -185,24 +187,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
         if (MODE == GM_BEST) grow_i = row_ok ? a.rowsel[(size_t)b * N + r0 + row] : 0;
         const size_t grow = (size_t)b * N + grow_i;
 
-        // ---- A operands: this thread's 64-element half of the row, hi and lo, into tensor memory
+        // ---- A operands: this thread's 32-element quarter of the row, hi and lo, into tensor memory
         {
             uint32_t h[16];
-            const uint4* xhi = reinterpret_cast<const uint4*>(a.Xs + grow * G_D) + 8 * half;
-            const uint4* xlo = reinterpret_cast<const uint4*>(a.Xs + ((size_t)a.B * N + grow) * G_D) + 8 * half;
+            const uint4* xhi = reinterpret_cast<const uint4*>(a.Xs + grow * G_D) + 4 * qt;
+            const uint4* xlo = reinterpret_cast<const uint4*>(a.Xs + ((size_t)a.B * N + grow) * G_D) + 4 * qt;
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
                 const uint4* src = part == 0 ? xhi : xlo;
-                const uint32_t col = (part == 0 ? GCOL_QHI : GCOL_QLO) + 32 * half;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint4 f = row_ok ? src[c * 4 + e] : make_uint4(0u, 0u, 0u, 0u);
-                        h[4 * e] = f.x; h[4 * e + 1] = f.y; h[4 * e + 2] = f.z; h[4 * e + 3] = f.w;
-                    }
-                    tmem_st16(tmem + lane_base + col + 16 * c, h);
+                for (int e = 0; e < 4; ++e) {
+                    const uint4 f = row_ok ? src[e] : make_uint4(0u, 0u, 0u, 0u);
+                    h[4 * e] = f.x; h[4 * e + 1] = f.y; h[4 * e + 2] = f.z; h[4 * e + 3] = f.w;
                 }
+                tmem_st16(tmem + lane_base + (part == 0 ? GCOL_QHI : GCOL_QLO) + 16 * qt, h);
             }
             tmem_wait_st();
             tc_fence_before();
@@ -213,11 +211,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
         float best = MODE == GM_NEAREST ? INFINITY : -1.0f;
         int besti = 0x7fffffff;
         float bwv = 0.f;
-        float* cmb_v = reinterpret_cast<float*>(scratch);                                  // NEAREST/BEST: [128]
-        int* cmb_i = reinterpret_cast<int*>(scratch) + G_BM;                               //               [128]
-        float* vt = reinterpret_cast<float*>(scratch + (size_t)G_BM * 8);                  // BEST: [2][128]
+        float* cmb_v = reinterpret_cast<float*>(scratch);                                  // NEAREST/BEST: [3][128]
+        int* cmb_i = reinterpret_cast<int*>(scratch) + 3 * G_BM;                           //               [3][128]
+        float* vt = reinterpret_cast<float*>(scratch + (size_t)3 * G_BM * 8);              // BEST: [2][128]
         uint32_t* hist = reinterpret_cast<uint32_t*>(scratch) + (size_t)row * HIST_WORDS;  // HIST: own row
-        uint16_t* cand = reinterpret_cast<uint16_t*>(scratch) + (size_t)(row * 2 + half) * CAND_HALF;   // COLLECT
+        uint16_t* cand = reinterpret_cast<uint16_t*>(scratch) + (size_t)(row * 4 + qt) * CAND_Q;   // COLLECT
         float win_lo = 0.f, win_hi = 0.f, hscale = HIST_SCALE0;
         int below = 0, ncand = 0, krem = 1;
         float vnext = 0.f;
@@ -226,7 +224,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
             vnext = et < G_BN && et < N ? (float)a.votes[(size_t)b * N + et] : 0.f;
         }
         if (MODE == GM_HIST) {
-            for (int q = half; q < HIST_WORDS; q += 2) hist[q] = 0u;
+            for (int q = qt; q < HIST_WORDS; q += 4) hist[q] = 0u;
             krem = max(1, min(a.kth[b], N));
             if (a.level > 0 && row_ok) {
                 const int2 ri = a.rowinfo[grow];
@@ -253,60 +251,60 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
             }
             mbar_wait(&bars->s_full[buf], ph);
             tc_fence_after();
-            uint32_t v[2][32];
-            tmem_ld32(tmem + lane_base + buf * 128 + 64 * half, v[0]);
-            tmem_ld32(tmem + lane_base + buf * 128 + 64 * half + 32, v[1]);
+            uint32_t v[32];
+            tmem_ld32(tmem + lane_base + buf * 128 + 32 * qt, v);
             tmem_wait_ld();
             tc_fence_before();
             mbar_arrive(&bars->s_free[buf]);                         // S is in registers: the MMA warp may refill it
-            const int ncols = min(G_BN, N - key0) - 64 * half;       // valid columns among this thread's 64
+            const int ncols = min(G_BN, N - key0) - 32 * qt;         // valid columns among this thread's 32
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int cl = 32 * c + e;                       // column within the half
-                    const float dist = tc_dist(v[c][e]);
-                    if (cl < ncols) {
-                        const int col = key0 + 64 * half + cl;
-                        if (MODE == GM_NEAREST) {
-                            if (dist < best) { best = dist; besti = col; }
-                        } else if (MODE == GM_BEST) {
-                            const float val = dist < bwv ? vt[buf * G_BN + 64 * half + cl] : 0.f;
-                            if (val > best) { best = val; besti = col; }
-                        } else if (MODE == GM_HIST) {
-                            const float t = (dist - win_lo) * hscale;
-                            if (t >= 0.f && t < (float)HIST_BINS) {
-                                const int bin = (int)t;
-                                atomicAdd(&hist[bin >> 1], (bin & 1) ? 65536u : 1u);
-                            }
-                        } else if (MODE == GM_COLLECT) {
-                            below += dist < win_lo ? 1 : 0;
-                            if (dist >= win_lo && dist <= win_hi) {
-                                if (ncand < CAND_HALF) cand[ncand] = (uint16_t)col;
-                                ++ncand;
-                            }
-                        } else if (row_ok) {
-                            a.dump[grow * N + col] = dist;
+            for (int e = 0; e < 32; ++e) {
+                const float dist = tc_dist(v[e]);
+                if (e < ncols) {
+                    const int col = key0 + 32 * qt + e;
+                    if (MODE == GM_NEAREST) {
+                        if (dist < best) { best = dist; besti = col; }
+                    } else if (MODE == GM_BEST) {
+                        const float val = dist < bwv ? vt[buf * G_BN + 32 * qt + e] : 0.f;
+                        if (val > best) { best = val; besti = col; }
+                    } else if (MODE == GM_HIST) {
+                        const float t = (dist - win_lo) * hscale;
+                        if (t >= 0.f && t < (float)HIST_BINS) {
+                            const int bin = (int)t;
+                            atomicAdd(&hist[bin >> 1], (bin & 1) ? 65536u : 1u);
                         }
+                    } else if (MODE == GM_COLLECT) {
+                        below += dist < win_lo ? 1 : 0;
+                        if (dist >= win_lo && dist <= win_hi) {
+                            if (ncand < CAND_Q) cand[ncand] = (uint16_t)col;
+                            ++ncand;
+                        }
+                    } else if (row_ok) {
+                        a.dump[grow * N + col] = dist;
                     }
                 }
+            }
         }
 
         // ---- per-mode finalisation
         if (MODE == GM_NEAREST || MODE == GM_BEST) {
-            // combine the two column halves of every row: better value, then lower index
-            if (half == 1) { cmb_v[row] = best; cmb_i[row] = besti; }
+            // combine the four column quarters of every row: better value, then lower index
+            if (qt > 0) { cmb_v[(qt - 1) * G_BM + row] = best; cmb_i[(qt - 1) * G_BM + row] = besti; }
             epi_barrier();
-            if (half == 0 && row_ok) {
-                const float ov = cmb_v[row];
-                const int oi = cmb_i[row];
-                const bool take = MODE == GM_NEAREST ? (ov < best || (ov == best && oi < besti))
-                                                     : (ov > best || (ov == best && oi < besti));
-                a.out_idx[grow] = take ? oi : besti;
+            if (qt == 0 && row_ok) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const float ov = cmb_v[q * G_BM + row];
+                    const int oi = cmb_i[q * G_BM + row];
+                    const bool take = MODE == GM_NEAREST ? (ov < best || (ov == best && oi < besti))
+                                                         : (ov > best || (ov == best && oi < besti));
+                    if (take) { best = ov; besti = oi; }
+                }
+                a.out_idx[grow] = besti;
             }
         } else if (MODE == GM_HIST) {
             epi_barrier();
-            if (half == 0 && row_ok) {
+            if (qt == 0 && row_ok) {
                 int cum = 0, bin = HIST_BINS - 1, before = 0;
                 bool found = false;
                 for (int q = 0; q < HIST_BINS / 2 && !found; ++q) {
@@ -321,21 +319,29 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                 a.rowinfo[grow] = make_int2(__float_as_int(lo_new), krem - before);
             }
         } else if (MODE == GM_COLLECT) {
-            // exact fp32 recompute of the candidates, one warp per row (16 rows per epilogue warp)
-            float* vals = reinterpret_cast<float*>(scratch + (size_t)G_EPI * CAND_HALF * 2) + ew * 2 * CAND_HALF;
-            int* below_s = reinterpret_cast<int*>(scratch + (size_t)G_EPI * CAND_HALF * 2 + 8 * 2 * CAND_HALF * sizeof(float));
+            // exact fp32 recompute of the candidates, one warp per row (8 rows per epilogue warp)
+            float* vals = reinterpret_cast<float*>(scratch + (size_t)G_EPI * CAND_Q * 2) + ew * 4 * CAND_Q;
+            int* below_s = reinterpret_cast<int*>(scratch + (size_t)G_EPI * CAND_Q * 2 + 16 * 4 * CAND_Q * sizeof(float));
             int* ncand_s = below_s + G_EPI;
-            below_s[row * 2 + half] = below;
-            ncand_s[row * 2 + half] = ncand;
+            below_s[row * 4 + qt] = below;
+            ncand_s[row * 4 + qt] = ncand;
             epi_barrier();
             const int k = max(1, min(a.kth[b], N));
             const uint16_t* call = reinterpret_cast<const uint16_t*>(scratch);
-            for (int rr = 0; rr < 16; ++rr) {
-                const int r = 16 * ew + rr;
+            for (int rr = 0; rr < 8; ++rr) {
+                const int r = 8 * ew + rr;
                 if (r0 + r >= N) break;                                         // warp-uniform
-                const int n0 = ncand_s[2 * r], n1 = ncand_s[2 * r + 1];
-                const int nc = n0 + n1, m = k - below_s[2 * r] - below_s[2 * r + 1];   // m-th smallest candidate (1-based)
-                if (n0 > CAND_HALF || n1 > CAND_HALF || m < 1 || m > nc) {
+                int n4[4], nc = 0, bel = 0;
+                bool over = false;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    n4[q] = ncand_s[4 * r + q];
+                    over |= n4[q] > CAND_Q;
+                    nc += n4[q];
+                    bel += below_s[4 * r + q];
+                }
+                const int m = k - bel;                                          // m-th smallest candidate (1-based)
+                if (over || m < 1 || m > nc) {
                     if (lane == 0) { atomicExch(a.overflow, 1); a.rowval[(size_t)b * N + r0 + r] = 0.f; }
                     continue;
                 }
@@ -343,7 +349,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                 // candidate row is one coalesced 512-byte request (4 candidates in flight per step)
                 const float4 xr = __ldg(reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + r0 + r) * G_D) + lane);
                 auto cand_of = [&](int ci) -> int {
-                    return ci < n0 ? call[(size_t)(2 * r) * CAND_HALF + ci] : call[(size_t)(2 * r + 1) * CAND_HALF + ci - n0];
+                    int q = 0;
+                    while (q < 3 && ci >= n4[q]) { ci -= n4[q]; ++q; }
+                    return call[(size_t)(4 * r + q) * CAND_Q + ci];
                 };
                 for (int c0 = 0; c0 < nc; c0 += 4) {
                     float acc[4];

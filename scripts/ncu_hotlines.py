@@ -25,7 +25,7 @@ def main(path, top=30):
             rows.append((int(d["# Samples"]), fname, int(r[0]), r[1].strip(), stalls, int(d["Instructions Executed"])))
     tot = sum(x[0] for x in rows)
     print("total samples %d" % tot)
-    for n, f, line, src, stalls, inst in sorted(rows, reverse=True)[:top]:
+    for n, f, line, src, stalls, inst in sorted(rows, key=lambda x: -x[0])[:top]:
         s = ", ".join("%s %d" % kv for kv in sorted(stalls.items(), key=lambda kv: -kv[1])[:3] if kv[1])
         print("%5.1f%% %-22s:%-4d inst %-8d [%s]  %s" % (100.0 * n / max(tot, 1), f[:22], line, inst, s, src[:90]))
 
