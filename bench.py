@@ -50,6 +50,16 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json); None when no capture exists."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path))[workload][kernel]["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -140,6 +150,7 @@ def run_ours(args):
     torch.manual_seed(1234 + rank)
 
     ms_events = []
+    last = {}
 
     def step_resident(i, timed):
         E = dev_E[i % N_SETS].detach().requires_grad_(True)
@@ -150,18 +161,53 @@ def run_ours(args):
         Lb.backward()
         return L, out
 
-    def step_e2e(i):
-        X = host_Xcf[i % N_SETS].to(dev, non_blocking=True).requires_grad_(True)
-        pts = host_Pcf[i % N_SETS].to(dev, non_blocking=True)
+    # End-to-end arm: every step copies its inputs host -> device from pinned memory and reads its loss back.
+    # Like a data loader would, the copy of step i+1 is issued on a side stream while step i computes, and the
+    # loss of step i is read (pinned D2H) while step i+1 is being enqueued; both stay inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    staged = {}
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    pending = {}
+
+    def stage_inputs(i):
+        with torch.cuda.stream(copy_stream):
+            X = host_Xcf[i % N_SETS].to(dev, non_blocking=True)
+            pts = host_Pcf[i % N_SETS].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        staged[i] = (X, pts, ev)
+
+    def drain_loss():
+        if pending:
+            pending.pop("ev").synchronize()
+            last["e2e_loss"] = float(loss_host[pending.pop("slot")])
+
+    def step_e2e(i, last_step):
+        if i not in staged:
+            stage_inputs(i)
+        X, pts, ev = staged.pop(i)
+        torch.cuda.current_stream().wait_event(ev)
+        X.record_stream(torch.cuda.current_stream()); pts.record_stream(torch.cuda.current_stream())
+        if not last_step:
+            stage_inputs(i + 1)
+        X = X.requires_grad_(True)
         total, l, params, labels = cl.convex_loss(pts, pts, X, quantile=q, iterations=T, max_num_clusters=kmax)
         if world > 1:
             valid = params.padded[3]
             n_local = (valid.sum(1) > 0).float().sum()
             L, Lb = pdist.global_mean_from_local(total, n_local)
             Lb.backward()
-            return float(L.item())
-        total.backward()
-        return float(total.item())               # D2H read of the step's result
+        else:
+            L = total
+            total.backward()
+        drain_loss()                                # the previous step's result, read while this one runs
+        slot = i & 1
+        loss_host[slot:slot + 1].copy_(L.detach().reshape(1), non_blocking=True)
+        ev2 = torch.cuda.Event()
+        ev2.record()
+        pending["ev"], pending["slot"] = ev2, slot
+        if last_step:
+            drain_loss()
 
     def barrier():
         if world > 1:
@@ -189,7 +235,6 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     _lib.reset_launch_count()
-    last = {}
 
     def resident(i, timed):
         L, out = step_resident(i, timed)
@@ -199,7 +244,8 @@ def run_ours(args):
     launches_total = _lib.launch_count()
     n_ms_launch = len(ms_events)
     ms_kernel = sum(a.elapsed_time(b) for a, b in ms_events) / max(n_ms_launch, 1)
-    e2e_ms, _ = timed_region(lambda i, timed: step_e2e(i), args.steps, args.warmup)
+    e2e_last = args.warmup + args.steps - 1
+    e2e_ms, _ = timed_region(lambda i, timed: step_e2e(i, i == e2e_last or i == args.warmup - 1), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
     res = last["out"]["cluster"]
@@ -233,7 +279,8 @@ def run_ours(args):
         "gpu_launches_per_step": round(launches_total / (args.steps + args.warmup), 1),
         "roofline": {"bound": "tensor", "kernel": "meanshift_fwd (%s)" % args.engine, "achieved": round(achieved, 2),
                      "peak": round(tc_peak, 1), "unit": "TFLOP/s", "frac": round(achieved / tc_peak, 4),
-                     "traffic": None, "kernel_ms": round(ms_kernel, 4), "launches_timed": n_ms_launch,
+                     "traffic": ncu_traffic(args.workload, "meanshift_tc_kernel") if engine == ops.MS_TF32_TCGEN05 else None,
+                     "kernel_ms": round(ms_kernel, 4), "launches_timed": n_ms_launch,
                      "flops_per_launch": flops_launch,
                      "peak_source": "%s dense bf16 GEMM, sustained (%.0f TF/s; burst %.0f)" % (pk["source"], pk["bf16_tflops_sustained"], pk["bf16_tflops"]),
                      "whole_step_tflops": round(shapes_per_s / world * algorithmic_flops_per_shape(N, T, K_mean, passes) / 1e12, 2)},
