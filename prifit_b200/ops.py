@@ -39,7 +39,8 @@ def _ptr(t):
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # torch.cuda.current_stream() costs ~20 us of Python per call; the raw handle is one C call
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def _chk(t, dtype=torch.float32):

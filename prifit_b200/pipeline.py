@@ -54,49 +54,101 @@ def _sample_rows(B, N, num_samples, device):
     return torch.from_numpy(rows).to(device)
 
 
+def _cluster_pass(X, quantiles, n_s, iterations, kcap, engine):
+    """One guard pass over a (sub-)batch: bandwidth -> T mean-shift iterations of all N seeds -> NMS.
+    Everything is enqueued; nothing is read back."""
+    B, N, _ = X.shape
+    kth = _kth_tensor(quantiles, n_s, X.device)
+    rows = _sample_rows(B, N, n_s, X.device)
+    bw = ops.bandwidth(X, kth, rows)
+    newX = ops.meanshift(X, bw, iterations, engine)
+    idx, K, labels, nlab = ops.nms(newX, bw, kcap)
+    return bw, idx, K, labels, nlab
+
+
+class _Counts:
+    """Asynchronous read-back of (K, n_labels) of a pass: pinned D2H copy + event."""
+    _pinned = {}
+
+    def __init__(self, K, nlab):
+        n = K.numel()
+        key = (K.device.index, n)
+        buf = _Counts._pinned.get(key)
+        if buf is None:
+            buf = _Counts._pinned[key] = torch.empty(2, n, dtype=torch.int32).pin_memory()
+        self.buf = buf
+        buf[0].copy_(K, non_blocking=True)
+        buf[1].copy_(nlab, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def wait(self):
+        self.event.synchronize()
+        return self.buf[0].tolist(), self.buf[1].tolist()
+
+
 @torch.no_grad()
-def cluster_batch(X, num_samples, quantile, iterations, max_num_clusters, engine=None) -> ClusterResult:
-    """guard_mean_shift (src/ellipsoid_utils.py:9-27) for all shapes at once: bandwidth -> T mean-shift
-    iterations of all N seeds -> NMS; shapes whose label count exceeds max_num_clusters are re-run
-    with a doubled quantile."""
+def cluster_batch_begin(X, num_samples, quantile, iterations, max_num_clusters, engine=None):
+    """First guard pass of guard_mean_shift (src/ellipsoid_utils.py:9-27) for all shapes, enqueued without
+    waiting for it: returns (ClusterResult with the device tensors of pass 1, pending counts).  The stages
+    that only need device-side cluster lists can be enqueued behind it speculatively; cluster_batch_end()
+    then reads the counts (the one host synchronisation of the pass) and runs the redo passes, if any."""
     X = ops._chk(X)
     B, N, d = X.shape
     kcap = ops.kcap_for(max_num_clusters)
     n_s = min(int(num_samples), N)
+    bw, idx, K, labels, nlab = _cluster_pass(X, [float(quantile)] * B, n_s, iterations, kcap, engine)
+    out = ClusterResult(bw=bw, idx=idx, K=K, labels=labels, K_host=[0] * B, n_labels_host=[0] * B, passes=[0] * B,
+                        quantiles=[float(quantile)] * B, kcap=kcap, iterations=int(iterations))
+    return out, (_Counts(K, nlab), X, n_s, max_num_clusters, engine)
+
+
+@torch.no_grad()
+def cluster_batch_end(out: ClusterResult, pending) -> bool:
+    """Completes cluster_batch_begin(): host read of the counts, then the guard loop -- shapes whose label
+    count exceeds max_num_clusters are re-run as a compacted sub-batch with a doubled quantile
+    (src/ellipsoid_utils.py:23-24).  Returns True when a redo pass replaced device tensors of `out`
+    (anything enqueued speculatively on the pass-1 tensors must then be recomputed)."""
+    counts, X, n_s, max_num_clusters, engine = pending
+    B, N, _ = X.shape
     dev = X.device
-    out = ClusterResult(
-        bw=torch.empty(B, dtype=torch.float32, device=dev), idx=torch.empty(B, kcap, dtype=torch.int32, device=dev),
-        K=torch.empty(B, dtype=torch.int32, device=dev), labels=torch.empty(B, N, dtype=torch.int32, device=dev),
-        K_host=[0] * B, n_labels_host=[0] * B, passes=[0] * B, quantiles=[float(quantile)] * B, kcap=kcap,
-        iterations=int(iterations))
+    kcap = out.kcap
     active = list(range(B))
-    while active:
-        whole = len(active) == B
-        sel = None if whole else torch.tensor(active, dtype=torch.long, device=dev)
-        Xa = X if whole else X.index_select(0, sel)
-        kth = _kth_tensor([out.quantiles[b] for b in active], n_s, dev)
-        rows = _sample_rows(len(active), N, n_s, dev)
-        bw = ops.bandwidth(Xa, kth, rows)
-        newX = ops.meanshift(Xa, bw, iterations, engine)
-        idx, K, labels, nlab = ops.nms(newX, bw, kcap)
-        counts = torch.stack([K, nlab]).cpu()                   # the one host sync of this pass
-        if whole:
-            out.bw, out.idx, out.K, out.labels = bw, idx, K, labels
-        else:
-            out.bw.index_copy_(0, sel, bw)
-            out.idx.index_copy_(0, sel, idx)
-            out.K.index_copy_(0, sel, K)
-            out.labels.index_copy_(0, sel, labels)
+    redone = False
+    while True:
+        K_l, nlab_l = counts.wait()
         again = []
         for i, b in enumerate(active):
             out.passes[b] += 1
-            out.K_host[b], out.n_labels_host[b] = int(counts[0, i]), int(counts[1, i])
+            out.K_host[b], out.n_labels_host[b] = int(K_l[i]), int(nlab_l[i])
             if out.n_labels_host[b] > max_num_clusters:         # src/ellipsoid_utils.py:23-24
                 out.quantiles[b] *= 2
                 again.append(b)
             elif out.K_host[b] > kcap:
                 raise _lib.PrifitError("shape %d: %d cluster centres exceed the padded capacity %d" % (b, out.K_host[b], kcap))
+        if not again:
+            return redone
+        if not redone:                                          # pass-1 tensors may be shared with speculative work
+            out.bw, out.idx, out.K, out.labels = out.bw.clone(), out.idx.clone(), out.K.clone(), out.labels.clone()
+        redone = True
         active = again
+        sel = torch.tensor(active, dtype=torch.long, device=dev)
+        bw, idx, K, labels, nlab = _cluster_pass(X.index_select(0, sel), [out.quantiles[b] for b in active], n_s,
+                                                 out.iterations, kcap, engine)
+        out.bw.index_copy_(0, sel, bw)
+        out.idx.index_copy_(0, sel, idx)
+        out.K.index_copy_(0, sel, K)
+        out.labels.index_copy_(0, sel, labels)
+        counts = _Counts(K, nlab)
+
+
+@torch.no_grad()
+def cluster_batch(X, num_samples, quantile, iterations, max_num_clusters, engine=None) -> ClusterResult:
+    """guard_mean_shift (src/ellipsoid_utils.py:9-27) for all shapes at once: bandwidth -> T mean-shift
+    iterations of all N seeds -> NMS; shapes whose label count exceeds max_num_clusters are re-run
+    with a doubled quantile."""
+    out, pending = cluster_batch_begin(X, num_samples, quantile, iterations, max_num_clusters, engine)
+    cluster_batch_end(out, pending)
     return out
 
 
@@ -111,12 +163,22 @@ def draw_noise(K_host, kcap, device):
     clusters inner (src/ellipsoid_fitting.py:38).  One batched CPU draw yields the same stream."""
     total = int(sum(K_host))
     flat = torch.rand(total, 3, 3)
-    padded = torch.zeros(len(K_host), kcap, 3, 3)
-    o = 0
-    for b, k in enumerate(K_host):
-        padded[b, :k] = flat[o:o + k]
-        o += k
-    return padded.pin_memory().to(device, non_blocking=True) if device.type == "cuda" else padded
+    B = len(K_host)
+    if device.type != "cuda":
+        padded = torch.zeros(B, kcap, 3, 3)
+    else:                                   # cached pinned staging buffer (pin_memory() per call costs ~100 us)
+        key = (device.index, B, kcap)
+        padded = _noise_pinned.get(key)
+        if padded is None:
+            padded = _noise_pinned[key] = torch.zeros(B, kcap, 3, 3).pin_memory()
+        else:
+            padded.zero_()
+    mask = torch.arange(kcap)[None, :] < torch.tensor(K_host)[:, None]
+    padded.view(B * kcap, 9)[mask.view(-1)] = flat.view(total, 9)
+    return padded.to(device, non_blocking=True) if device.type == "cuda" else padded
+
+
+_noise_pinned = {}
 
 
 def masked_mean(loss_b, valid):
@@ -131,9 +193,13 @@ def fit_loss(E, P, quantile=0.05, iterations=10, max_num_clusters=25, noise=None
 
     `loss` is differentiable w.r.t. E (and P/Q if they require grad)."""
     X = ops.NormalizeTwice.apply(E)
-    res = cluster_batch(X.detach(), X.shape[1] if num_samples is None else num_samples, quantile, iterations,
-                        max_num_clusters, engine)
+    # the differentiable stages that only need the device-side cluster lists are enqueued behind pass 1 before
+    # the host learns the counts; in the rare guard-redo case they are recomputed on the final clustering
+    res, pending = cluster_batch_begin(X.detach(), X.shape[1] if num_samples is None else num_samples, quantile,
+                                       iterations, max_num_clusters, engine)
     W, C = soft_memberships(X, res)
+    if cluster_batch_end(res, pending):
+        W, C = soft_memberships(X, res)
     if noise is None:
         noise = draw_noise(res.K_host, res.kcap, X.device)
     s, V, c, valid = ops.EllipsoidFit.apply(P, W, res.K, noise)
