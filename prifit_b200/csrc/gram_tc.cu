@@ -35,6 +35,7 @@
 // duplicates) raise the overflow flag and the exact CUDA-core kernel (bandwidth.cu) redoes the batch.
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -257,10 +258,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
             tc_fence_before();
             mbar_arrive(&bars->s_free[buf]);                         // S is in registers: the MMA warp may refill it
             const int ncols = min(G_BN, N - key0) - 32 * qt;         // valid columns among this thread's 32
+            // per-element epilogue; CHK = false on full tiles (every tile but possibly the last) drops the column test
+            auto consume = [&](auto chk) {
+                constexpr bool CHK = decltype(chk)::value;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const float dist = tc_dist(v[e]);
-                if (e < ncols) {
+                for (int e = 0; e < 32; ++e) {
+                    if (CHK && e >= ncols) break;
+                    const float dist = tc_dist(v[e]);
                     const int col = key0 + 32 * qt + e;
                     if (MODE == GM_NEAREST) {
                         if (dist < best) { best = dist; besti = col; }
@@ -268,11 +272,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                         const float val = dist < bwv ? vt[buf * G_BN + 32 * qt + e] : 0.f;
                         if (val > best) { best = val; besti = col; }
                     } else if (MODE == GM_HIST) {
-                        const float t = (dist - win_lo) * hscale;
-                        if (t >= 0.f && t < (float)HIST_BINS) {
-                            const int bin = (int)t;
-                            atomicAdd(&hist[bin >> 1], (bin & 1) ? 65536u : 1u);
-                        }
+                        // bin = floor((dist - lo) * scale); one unsigned compare covers 0 <= bin < 256; the
+                        // update is a single predicated shared-memory atomic (no divergent region)
+                        const int bin = __float2int_rd((dist - win_lo) * hscale);
+                        const uint32_t inc = (bin & 1) ? 65536u : 1u;
+                        if ((uint32_t)bin < (uint32_t)HIST_BINS) atomicAdd(hist + (bin >> 1), inc);
                     } else if (MODE == GM_COLLECT) {
                         below += dist < win_lo ? 1 : 0;
                         if (dist >= win_lo && dist <= win_hi) {
@@ -283,7 +287,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                         a.dump[grow * N + col] = dist;
                     }
                 }
-            }
+            };
+            if (ncols >= 32) consume(std::false_type{}); else consume(std::true_type{});
         }
 
         // ---- per-mode finalisation
