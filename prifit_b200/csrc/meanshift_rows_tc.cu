@@ -20,9 +20,13 @@
 //                             gX[128 keys x d]    = [ds | e1] . [Y ; Gm]     (A smem K-major, B smem MN-major)
 //
 // Precision.  Every operand is split into two fp16 numbers (hi + lo, 22 significant bits) after a
-// power-of-two pre-scale that keeps both halves normal, and every product is three tcgen05.mma
-// (lo.hi + hi.lo + hi.hi) accumulated in fp32 -- the same scheme as the Gram engine (gram_tc.cu),
-// |error| ~ 3e-7 on a dot product of unit vectors, i.e. fp32-class.  Scales:
+// power-of-two pre-scale that keeps both halves normal, and every product is the three partial products
+// lo.hi + hi.lo + hi.hi accumulated in fp32 -- the scheme of the Gram engine (gram_tc.cu), |error| ~ 3e-7
+// on a dot product of unit vectors, i.e. fp32-class.  The MMAs are bound by the shared-memory fetch of
+// the 128-row key tile (~80 clk per instruction whatever N is), so the hi and lo halves of the SMALL
+// operand are stacked along N: one MMA of the key tile's hi half against [b_hi ; b_lo] (two accumulator
+// column groups, summed by the epilogue) plus one of its lo half against b_hi -- two key-tile fetches
+// per K step instead of three.  Scales:
 //   x, y      * 2^8                       (unit vectors)
 //   p         * 2^14                      (p in [e^-13, 1])
 //   gm        * SG  (power of two, max |gm| of the shape and iteration -> [2^7, 2^8))
@@ -58,24 +62,26 @@ constexpr float RT_LOG2E = 1.4426950408889634f;
 
 // ---- shared-memory plans (offsets from a 1024-aligned base; every MMA tile is 1024-aligned)
 struct FwdPlan {
-    static constexpr uint32_t Y_KB = RT_SEEDS * 128;                         // [32 rows][128 B] per 64-column block
-    static constexpr uint32_t Y_PART = 2 * Y_KB;                             // 8 KB (hi or lo)
+    // Y tile: per 64-column block, rows [y_hi 0-31 ; y_lo 32-63] x 128 B -- one N = 64 B operand for the key tile's
+    // hi half (x_hi.y_hi | x_hi.y_lo in separate accumulator columns) and an N = 32 one for its lo half
+    static constexpr uint32_t Y_KB = 2 * RT_SEEDS * 128;                     // 8 KB
+    static constexpr uint32_t Y_LO = RT_SEEDS * 128;                         // row 32 of a block
     static constexpr uint32_t x = 0;
-    static constexpr uint32_t y = x + RT_STAGES * RT_STAGE_BYTES;            // Y tile hi | lo
-    static constexpr uint32_t p = y + 2 * Y_PART;                            // P tile hi | lo
-    static constexpr uint32_t ys = p + 2 * RT_PPART;                         // fp32 [32][128] current seeds
+    static constexpr uint32_t y = x + RT_STAGES * RT_STAGE_BYTES;            // Y tile, two 64-column blocks
+    static constexpr uint32_t p = y + 2 * Y_KB;                              // P tile [128 keys][p_hi 64 B | p_lo 64 B]
+    static constexpr uint32_t ys = p + RT_PPART;                             // fp32 [32][128] current seeds
     static constexpr uint32_t misc = ys + RT_SEEDS * RT_D * 4;
     static constexpr uint32_t total = misc + 4096;
-    // aliases inside the coefficient tile (dead between the tile loop and the next one)
+    // aliases inside operand tiles that are dead between the tile loop and the next one
     static constexpr uint32_t part_o = p;                                    // fp32 [32][128] partial numerators
-    static constexpr uint32_t urow = p + RT_PPART;                           // fp32 [32][128] owned rows being finished
 };
 struct BwdPlan {
-    static constexpr uint32_t YG_KB = 2 * RT_SEEDS * 128;                    // [Y rows 0-31 | Gm rows 32-63][128 B]: 8 KB
-    static constexpr uint32_t YG_PART = 2 * YG_KB;                           // 16 KB (hi or lo)
+    // stacked operand tile: per 64-column block, rows [y_hi 0-31 ; gm_hi 32-63 ; y_lo 64-95 ; gm_lo 96-127] x 128 B
+    static constexpr uint32_t YG_KB = 4 * RT_SEEDS * 128;                    // 16 KB
+    static constexpr uint32_t YG_ROWS = RT_SEEDS * 128;                      // 32 rows
     static constexpr uint32_t x = 0;
     static constexpr uint32_t yg = x + RT_STAGES * RT_STAGE_BYTES;
-    static constexpr uint32_t de = yg + 2 * YG_PART;                         // [128 keys][ds 64 B | e1 64 B] hi | lo
+    static constexpr uint32_t de = yg + 2 * YG_KB;                           // [128 keys][ds_hi | ds_lo] , [128 keys][e1_hi | e1_lo]
     static constexpr uint32_t gy = de + 2 * RT_PPART;                        // fp32 [32][128] dL/dy^{t+1}
     static constexpr uint32_t misc = gy + RT_SEEDS * RT_D * 4;
     static constexpr uint32_t total = misc + 4096;
@@ -88,7 +94,7 @@ struct RtMisc {
     uint64_t x_full[RT_STAGES], x_empty[RT_STAGES];
     uint64_t s_full[2], s_free[2];
     uint64_t c_full, c_free;             // coefficient tile (P / ds|e1) written / consumed
-    uint64_t gx_full[2], gx_free[2];     // backward: gX accumulator of a tile complete / flushed
+    uint64_t gx_full, gx_free;           // backward: gX accumulator of a tile complete / read out
     uint64_t o_full, y_full;
     uint32_t tmem_base;
     float part_z[RT_SEEDS];
@@ -124,13 +130,6 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
-// three MMAs of one 16-element K step: D (+)= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi
-__device__ __forceinline__ void mma3(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc, bool acc) {
-    mma_f16_ss(d, a_lo, b_hi, idesc, acc);
-    mma_f16_ss(d, a_hi, b_lo, idesc, true);
-    mma_f16_ss(d, a_hi, b_hi, idesc, true);
 }
 
 // Sum 16 per-lane values over the 32 lanes of a warp; lane l ends up with the total of value index (l >> 1) & 15.
@@ -193,7 +192,7 @@ __device__ __forceinline__ float pow2_scale_to(float v, int top) {
 __device__ long long g_rt_dbg[8192];
 __device__ int g_rt_dbg_n;
 #define RT_MARK(id)                                                                        \
-    do { if (a.dbg && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 128) {          \
+    do { if ((a.dbg & 1) && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 128) {          \
              const int n__ = g_rt_dbg_n; if (n__ < 4090) { g_rt_dbg[2 * n__] = (id); g_rt_dbg[2 * n__ + 1] = clock64(); g_rt_dbg_n = n__ + 1; } } } while (0)
 
 struct RowsArgs {
@@ -253,7 +252,6 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
     RtMisc* m = reinterpret_cast<RtMisc*>(smem + FwdPlan::misc);
     float* ys = reinterpret_cast<float*>(smem + FwdPlan::ys);
     float* part_o = reinterpret_cast<float*>(smem + FwdPlan::part_o);
-    float* urow = reinterpret_cast<float*>(smem + FwdPlan::urow);
 
     int j0, ntl;
     my_tiles(N, csize, rank, j0, ntl);
@@ -267,12 +265,12 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) prefetch_tensormap(&tmap);
-    if (warp == 2) { tmem_alloc(&m->tmem_base, 128); tmem_relinquish(); }
+    if (warp == 2) { tmem_alloc(&m->tmem_base, 256); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = m->tmem_base;
-    constexpr uint32_t COL_S = 0, COL_O = 64;
+    constexpr uint32_t COL_S = 0 /* [buf][x_hi.y_hi + x_lo.y_hi | x_hi.y_lo] */, COL_O = 128 /* same split */;
 
     const float* Xb = a.X + (size_t)b * N * RT_D;
     const int32_t* idx_b = a.idx + (size_t)b * Kcap + k0;
@@ -286,10 +284,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
     const int row = 32 * (ew & 3) + lane;                          // TMEM lane: key within the tile / column d of O^T
     const uint32_t lane_base = (uint32_t)(32 * (ew & 3)) << 16;
     // reduce-phase ownership: this CTA finishes seeds [rank * rpc, rank * rpc + rpc)
-    const int rpc = (RT_SEEDS + csize - 1) / csize, tpr = RT_EPI / rpc;
-    const int rr = et / tpr, tc = et - rr * tpr;
-    const int myrow = rank * rpc + rr;
-    const bool owner = warp >= 4 && rr < rpc && myrow < RT_SEEDS;
+    const int rpc = (RT_SEEDS + csize - 1) / csize;
 
     auto write_y_tile = [&]() {      // ys (fp32) -> Y tile hi | lo, K-major SWIZZLE_128B, rows = seeds
         for (int q = et; q < RT_SEEDS * 16; q += RT_EPI) {
@@ -298,7 +293,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = ys[r * RT_D + 8 * c8 + e] * RT_XSCALE;
             uint8_t* hi_blk = smem + FwdPlan::y + (c8 >> 3) * FwdPlan::Y_KB;
-            store_chunk_hilo(hi_blk, hi_blk + FwdPlan::Y_PART, r, c8 & 7, f);
+            store_chunk_hilo(hi_blk, hi_blk + FwdPlan::Y_LO, r, c8 & 7, f);
         }
         fence_proxy_async();
         mbar_arrive(&m->y_full);
@@ -333,8 +328,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
         } else if (warp == 1) {
             // ================================= MMA issuer =================================
             if (lane == 0) {
-                constexpr uint32_t id1 = idesc_f16_mm(RT_KEYS, RT_SEEDS, false, false);   // S^T = X . Y^T
-                constexpr uint32_t id2 = idesc_f16_mm(RT_D, RT_SEEDS, true, true);        // O^T += X^T . P^T
+                constexpr uint32_t id1w = idesc_f16_mm(RT_KEYS, 2 * RT_SEEDS, false, false);   // x_hi . [y_hi ; y_lo]^T
+                constexpr uint32_t id1n = idesc_f16_mm(RT_KEYS, RT_SEEDS, false, false);       // x_lo . y_hi^T
+                constexpr uint32_t id2w = idesc_f16_mm(RT_D, 2 * RT_SEEDS, true, true);        // x_hi^T . [p_hi | p_lo]
+                constexpr uint32_t id2n = idesc_f16_mm(RT_D, RT_SEEDS, true, true);            // x_lo^T . p_hi
                 const uint32_t ybase = smem_u32(smem + FwdPlan::y), pbase = smem_u32(smem + FwdPlan::p);
                 auto gemm2 = [&](uint32_t i, int jl, bool first) {
                     const uint32_t st = resident ? (uint32_t)jl : i % RT_STAGES;
@@ -345,9 +342,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                     for (int kk = 0; kk < RT_KEYS / 16; ++kk) {        // 16 keys per MMA
                         const uint64_t a_hi = smem_desc_sw128(xb + kk * 2048, RT_KBLOCK, 1024);
                         const uint64_t a_lo = smem_desc_sw128(xb + RT_HALF_BYTES + kk * 2048, RT_KBLOCK, 1024);
-                        const uint64_t b_hi = smem_desc_sw128(pbase + kk * 2048, RT_KBLOCK, 1024);
-                        const uint64_t b_lo = smem_desc_sw128(pbase + RT_PPART + kk * 2048, RT_KBLOCK, 1024);
-                        mma3(tmem + COL_O, a_hi, a_lo, b_hi, b_lo, id2, !(first && kk == 0));
+                        const uint64_t bp = smem_desc_sw128(pbase + kk * 2048, RT_KBLOCK, 1024);
+                        mma_f16_ss(tmem + COL_O, a_hi, bp, id2w, !(first && kk == 0));
+                        mma_f16_ss(tmem + COL_O, a_lo, bp, id2n, true);
                     }
                     if (!resident) mma_commit(&m->x_empty[st]);
                     mma_commit(&m->c_free);
@@ -369,9 +366,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                             const uint32_t xo = kb * RT_KBLOCK + ks * 32, yo = kb * FwdPlan::Y_KB + ks * 32;
                             const uint64_t a_hi = smem_desc_sw128(xb + xo, 16, 1024);
                             const uint64_t a_lo = smem_desc_sw128(xb + RT_HALF_BYTES + xo, 16, 1024);
-                            const uint64_t b_hi = smem_desc_sw128(ybase + yo, 16, 1024);
-                            const uint64_t b_lo = smem_desc_sw128(ybase + FwdPlan::Y_PART + yo, 16, 1024);
-                            mma3(tmem + COL_S + buf * 32, a_hi, a_lo, b_hi, b_lo, id1, (kb | ks) != 0);
+                            const uint64_t by = smem_desc_sw128(ybase + yo, 16, 1024);
+                            mma_f16_ss(tmem + COL_S + buf * 64, a_hi, by, id1w, (kb | ks) != 0);
+                            mma_f16_ss(tmem + COL_S + buf * 64, a_lo, by, id1n, true);
                         }
                     mma_commit(&m->s_full[buf]);
                     if (jl > 0) gemm2(mit - 1, jl - 1, jl == 1);
@@ -388,8 +385,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                 mbar_wait(&m->s_full[buf], (eit >> 1) & 1);
                 RT_MARK(4);
                 tc_fence_after();
-                uint32_t v[16];
-                tmem_ld16(tmem + lane_base + COL_S + buf * 32 + 16 * half, v);
+                uint32_t v[16], w[16];
+                tmem_ld16(tmem + lane_base + COL_S + buf * 64 + 16 * half, v);
+                tmem_ld16(tmem + lane_base + COL_S + buf * 64 + 32 + 16 * half, w);
                 tmem_wait_ld();
                 tc_fence_before();
                 mbar_arrive(&m->s_free[buf]);
@@ -399,7 +397,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
 #pragma unroll
                     for (int s = 0; s < 16; ++s) {
                         // a = -(2 - 2 dot) / b^2 / 2 = (dot - 1) / b^2 with dot = S 2^-16   (src/mean_shift.py:65,68)
-                        const float av = (__uint_as_float(v[s]) - RT_XSCALE * RT_XSCALE) * a_mul;
+                        const float av = ((__uint_as_float(v[s]) + __uint_as_float(w[s])) - RT_XSCALE * RT_XSCALE) * a_mul;
                         p[s] = ex2_approx(fminf(fmaxf(av, PRIFIT_LO), PRIFIT_HI) * RT_LOG2E);
                     }
                 } else {
@@ -415,30 +413,32 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                 RT_MARK(6);
                 uint8_t* prow = smem + FwdPlan::p + (uint32_t)row * 128u;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const uint32_t off = (uint32_t)(((2 * half + c) ^ (row & 7)) << 4);
-                    *reinterpret_cast<uint4*>(prow + off) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
-                    *reinterpret_cast<uint4*>(prow + RT_PPART + off) = make_uint4(l[4 * c], l[4 * c + 1], l[4 * c + 2], l[4 * c + 3]);
+                for (int c = 0; c < 2; ++c) {          // p_hi: chunks 0-3 of the row, p_lo: chunks 4-7
+                    const uint32_t oh = (uint32_t)(((2 * half + c) ^ (row & 7)) << 4);
+                    const uint32_t ol = (uint32_t)(((4 + 2 * half + c) ^ (row & 7)) << 4);
+                    *reinterpret_cast<uint4*>(prow + oh) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+                    *reinterpret_cast<uint4*>(prow + ol) = make_uint4(l[4 * c], l[4 * c + 1], l[4 * c + 2], l[4 * c + 3]);
                 }
                 fence_proxy_async();
                 mbar_arrive(&m->c_full);
                 RT_MARK(7);
             }
             // partial numerators O^T (lane = column d) and denominators of this CTA's key slice
-            uint32_t v[16];
+            uint32_t v[16], w[16];
             if (ntl > 0) {
                 mbar_wait(&m->o_full, t & 1);
                 tc_fence_after();
                 tmem_ld16(tmem + lane_base + COL_O + 16 * half, v);
+                tmem_ld16(tmem + lane_base + COL_O + 32 + 16 * half, w);
                 tmem_wait_ld();
                 tc_fence_before();
             } else {
 #pragma unroll
-                for (int s = 0; s < 16; ++s) v[s] = 0u;
+                for (int s = 0; s < 16; ++s) { v[s] = 0u; w[s] = 0u; }
             }
 #pragma unroll
             for (int s = 0; s < 16; ++s)
-                part_o[(16 * half + s) * RT_D + row] = __uint_as_float(v[s]) * (1.0f / (RT_XSCALE * RT_PSCALE));
+                part_o[(16 * half + s) * RT_D + row] = (__uint_as_float(v[s]) + __uint_as_float(w[s])) * (1.0f / (RT_XSCALE * RT_PSCALE));
             if ((lane & 1) == 0) m->zwarp[ew][lane >> 1] = zlane;
             epi_bar();
             if (et < RT_SEEDS) {
@@ -450,46 +450,40 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
         it += ntl;
         cluster.sync();
         RT_MARK(12);
-        // ---- reduce over the cluster in fixed rank order; finish the owned seeds (src/mean_shift.py:75-82)
-        float nrm = 0.f, zsum = 0.f;
-        if (owner) {
-            float zq[RT_MAXC];
+        // ---- reduce over the cluster in fixed rank order; finish the owned seeds (src/mean_shift.py:75-82).
+        //      One warp per owned seed row, one float4 per lane: every remote load of the step is independent.
+        if (warp >= 4) {
+            for (int f = et; f < rpc * 32; f += RT_EPI) {
+                const int orow = rank * rpc + (f >> 5), c4 = f & 31;       // warp-uniform row
+                if (orow >= RT_SEEDS) break;
+                float zq[RT_MAXC];
+                float4 oq[RT_MAXC];
 #pragma unroll
-            for (int q = 0; q < RT_MAXC; ++q) zq[q] = q < csize ? cluster.map_shared_rank(m->part_z, q)[myrow] : 0.f;
-#pragma unroll
-            for (int q = 0; q < RT_MAXC; ++q) zsum += zq[q];
-            const float dinv = 1.0f / zsum;
-            float n2 = 0.f;
-            for (int col = tc; col < RT_D; col += tpr) {
-                float oq[RT_MAXC], s = 0.f;
-#pragma unroll
-                for (int q = 0; q < RT_MAXC; ++q) oq[q] = q < csize ? cluster.map_shared_rank(part_o, q)[myrow * RT_D + col] : 0.f;
-#pragma unroll
-                for (int q = 0; q < RT_MAXC; ++q) s += oq[q];
-                const float y = ys[myrow * RT_D + col];
-                const float mm = s * dinv - y;
-                const float u = y + mm;
-                urow[rr * RT_D + col] = u;
-                n2 = fmaf(u, u, n2);
-            }
-            m->red[et] = n2;
-        }
-        if (warp >= 4) epi_bar();
-        if (owner) {
-            for (int q = 0; q < tpr; ++q) nrm += m->red[rr * tpr + q];
-            nrm = sqrtf(nrm);
-            const bool live = myrow < nrows;
-            for (int col = tc; col < RT_D; col += tpr) {
-                const float ynew = urow[rr * RT_D + col] / nrm;
-                for (int q = 0; q < csize; ++q) cluster.map_shared_rank(ys, q)[myrow * RT_D + col] = ynew;
-                if (live) {
-                    traj_b[((size_t)(t + 1) * Kcap + k0 + myrow) * RT_D + col] = ynew;
-                    if (t == T - 1) a.C_out[((size_t)b * Kcap + k0 + myrow) * RT_D + col] = ynew;
+                for (int q = 0; q < RT_MAXC; ++q) {
+                    zq[q] = q < csize ? cluster.map_shared_rank(m->part_z, q)[orow] : 0.f;
+                    oq[q] = q < csize ? reinterpret_cast<const float4*>(cluster.map_shared_rank(part_o, q) + orow * RT_D)[c4]
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-            }
-            if (live && tc == 0) {
-                stat_b[((size_t)t * Kcap + k0 + myrow) * 2 + 0] = zsum;
-                stat_b[((size_t)t * Kcap + k0 + myrow) * 2 + 1] = nrm;
+                float zsum = 0.f;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < RT_MAXC; ++q) { zsum += zq[q]; o.x += oq[q].x; o.y += oq[q].y; o.z += oq[q].z; o.w += oq[q].w; }
+                const float dinv = 1.0f / zsum;
+                const float4 y = reinterpret_cast<const float4*>(ys + orow * RT_D)[c4];
+                float4 u;                                                  // new = y + ((K X) D - y)
+                u.x = y.x + (o.x * dinv - y.x); u.y = y.y + (o.y * dinv - y.y);
+                u.z = y.z + (o.z * dinv - y.z); u.w = y.w + (o.w * dinv - y.w);
+                const float nrm = sqrtf(warp_sum(fmaf(u.x, u.x, fmaf(u.y, u.y, fmaf(u.z, u.z, u.w * u.w)))));
+                const float4 yn = make_float4(u.x / nrm, u.y / nrm, u.z / nrm, u.w / nrm);   // new /= ||new||
+                for (int q = 0; q < csize; ++q) reinterpret_cast<float4*>(cluster.map_shared_rank(ys, q) + orow * RT_D)[c4] = yn;
+                if (orow < nrows) {
+                    reinterpret_cast<float4*>(traj_b + ((size_t)(t + 1) * Kcap + k0 + orow) * RT_D)[c4] = yn;
+                    if (t == T - 1) reinterpret_cast<float4*>(a.C_out + ((size_t)b * Kcap + k0 + orow) * RT_D)[c4] = yn;
+                    if (c4 == 0) {
+                        stat_b[((size_t)t * Kcap + k0 + orow) * 2 + 0] = zsum;
+                        stat_b[((size_t)t * Kcap + k0 + orow) * 2 + 1] = nrm;
+                    }
+                }
             }
         }
         RT_MARK(13);
@@ -500,7 +494,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 // ========================================================================================== backward
@@ -539,8 +533,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
         for (int s = 0; s < RT_STAGES; ++s) { mbar_init(&m->x_full[s], 1); mbar_init(&m->x_empty[s], 1); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&m->s_full[s], 1); mbar_init(&m->s_free[s], RT_EPI);
-            mbar_init(&m->gx_full[s], 1); mbar_init(&m->gx_free[s], RT_EPI);
         }
+        mbar_init(&m->gx_full, 1); mbar_init(&m->gx_free, RT_EPI);
         mbar_init(&m->c_full, RT_EPI); mbar_init(&m->c_free, 1);
         mbar_init(&m->o_full, 1); mbar_init(&m->y_full, RT_EPI);
         fence_barrier_init();
@@ -551,9 +545,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = m->tmem_base;
-    constexpr uint32_t COL_S = 0 /* [buf][S1 32 | S2 32] */, COL_GY = 128, COL_GX = 256 /* [buf][128] */;
+    // S[buf]: [x.y_hi | x.gm_hi | x_hi.y_lo | x_hi.gm_lo] (32 columns each); GY: [x.ds_hi | x_hi.ds_lo]; GX: one 128-column accumulator
+    constexpr uint32_t COL_S = 0, COL_GY = 256, COL_GX = 384;
 
-    const float* Xb = a.X + (size_t)b * N * RT_D;
     float* gXb = a.gX + (size_t)b * N * RT_D;
     const float* traj_b = a.traj_in + (size_t)b * (T + 1) * Kcap * RT_D;
     const float* stat_b = a.stat_in + (size_t)b * T * Kcap * 2;
@@ -597,35 +591,42 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                 __syncwarp();
             } else if (warp == 1) {
                 if (lane == 0) {
-                    constexpr uint32_t id1 = idesc_f16_mm(RT_KEYS, RT_SEEDS, false, false);   // S1^T, S2^T
-                    constexpr uint32_t id2 = idesc_f16_mm(RT_D, RT_SEEDS, true, true);        // gy^T += X^T . ds^T
-                    constexpr uint32_t id3 = idesc_f16_mm(RT_KEYS, RT_D, false, true);        // gX = [ds|e1] . [Y;Gm]
+                    constexpr uint32_t id1w = idesc_f16_mm(RT_KEYS, 4 * RT_SEEDS, false, false);  // x_hi . [y_hi; gm_hi; y_lo; gm_lo]^T
+                    constexpr uint32_t id1n = idesc_f16_mm(RT_KEYS, 2 * RT_SEEDS, false, false);  // x_lo . [y_hi; gm_hi]^T
+                    constexpr uint32_t id2w = idesc_f16_mm(RT_D, 2 * RT_SEEDS, true, true);       // x_hi^T . [ds_hi | ds_lo]
+                    constexpr uint32_t id2n = idesc_f16_mm(RT_D, RT_SEEDS, true, true);           // x_lo^T . ds_hi
+                    constexpr uint32_t id3 = idesc_f16_mm(RT_KEYS, RT_D, false, true);            // gX = [ds | e1] . [Y ; Gm]
                     const uint32_t ygbase = smem_u32(smem + BwdPlan::yg), cbase = smem_u32(smem + BwdPlan::de);
                     auto gemm_g = [&](uint32_t i, int jl, bool first) {
-                        const uint32_t st = resident ? (uint32_t)jl : i % RT_STAGES, buf = i & 1;
+                        const uint32_t st = resident ? (uint32_t)jl : i % RT_STAGES;
                         mbar_wait(&m->c_full, i & 1);
-                        mbar_wait(&m->gx_free[buf], ((i >> 1) & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t xb = smem_u32(smem + (size_t)st * RT_STAGE_BYTES);
 #pragma unroll
                         for (int kk = 0; kk < RT_KEYS / 16; ++kk) {
                             const uint64_t a_hi = smem_desc_sw128(xb + kk * 2048, RT_KBLOCK, 1024);
                             const uint64_t a_lo = smem_desc_sw128(xb + RT_HALF_BYTES + kk * 2048, RT_KBLOCK, 1024);
-                            const uint64_t b_hi = smem_desc_sw128(cbase + kk * 2048, RT_KBLOCK, 1024);
-                            const uint64_t b_lo = smem_desc_sw128(cbase + RT_PPART + kk * 2048, RT_KBLOCK, 1024);
-                            mma3(tmem + COL_GY, a_hi, a_lo, b_hi, b_lo, id2, !(first && kk == 0));
+                            const uint64_t bd = smem_desc_sw128(cbase + kk * 2048, RT_KBLOCK, 1024);
+                            mma_f16_ss(tmem + COL_GY, a_hi, bd, id2w, !(first && kk == 0));
+                            mma_f16_ss(tmem + COL_GY, a_lo, bd, id2n, true);
                         }
+                        mbar_wait(&m->gx_free, (i & 1) ^ 1);           // the previous tile's gX has been read out
+                        tc_fence_after();
+                        // K pairs (coefficient columns, operand rows): (ds_hi, y_hi) (ds_hi, y_lo) (ds_lo, y_hi)
+                        //                                              (e1_hi, gm_hi) (e1_hi, gm_lo) (e1_lo, gm_hi)
+                        constexpr uint32_t a_off[6] = {0, 0, 64, RT_PPART, RT_PPART, RT_PPART + 64};
+                        constexpr uint32_t b_row[6] = {0, 64, 0, 32, 96, 32};
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {               // K = 64: seeds of ds (0,1), seeds of e1 (2,3)
-                            const uint64_t a_hi = smem_desc_sw128(cbase + ks * 32, 16, 1024);
-                            const uint64_t a_lo = smem_desc_sw128(cbase + RT_PPART + ks * 32, 16, 1024);
-                            const uint64_t b_hi = smem_desc_sw128(ygbase + ks * 2048, BwdPlan::YG_KB, 1024);
-                            const uint64_t b_lo = smem_desc_sw128(ygbase + BwdPlan::YG_PART + ks * 2048, BwdPlan::YG_KB, 1024);
-                            mma3(tmem + COL_GX + buf * 128, a_hi, a_lo, b_hi, b_lo, id3, ks != 0);
-                        }
+                        for (int pr = 0; pr < 6; ++pr)
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {           // 16 seeds per MMA
+                                const uint64_t ad = smem_desc_sw128(cbase + a_off[pr] + ks * 32, 16, 1024);
+                                const uint64_t bd = smem_desc_sw128(ygbase + (b_row[pr] + 16 * ks) * 128, BwdPlan::YG_KB, 1024);
+                                mma_f16_ss(tmem + COL_GX, ad, bd, id3, (pr | ks) != 0);
+                            }
                         if (!resident) mma_commit(&m->x_empty[st]);
                         mma_commit(&m->c_free);
-                        mma_commit(&m->gx_full[buf]);
+                        mma_commit(&m->gx_full);
                     };
                     mbar_wait(&m->y_full, itn & 1);
                     tc_fence_after();
@@ -638,19 +639,16 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                         tc_fence_after();
                         const uint32_t xb = smem_u32(smem + (size_t)st * RT_STAGE_BYTES);
 #pragma unroll
-                        for (int which = 0; which < 2; ++which)        // 0: y^t rows, 1: g_m rows of the stacked tile
+                        for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                            for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    const uint32_t xo = kb * RT_KBLOCK + ks * 32;
-                                    const uint32_t yo = kb * BwdPlan::YG_KB + which * (RT_SEEDS * 128) + ks * 32;
-                                    const uint64_t a_hi = smem_desc_sw128(xb + xo, 16, 1024);
-                                    const uint64_t a_lo = smem_desc_sw128(xb + RT_HALF_BYTES + xo, 16, 1024);
-                                    const uint64_t b_hi = smem_desc_sw128(ygbase + yo, 16, 1024);
-                                    const uint64_t b_lo = smem_desc_sw128(ygbase + BwdPlan::YG_PART + yo, 16, 1024);
-                                    mma3(tmem + COL_S + buf * 64 + which * 32, a_hi, a_lo, b_hi, b_lo, id1, (kb | ks) != 0);
-                                }
+                            for (int ks = 0; ks < 4; ++ks) {           // 16 d-elements (32 B) per MMA
+                                const uint32_t xo = kb * RT_KBLOCK + ks * 32;
+                                const uint64_t a_hi = smem_desc_sw128(xb + xo, 16, 1024);
+                                const uint64_t a_lo = smem_desc_sw128(xb + RT_HALF_BYTES + xo, 16, 1024);
+                                const uint64_t bd = smem_desc_sw128(ygbase + kb * BwdPlan::YG_KB + ks * 32, 16, 1024);
+                                mma_f16_ss(tmem + COL_S + buf * 128, a_hi, bd, id1w, (kb | ks) != 0);
+                                mma_f16_ss(tmem + COL_S + buf * 128, a_lo, bd, id1n, true);
+                            }
                         mma_commit(&m->s_full[buf]);
                         if (jl > 0) gemm_g(mit - 1, jl - 1, jl == 1);
                     }
@@ -745,8 +743,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] = gms[r * RT_D + 8 * c8 + e] * sg;
                     }
-                    uint8_t* hi_blk = smem + BwdPlan::yg + (c8 >> 3) * BwdPlan::YG_KB + which * (RT_SEEDS * 128);
-                    store_chunk_hilo(hi_blk, hi_blk + BwdPlan::YG_PART, r, c8 & 7, f);
+                    uint8_t* hi_blk = smem + BwdPlan::yg + (c8 >> 3) * BwdPlan::YG_KB + which * BwdPlan::YG_ROWS;
+                    store_chunk_hilo(hi_blk, hi_blk + 2 * BwdPlan::YG_ROWS, r, c8 & 7, f);
                 }
                 float gmm_r[16], dinv_r[16];
 #pragma unroll
@@ -759,17 +757,16 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                 const float s2_mul = 1.0f / (RT_XSCALE * sg), ds_mul = sd / b2;
                 const float gx_mul = 1.0f / (sd * RT_XSCALE);
                 auto flush = [&](uint32_t i, int jl) {                 // gX accumulator of tile i -> global (rows owned by this CTA)
-                    const uint32_t buf = i & 1;
-                    mbar_wait(&m->gx_full[buf], (i >> 1) & 1);
+                    mbar_wait(&m->gx_full, i & 1);
                     tc_fence_after();
                     uint32_t g0[32], g1[32];
-                    tmem_ld32(tmem + lane_base + COL_GX + buf * 128 + 64 * half, g0);
-                    tmem_ld32(tmem + lane_base + COL_GX + buf * 128 + 64 * half + 32, g1);
+                    tmem_ld32(tmem + lane_base + COL_GX + 64 * half, g0);
+                    tmem_ld32(tmem + lane_base + COL_GX + 64 * half + 32, g1);
                     tmem_wait_ld();
                     tc_fence_before();
-                    mbar_arrive(&m->gx_free[buf]);
+                    mbar_arrive(&m->gx_free);
                     const int key = (j0 + jl) * RT_KEYS + row;
-                    if (key < N) {
+                    if (key < N && !(a.dbg & 2)) {
                         // fire-and-forget vector reductions: no read round trip on the critical path
                         float* dst = gXb + (size_t)key * RT_D + 64 * half;
 #pragma unroll
@@ -789,9 +786,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                     mbar_wait(&m->s_full[buf], (eit >> 1) & 1);
                     RT_MARK(4);
                     tc_fence_after();
-                    uint32_t v1[16], v2[16];
-                    tmem_ld16(tmem + lane_base + COL_S + buf * 64 + 16 * half, v1);
-                    tmem_ld16(tmem + lane_base + COL_S + buf * 64 + 32 + 16 * half, v2);
+                    uint32_t v1[16], v2[16], w1[16], w2[16];
+                    tmem_ld16(tmem + lane_base + COL_S + buf * 128 + 16 * half, v1);
+                    tmem_ld16(tmem + lane_base + COL_S + buf * 128 + 32 + 16 * half, v2);
+                    tmem_ld16(tmem + lane_base + COL_S + buf * 128 + 64 + 16 * half, w1);
+                    tmem_ld16(tmem + lane_base + COL_S + buf * 128 + 96 + 16 * half, w2);
                     tmem_wait_ld();
                     tc_fence_before();
                     mbar_arrive(&m->s_free[buf]);
@@ -803,10 +802,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
                             const int s = 2 * s2i + u;
-                            const float av = (__uint_as_float(v1[s]) - RT_XSCALE * RT_XSCALE) * a_mul;    // (dot - 1) / b^2
+                            const float av = ((__uint_as_float(v1[s]) + __uint_as_float(w1[s])) - RT_XSCALE * RT_XSCALE) * a_mul;    // (dot - 1) / b^2
                             const float kap = ex2_approx(fminf(fmaxf(av, PRIFIT_LO), PRIFIT_HI) * RT_LOG2E);
                             const bool inr = (av >= PRIFIT_LO) && (av <= PRIFIT_HI);
-                            const float dk = (__uint_as_float(v2[s]) * s2_mul - gmm_r[s]) * dinv_r[s];
+                            const float dk = ((__uint_as_float(v2[s]) + __uint_as_float(w2[s])) * s2_mul - gmm_r[s]) * dinv_r[s];
                             dsv[u] = (inr && live) ? (kap * dk) * ds_mul : 0.f;
                             e1v[u] = live ? (kap * dinv_r[s]) * se : 0.f;
                         }
@@ -818,13 +817,13 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                     RT_MARK(6);
                     uint8_t* crow = smem + BwdPlan::de + (uint32_t)row * 128u;
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const uint32_t od = (uint32_t)(((2 * half + c) ^ (row & 7)) << 4);          // ds: seeds 16 half + 8 c ..
-                        const uint32_t oe = (uint32_t)(((4 + 2 * half + c) ^ (row & 7)) << 4);      // e1: K index 32 + ..
-                        *reinterpret_cast<uint4*>(crow + od) = make_uint4(dh[4 * c], dh[4 * c + 1], dh[4 * c + 2], dh[4 * c + 3]);
-                        *reinterpret_cast<uint4*>(crow + RT_PPART + od) = make_uint4(dl[4 * c], dl[4 * c + 1], dl[4 * c + 2], dl[4 * c + 3]);
-                        *reinterpret_cast<uint4*>(crow + oe) = make_uint4(eh[4 * c], eh[4 * c + 1], eh[4 * c + 2], eh[4 * c + 3]);
-                        *reinterpret_cast<uint4*>(crow + RT_PPART + oe) = make_uint4(el[4 * c], el[4 * c + 1], el[4 * c + 2], el[4 * c + 3]);
+                    for (int c = 0; c < 2; ++c) {          // block 0: [ds_hi | ds_lo], block 1: [e1_hi | e1_lo]; hi = chunks 0-3, lo = chunks 4-7
+                        const uint32_t oh = (uint32_t)(((2 * half + c) ^ (row & 7)) << 4);
+                        const uint32_t ol = (uint32_t)(((4 + 2 * half + c) ^ (row & 7)) << 4);
+                        *reinterpret_cast<uint4*>(crow + oh) = make_uint4(dh[4 * c], dh[4 * c + 1], dh[4 * c + 2], dh[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(crow + ol) = make_uint4(dl[4 * c], dl[4 * c + 1], dl[4 * c + 2], dl[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(crow + RT_PPART + oh) = make_uint4(eh[4 * c], eh[4 * c + 1], eh[4 * c + 2], eh[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(crow + RT_PPART + ol) = make_uint4(el[4 * c], el[4 * c + 1], el[4 * c + 2], el[4 * c + 3]);
                     }
                     fence_proxy_async();
                     mbar_arrive(&m->c_full);
@@ -835,35 +834,41 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                 if (ntl > 0) flush(eit - 1, ntl - 1);
                 RT_MARK(9);
                 // partial dL/dy^t of this CTA's keys (lane = column d); the coefficient tile is dead now
-                uint32_t v[16];
+                uint32_t v[16], w[16];
                 if (ntl > 0) {
                     mbar_wait(&m->o_full, itn & 1);
                     tc_fence_after();
                     tmem_ld16(tmem + lane_base + COL_GY + 16 * half, v);
+                    tmem_ld16(tmem + lane_base + COL_GY + 32 + 16 * half, w);
                     tmem_wait_ld();
                     tc_fence_before();
                 } else {
 #pragma unroll
-                    for (int s = 0; s < 16; ++s) v[s] = 0u;
+                    for (int s = 0; s < 16; ++s) { v[s] = 0u; w[s] = 0u; }
                 }
                 RT_MARK(10);
                 epi_bar();                                             // all flush() loads of this CTA are done with TMEM
 #pragma unroll
-                for (int s = 0; s < 16; ++s) part_o[(16 * half + s) * RT_D + row] = __uint_as_float(v[s]) * gx_mul;
+                for (int s = 0; s < 16; ++s) part_o[(16 * half + s) * RT_D + row] = (__uint_as_float(v[s]) + __uint_as_float(w[s])) * gx_mul;
                 RT_MARK(11);
             }
             it += ntl;
             x_loaded = true;
             cluster.sync();
             RT_MARK(12);
-            if (owner) {
-                for (int col = tc; col < RT_D; col += tpr) {
-                    float oq[RT_MAXC], s = 0.f;
+            if (warp >= 4) {
+                for (int f = et; f < rpc * 32; f += RT_EPI) {
+                    const int orow = rank * rpc + (f >> 5), c4 = f & 31;
+                    if (orow >= RT_SEEDS) break;
+                    float4 oq[RT_MAXC];
 #pragma unroll
-                    for (int q = 0; q < RT_MAXC; ++q) oq[q] = q < csize ? cluster.map_shared_rank(part_o, q)[myrow * RT_D + col] : 0.f;
+                    for (int q = 0; q < RT_MAXC; ++q)
+                        oq[q] = q < csize ? reinterpret_cast<const float4*>(cluster.map_shared_rank(part_o, q) + orow * RT_D)[c4]
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int q = 0; q < RT_MAXC; ++q) s += oq[q];
-                    for (int q = 0; q < csize; ++q) cluster.map_shared_rank(gy, q)[myrow * RT_D + col] = s;
+                    for (int q = 0; q < RT_MAXC; ++q) { o.x += oq[q].x; o.y += oq[q].y; o.z += oq[q].z; o.w += oq[q].w; }
+                    for (int q = 0; q < csize; ++q) reinterpret_cast<float4*>(cluster.map_shared_rank(gy, q) + orow * RT_D)[c4] = o;
                 }
             }
             RT_MARK(13);
@@ -928,11 +933,11 @@ extern "C" int prifit_debug_rows_timeline(long long* host_pairs, int max_pairs) 
 }
 
 static int rows_dbg_begin() {
-    const char* e = getenv("PRIFIT_ROWS_TIMELINE");
+    const char* e = getenv("PRIFIT_ROWS_TIMELINE");        // bit 0: record the phase timeline; bit 1: skip the gX flush (timing experiment)
     if (!e || atoi(e) == 0) return 0;
     int zero = 0;
-    cudaMemcpyToSymbol(g_rt_dbg_n, &zero, sizeof(int));
-    return 1;
+    if (atoi(e) & 1) cudaMemcpyToSymbol(g_rt_dbg_n, &zero, sizeof(int));
+    return atoi(e);
 }
 
 size_t prifit_rows_tc_workspace_bytes(int B, int N) { return (size_t)2 * B * N * RT_D * sizeof(__half) + 256; }

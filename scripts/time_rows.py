@@ -33,7 +33,7 @@ def main():
     gX = torch.zeros_like(X)
     print("B=%d N=%d K=%s kcap=%d" % (B, N, res.K_host[:4], res.kcap))
     for engine, name in ((1, "simt"), (0, "tc")):
-        for cs in ([0] if engine == 1 else [8, 7, 6, 5, 4, 3, 2]):
+        for cs in ([0] if engine == 1 else [int(c) for c in os.environ.get("CS_LIST", "8,4").split(",")]):
             if cs:
                 os.environ["PRIFIT_ROWS_CLUSTER"] = str(cs)
             traj, stat, C = ops.rows_fwd(X, res.bw, res.idx, res.K, 10, res.kcap, engine)
