@@ -220,6 +220,54 @@ def test_rows_fwd_bwd_vs_oracle_autograd(cuda, n, k, T, kcap, engine):
     assert rel_err(Xc.grad, Xd.grad) < 1e-4
 
 
+@pytest.mark.parametrize("engine", ROWS_ENGINES)
+@pytest.mark.parametrize("T", [0, 1])
+def test_rows_degenerate_iteration_counts(cuda, engine, T):
+    """T = 0: center = X[idx] and the gradient lands on the seeds' own rows; T = 1: a single step."""
+    from prifit_b200 import ops
+
+    n, k, kcap = 260, 6, 32
+    g = torch.Generator().manual_seed(4)
+    X = torch.stack([_unit(n, 128, 21), _unit(n, 128, 22)])
+    bw = torch.tensor([0.7, 0.9])
+    ids = torch.stack([torch.randperm(n, generator=g)[:k].sort()[0] for _ in range(2)])
+    gC = torch.randn(2, k, 128, generator=g)
+    Xd = X.double().requires_grad_(True)
+    ref_C = torch.stack([R.mean_shift_iterations(Xd[b], bw[b].double(), T)[ids[b]] for b in range(2)])
+    (ref_C * gC.double()).sum().backward()
+    idx = torch.full((2, kcap), -1, dtype=torch.int32)
+    idx[:, :k] = ids.int()
+    Xc = X.to(cuda).requires_grad_(True)
+    C = ops.SeedCentres.apply(Xc, bw.to(cuda), idx.to(cuda), torch.tensor([k, k], dtype=torch.int32, device=cuda), T, engine)
+    gpad = torch.zeros(2, kcap, 128)
+    gpad[:, :k] = gC
+    (C * gpad.to(cuda)).sum().backward()
+    assert rel_err(C[:, :k], ref_C) < 1e-5
+    assert float(C[:, k:].abs().max()) == 0.0
+    assert rel_err(Xc.grad, Xd.grad) < 1e-4
+
+
+def test_rows_tensor_core_result_is_independent_of_the_batch(cuda):
+    """Shard invariance: a shape's trajectories and gradient are bit-identical whether it is processed alone
+    or inside a larger batch (fixed cluster size and summation order)."""
+    from prifit_b200 import ops, pipeline, synthetic
+
+    E, _, _ = synthetic.planted_shapes(5, n_points=1000, n_clusters=7, seed=9)
+    X = ops.normalize_fwd(E.to(cuda))
+    res = pipeline.cluster_batch(X, 1000, 0.05, 6, 25)
+    gC = torch.randn(5, res.kcap, 128, generator=torch.Generator().manual_seed(1)).to(cuda)
+
+    def run(sl):
+        Xc = X[sl].clone().requires_grad_(True)
+        C = ops.SeedCentres.apply(Xc, res.bw[sl].contiguous(), res.idx[sl].contiguous(), res.K[sl].contiguous(), 6, 0)
+        (C * gC[sl]).sum().backward()
+        return C.detach(), Xc.grad
+
+    C_all, g_all = run(slice(0, 5))
+    C_one, g_one = run(slice(3, 4))
+    assert torch.equal(C_all[3:4], C_one) and torch.equal(g_all[3:4], g_one)
+
+
 @pytest.mark.parametrize("n,kc,T", [(2048, 16, 10), (1500, 9, 10), (10000, 40, 10)])
 def test_rows_engines_agree_on_planted_shapes(cuda, n, kc, T):
     """cfg2 / cfg4-like planted shapes: tensor-core (split-fp16) trajectories and their backward against the
