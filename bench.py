@@ -157,7 +157,7 @@ def run_ours(args):
         ops.TIMING = ms_events if timed else None
         out = pipeline.fit_loss(E, dev_P[i % N_SETS], quantile=q, iterations=T, max_num_clusters=kmax)
         ops.TIMING = None
-        L, Lb = pdist.global_masked_mean(out["loss_b"], out["has"])
+        L, Lb = pdist.global_loss(out)
         Lb.backward()
         return L, out
 

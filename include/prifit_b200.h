@@ -138,6 +138,17 @@ int prifit_sdf_loss_bwd(const float* Q, const float* s, const float* V, const fl
                         const int32_t* K, const int32_t* argmin, const float* gloss, int B, int M, int Kcap,
                         float* gs_out, float* gV_out, float* gc_out, float* gQ_out, void* stream);
 
+/* batch mean of the per-shape losses.  src/utils.py:418,425 (mean over the shapes that kept at least one
+ *   ellipsoid) and train_partseg_shapenet.py:445 (mean over the replicas).
+ *   has_out[B] = 1 if any valid[b,:] else 0;  stats_out[3] = { sum_b loss_b has_b, sum_b has_b, sum / max(n, 1) }.
+ *   One CTA; deterministic summation order. */
+int prifit_masked_mean_fwd(const float* loss_b, const uint8_t* valid, int B, int Kcap, float* has_out,
+                           float* stats_out, void* stream);
+/* gloss_out[b] = has[b] * (g_sum + g_mean / max(n, 1));  g_sum / g_mean: device scalars, either may be NULL;
+ *   n = stats[1] of the forward call. */
+int prifit_masked_mean_bwd(const float* g_sum, const float* g_mean, const float* has, const float* stats, int B,
+                           float* gloss_out, void* stream);
+
 /* diagnostics -- hardware self-test of the tcgen05 / TMA descriptor encodings the tensor-core engine
  *   uses: D[128,128] = A . B^T (mode 0: B K-major in shared memory) or A . B (mode 1: B MN-major), A staged
  *   in tensor memory, B fetched by TMA with SWIZZLE_128B; lbo/sbo = descriptor byte offsets under test.

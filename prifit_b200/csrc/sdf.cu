@@ -165,6 +165,36 @@ __global__ void __launch_bounds__(SDF_THREADS) sdf_bwd_points_kernel(
     out[0] = dpt[0]; out[1] = dpt[1]; out[2] = dpt[2];
 }
 
+// ---- batch mean over the shapes that kept at least one ellipsoid (src/utils.py:418,425)
+__global__ void __launch_bounds__(256) masked_mean_fwd_kernel(const float* __restrict__ loss_b, const uint8_t* __restrict__ valid,
+                                                              int B, int Kcap, float* __restrict__ has_out, float* __restrict__ stats) {
+    __shared__ float red[2 * 32];
+    float acc[2] = {0.f, 0.f};
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        int any = 0;
+        for (int k = 0; k < Kcap; ++k) any |= valid[(size_t)b * Kcap + k];
+        const float h = any ? 1.0f : 0.0f;
+        has_out[b] = h;
+        acc[0] += any ? loss_b[b] : 0.f;
+        acc[1] += h;
+    }
+    block_sum<2>(acc, red);
+    if (threadIdx.x == 0) {
+        stats[0] = acc[0];
+        stats[1] = acc[1];
+        stats[2] = acc[0] / fmaxf(acc[1], 1.0f);
+    }
+}
+
+__global__ void masked_mean_bwd_kernel(const float* __restrict__ g_sum, const float* __restrict__ g_mean,
+                                       const float* __restrict__ has, const float* __restrict__ stats, int B,
+                                       float* __restrict__ gloss) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float g = (g_sum ? g_sum[0] : 0.f) + (g_mean ? g_mean[0] / fmaxf(stats[1], 1.0f) : 0.f);
+    gloss[b] = has[b] * g;
+}
+
 }  // namespace
 
 extern "C" size_t prifit_sdf_workspace_bytes(int B, int M) {
@@ -199,5 +229,23 @@ extern "C" int prifit_sdf_loss_bwd(const float* Q, const float* s, const float* 
         sdf_bwd_points_kernel<<<dim3((M + SDF_THREADS - 1) / SDF_THREADS, B), SDF_THREADS, 0, pf_stream(stream)>>>(Q, s, V, c, argmin, gloss, M, Kcap, gQ_out);
         PF_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+extern "C" int prifit_masked_mean_fwd(const float* loss_b, const uint8_t* valid, int B, int Kcap, float* has_out,
+                                      float* stats_out, void* stream) {
+    PF_CHECK_ARG(loss_b && valid && has_out && stats_out, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(B > 0 && Kcap > 0, PRIFIT_E_BADARG, "B, Kcap > 0 required");
+    masked_mean_fwd_kernel<<<1, 256, 0, pf_stream(stream)>>>(loss_b, valid, B, Kcap, has_out, stats_out);
+    PF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int prifit_masked_mean_bwd(const float* g_sum, const float* g_mean, const float* has, const float* stats, int B,
+                                      float* gloss_out, void* stream) {
+    PF_CHECK_ARG(has && stats && gloss_out, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(B > 0, PRIFIT_E_BADARG, "B > 0 required");
+    masked_mean_bwd_kernel<<<(B + 127) / 128, 128, 0, pf_stream(stream)>>>(g_sum, g_mean, has, stats, B, gloss_out);
+    PF_LAUNCH_CHECK();
     return 0;
 }

@@ -35,3 +35,14 @@ def global_mean_from_local(local_mean, n_local, group=None):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
     n = tot[1].clamp(min=1.0)
     return tot[0] / n, local[0] / n
+
+
+def global_loss(out, group=None):
+    """Same reduction from pipeline.fit_loss()'s fused outputs (`loss_sum`, `n_valid`, `loss`): on one rank the
+    local mean is the global mean and nothing is enqueued."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return out["loss"].detach(), out["loss"]
+    tot = torch.stack([out["loss_sum"].detach(), out["n_valid"]])
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    n = tot[1].clamp(min=1.0)
+    return tot[0] / n, out["loss_sum"] / n

@@ -326,3 +326,89 @@ class SdfLoss(torch.autograd.Function):
         Q, s, V, c, valid, K, argmin = ctx.saved_tensors
         gs, gV, gc, gQ = sdf_bwd(Q, s, V, c, valid, K, argmin, gloss.contiguous(), ctx.needs_input_grad[0])
         return gQ, gs, gV, gc, None, None
+
+
+# ------------------------------------------------------------------ fused nodes of the batched pipeline
+# The stages between the guard read-back and the start of the heavy backward kernels are microsecond-scale
+# launches; as separate autograd nodes (plus torch reductions for the batch mean) the device waits for the
+# host between them.  These two nodes enqueue the same C-ABI calls back to back.
+def masked_mean_fwd(loss_b, valid):
+    B, kcap = valid.shape
+    has = torch.empty(B, dtype=torch.float32, device=loss_b.device)
+    stats = torch.empty(3, dtype=torch.float32, device=loss_b.device)
+    _lib.call("prifit_masked_mean_fwd", _ptr(loss_b), _ptr(valid), B, kcap, _ptr(has), _ptr(stats), _stream())
+    return has, stats
+
+
+def masked_mean_bwd(g_sum, g_mean, has, stats):
+    gloss = torch.empty_like(has)
+    _lib.call("prifit_masked_mean_bwd", _ptr(g_sum), _ptr(g_mean), _ptr(has), _ptr(stats), has.numel(), _ptr(gloss), _stream())
+    return gloss
+
+
+class SoftMemberships(torch.autograd.Function):
+    """SeedCentres followed by Membership as one node: (X, bw, idx, K) -> (W[B,Kcap,N], C[B,Kcap,d]).
+    Backward accumulates both input gradients into one dL/dX buffer."""
+
+    @staticmethod
+    def forward(ctx, X, bw, idx, K, iterations, engine=None):
+        X = _chk(X)
+        kcap = idx.shape[1]
+        traj, stat, C = rows_fwd(X, bw, idx, K, iterations, kcap, engine)
+        W, smax = membership_fwd(C, X, bw, K)
+        ctx.save_for_backward(X, bw, idx, K, traj, stat, C, W, smax)
+        ctx.iterations, ctx.kcap, ctx.engine = int(iterations), kcap, engine
+        ctx.set_materialize_grads(False)
+        return W, C
+
+    @staticmethod
+    def backward(ctx, gW, gC_ext):
+        X, bw, idx, K, traj, stat, C, W, smax = ctx.saved_tensors
+        if gW is None and gC_ext is None:
+            return None, None, None, None, None, None
+        gX = torch.zeros_like(X)
+        gC = gC_ext
+        if gW is not None:
+            gC = membership_bwd(C, X, bw, K, W, smax, gW.contiguous(), gX)
+            if gC_ext is not None:
+                gC = gC + gC_ext
+        rows_bwd(X, bw, idx, K, traj, stat, gC.contiguous(), gX, ctx.iterations, ctx.kcap, ctx.engine)
+        return gX, None, None, None, None, None
+
+
+class FitSdfMean(torch.autograd.Function):
+    """EllipsoidFit -> SdfLoss -> batch mean as one node.
+    (P, Q, W, K, noise) -> (loss_sum, loss_mean, loss_b, s, V, c, valid, has, n_valid); gradients flow from
+    loss_sum / loss_mean / loss_b / s / V / c back to W (and to P, Q when they require grad)."""
+
+    @staticmethod
+    def forward(ctx, P, Q, W, K, noise):
+        P, Q, W, noise = _chk(P), _chk(Q), _chk(W), _chk(noise)
+        s, V, c, valid, fctx = fit_fwd(P, W, K, noise)
+        loss_b, argmin, _sdf = sdf_fwd(Q, s, V, c, valid, K)
+        has, stats = masked_mean_fwd(loss_b, valid)
+        ctx.save_for_backward(P, Q, W, K, noise, fctx, valid, s, V, c, argmin, has, stats)
+        ctx.set_materialize_grads(False)
+        loss_sum, n_valid, loss_mean = stats.unbind(0)
+        ctx.mark_non_differentiable(valid, has, n_valid)
+        return loss_sum, loss_mean, loss_b, s, V, c, valid, has, n_valid
+
+    @staticmethod
+    def backward(ctx, g_sum, g_mean, g_lb, g_s, g_V, g_c, _gv, _gh, _gn):
+        P, Q, W, K, noise, fctx, valid, s, V, c, argmin, has, stats = ctx.saved_tensors
+        if g_sum is None and g_mean is None:
+            gloss = torch.zeros_like(has) if g_lb is None else g_lb.contiguous()
+        else:
+            gloss = masked_mean_bwd(None if g_sum is None else g_sum.contiguous(),
+                                    None if g_mean is None else g_mean.contiguous(), has, stats)
+            if g_lb is not None:
+                gloss = gloss + g_lb
+        gs, gV, gc, gQ = sdf_bwd(Q, s, V, c, valid, K, argmin, gloss, ctx.needs_input_grad[1])
+        if g_s is not None:
+            gs = gs + g_s
+        if g_V is not None:
+            gV = gV + g_V
+        if g_c is not None:
+            gc = gc + g_c
+        gW, gP = fit_bwd(P, W, K, noise, fctx, valid, gs, gV, gc, ctx.needs_input_grad[0])
+        return gP, gQ, gW, None, None

@@ -154,8 +154,7 @@ def cluster_batch(X, num_samples, quantile, iterations, max_num_clusters, engine
 
 def soft_memberships(X, res: ClusterResult):
     """Differentiable part of clustering(): fp32 centres of the K seeds + membership.  W[B,Kcap,N]."""
-    C = ops.SeedCentres.apply(X, res.bw, res.idx, res.K, res.iterations)
-    return ops.Membership.apply(C, X, res.bw, res.K), C
+    return ops.SoftMemberships.apply(X, res.bw, res.idx, res.K, res.iterations)
 
 
 def draw_noise(K_host, kcap, device):
@@ -202,8 +201,7 @@ def fit_loss(E, P, quantile=0.05, iterations=10, max_num_clusters=25, noise=None
         W, C = soft_memberships(X, res)
     if noise is None:
         noise = draw_noise(res.K_host, res.kcap, X.device)
-    s, V, c, valid = ops.EllipsoidFit.apply(P, W, res.K, noise)
-    loss_b = ops.SdfLoss.apply(P if Q is None else Q, s, V, c, valid, res.K)
-    loss, has = masked_mean(loss_b, valid)
-    return {"loss": loss, "loss_b": loss_b, "has": has, "s": s, "V": V, "c": c, "valid": valid,
-            "cluster": res, "W": W, "C": C, "X": X, "noise": noise}
+    # fit -> SDF loss -> batch mean as one autograd node (three launches back to back)
+    loss_sum, loss, loss_b, s, V, c, valid, has, n_valid = ops.FitSdfMean.apply(P, P if Q is None else Q, W, res.K, noise)
+    return {"loss": loss, "loss_sum": loss_sum, "n_valid": n_valid, "loss_b": loss_b, "has": has, "s": s, "V": V, "c": c,
+            "valid": valid, "cluster": res, "W": W, "C": C, "X": X, "noise": noise}

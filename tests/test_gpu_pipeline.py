@@ -248,3 +248,56 @@ def test_guard_loop_full_size(cuda):
     assert res.passes[0] == info[0]["passes"] and res.passes[0] >= 2
     assert res.K_host[0] == info[0]["ids"].shape[0]
     assert max(res.n_labels_host) <= 25
+
+
+def test_fused_nodes_match_separate_nodes(cuda):
+    """pipeline.fit_loss runs SoftMemberships / FitSdfMean (several C-ABI calls per autograd node); the same
+    calls as separate nodes + torch reductions must give the same loss and the same input gradient."""
+    from prifit_b200 import ops, pipeline, synthetic
+
+    E, P, _ = synthetic.planted_shapes(3, n_points=640, n_clusters=5, seed=77)
+    noise = torch.rand(3, 32, 3, 3, generator=torch.Generator().manual_seed(5)).to(cuda)
+    fused = _run(E, P, cuda, 0.05, 8, 25, noise=noise)
+    res = fused["cluster"]
+
+    Ec = E.to(cuda).requires_grad_(True)
+    X = ops.NormalizeTwice.apply(Ec)
+    C = ops.SeedCentres.apply(X, res.bw, res.idx, res.K, res.iterations)
+    W = ops.Membership.apply(C, X, res.bw, res.K)
+    s, V, c, valid = ops.EllipsoidFit.apply(P.to(cuda), W, res.K, noise)
+    loss_b = ops.SdfLoss.apply(P.to(cuda), s, V, c, valid, res.K)
+    loss, has = pipeline.masked_mean(loss_b, valid)
+    loss.backward()
+    assert torch.equal(fused["loss_b"], loss_b) and torch.equal(fused["has"], has)
+    assert rel_err(fused["loss"], loss) < 1e-6
+    assert float(fused["n_valid"]) == float(has.sum())
+    assert rel_err(fused["loss_sum"], (loss_b * has).sum()) < 1e-6
+    scale = float(Ec.grad.abs().max())
+    assert float((fused["grad_E"] - Ec.grad).abs().max()) <= 2e-6 * scale
+
+    # gradient through loss_sum / n (the multi-GPU form) and through an external use of the centres
+    Ec2 = E.to(cuda).requires_grad_(True)
+    out = pipeline.fit_loss(Ec2, P.to(cuda), quantile=0.05, iterations=8, max_num_clusters=25, noise=noise)
+    (out["loss_sum"] / out["n_valid"] + 0.5 * out["C"].sum()).backward()
+    Ec3 = E.to(cuda).requires_grad_(True)
+    X3 = ops.NormalizeTwice.apply(Ec3)
+    C3 = ops.SeedCentres.apply(X3, res.bw, res.idx, res.K, res.iterations)
+    C3.mul(0.5).sum().backward()
+    assert float((Ec2.grad - (Ec.grad + Ec3.grad)).abs().max()) <= 1e-5 * float((Ec.grad + Ec3.grad).abs().max())
+
+
+def test_masked_mean_kernels(cuda):
+    from prifit_b200 import ops
+
+    loss_b = torch.tensor([0.5, 2.0, 7.0, 1.25], device=cuda)
+    valid = torch.zeros(4, 32, dtype=torch.uint8, device=cuda)
+    valid[0, 3] = 1; valid[1, 0] = 1; valid[3, 31] = 1
+    has, stats = ops.masked_mean_fwd(loss_b, valid)
+    assert has.tolist() == [1.0, 1.0, 0.0, 1.0]
+    assert stats.tolist() == [3.75, 3.0, 1.25]
+    g = ops.masked_mean_bwd(torch.tensor([2.0], device=cuda), torch.tensor([3.0], device=cuda), has, stats)
+    assert g.tolist() == [3.0, 3.0, 0.0, 3.0]
+    g = ops.masked_mean_bwd(None, torch.tensor([3.0], device=cuda), has, stats)
+    assert g.tolist() == [1.0, 1.0, 0.0, 1.0]
+    has, stats = ops.masked_mean_fwd(loss_b, torch.zeros_like(valid))      # no shape kept an ellipsoid
+    assert stats.tolist() == [0.0, 0.0, 0.0]
