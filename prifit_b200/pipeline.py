@@ -180,6 +180,37 @@ def draw_noise(K_host, kcap, device):
 _noise_pinned = {}
 
 
+def stage_noise(B, kcap, device):
+    """Stages the host generator's next B*kcap draws of torch.rand(3, 3) on the device WITHOUT knowing how many
+    clusters each shape has: returns (generator state before the draw, flat[B*kcap,3,3] on the device).
+    torch.rand(n, 3, 3) is prefix-stable on the CPU (the first m matrices equal m successive rand(3, 3) calls), so
+    cluster (b, k) later picks draw number prefix_sum(K)[b] + k on the device (scatter_noise) and the caller
+    rewinds the generator to `state` and consumes exactly sum(K) matrices once the counts are known."""
+    state = torch.get_rng_state()
+    key = ("flat", device.index, B, kcap)
+    ring = _noise_pinned.get(key)
+    if ring is None:                                    # two pinned staging buffers, each guarded by the event of its
+        ring = _noise_pinned[key] = {"next": 0, "slots": [[torch.empty(B * kcap, 3, 3).pin_memory(), None] for _ in range(2)]}
+    slot = ring["slots"][ring["next"]]                  # last copy: the host may run a step ahead of the device
+    ring["next"] ^= 1
+    if slot[1] is not None:
+        slot[1].synchronize()
+    torch.rand(B * kcap, 3, 3, out=slot[0])
+    flat = slot[0].to(device, non_blocking=True)
+    slot[1] = torch.cuda.Event()
+    slot[1].record()
+    return state, flat
+
+
+def scatter_noise(spec, K):
+    flat = spec[1]
+    B = K.numel()
+    kcap = flat.shape[0] // B
+    noise = torch.empty(B, kcap, 3, 3, dtype=torch.float32, device=flat.device)
+    _lib.call("prifit_noise_scatter", ops._ptr(flat), ops._ptr(K), B, kcap, ops._ptr(noise), ops._stream())
+    return noise
+
+
 def masked_mean(loss_b, valid):
     """src/utils.py:418,425: mean over the shapes that have at least one fitted ellipsoid."""
     has = (valid.sum(1) > 0).to(loss_b.dtype)
@@ -197,11 +228,23 @@ def fit_loss(E, P, quantile=0.05, iterations=10, max_num_clusters=25, noise=None
     res, pending = cluster_batch_begin(X.detach(), X.shape[1] if num_samples is None else num_samples, quantile,
                                        iterations, max_num_clusters, engine)
     W, C = soft_memberships(X, res)
-    if cluster_batch_end(res, pending):
-        W, C = soft_memberships(X, res)
+    Qp = P if Q is None else Q
+    spec = None
     if noise is None:
-        noise = draw_noise(res.K_host, res.kcap, X.device)
+        spec = stage_noise(X.shape[0], res.kcap, X.device)
+        noise = scatter_noise(spec, res.K)
     # fit -> SDF loss -> batch mean as one autograd node (three launches back to back)
-    loss_sum, loss, loss_b, s, V, c, valid, has, n_valid = ops.FitSdfMean.apply(P, P if Q is None else Q, W, res.K, noise)
+    outs = ops.FitSdfMean.apply(P, Qp, W, res.K, noise)
+    redone = cluster_batch_end(res, pending)            # the step's one host synchronisation (2 B int32)
+    if spec is not None:
+        torch.set_rng_state(spec[0])                    # leave the host generator where the reference leaves it:
+        if not redone:                                  # exactly one rand(3, 3) per attempted cluster consumed
+            torch.rand(int(sum(res.K_host)), 3, 3)
+    if redone:                                          # rare: a shape exceeded the cap and was re-clustered
+        W, C = soft_memberships(X, res)
+        if spec is not None:
+            noise = draw_noise(res.K_host, res.kcap, X.device)
+        outs = ops.FitSdfMean.apply(P, Qp, W, res.K, noise)
+    loss_sum, loss, loss_b, s, V, c, valid, has, n_valid = outs
     return {"loss": loss, "loss_sum": loss_sum, "n_valid": n_valid, "loss_b": loss_b, "has": has, "s": s, "V": V, "c": c,
             "valid": valid, "cluster": res, "W": W, "C": C, "X": X, "noise": noise}

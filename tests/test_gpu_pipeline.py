@@ -301,3 +301,35 @@ def test_masked_mean_kernels(cuda):
     assert g.tolist() == [1.0, 1.0, 0.0, 1.0]
     has, stats = ops.masked_mean_fwd(loss_b, torch.zeros_like(valid))      # no shape kept an ellipsoid
     assert stats.tolist() == [0.0, 0.0, 0.0]
+
+
+def test_noise_staged_before_counts_equals_reference_stream(cuda):
+    """The speculative staging (draws uploaded before the host knows K, picked by prefix sum on the device) gives
+    every attempted cluster the matrix the reference's sequential torch.rand(3, 3) calls would, and leaves the
+    host generator in the same state."""
+    from prifit_b200 import pipeline
+
+    K_host = [3, 0, 7, 32, 1]
+    K = torch.tensor(K_host, dtype=torch.int32, device=cuda)
+    torch.manual_seed(21)
+    expect = pipeline.draw_noise(K_host, 32, cuda)
+    nxt = torch.rand(4)
+    for _ in range(3):                                       # also cycles the two staging buffers
+        torch.manual_seed(21)
+        spec = pipeline.stage_noise(len(K_host), 32, cuda)
+        got = pipeline.scatter_noise(spec, K)
+        torch.set_rng_state(spec[0])
+        torch.rand(sum(K_host), 3, 3)
+        assert torch.equal(got, expect)
+        assert torch.equal(torch.rand(4), nxt)
+
+    # and through fit_loss: the noise it used is the sequential stream matched to the final cluster counts
+    from prifit_b200 import synthetic
+    E, P, _ = synthetic.planted_shapes(3, n_points=512, n_clusters=4, seed=5)
+    torch.manual_seed(99)
+    out = pipeline.fit_loss(E.to(cuda), P.to(cuda), quantile=0.05, iterations=6, max_num_clusters=25)
+    after = torch.rand(3)
+    torch.manual_seed(99)
+    expect = pipeline.draw_noise(out["cluster"].K_host, out["cluster"].kcap, cuda)
+    assert torch.equal(out["noise"], expect)
+    assert torch.equal(torch.rand(3), after)

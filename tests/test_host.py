@@ -168,3 +168,21 @@ def test_global_mean_world_size_2_gloo(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out.decode()
+
+
+def test_host_rand_stream_is_prefix_stable():
+    """pipeline.stage_noise relies on it: the first m matrices of one batched torch.rand(n, 3, 3) are the m
+    successive torch.rand(3, 3) calls of src/ellipsoid_fitting.py:38, whatever n is, and rewinding the generator
+    then drawing m matrices leaves it where those m calls would."""
+    for n, m in ((768, 40), (64 * 64, 1000), (24 * 32, 24 * 32), (16, 1)):
+        torch.manual_seed(11)
+        state = torch.get_rng_state()
+        big = torch.rand(n, 3, 3)
+        torch.set_rng_state(state)
+        torch.rand(m, 3, 3)
+        after_batched = torch.rand(5)
+        torch.manual_seed(11)
+        seq = torch.stack([torch.rand(3, 3) for _ in range(m)])
+        after_seq = torch.rand(5)
+        assert torch.equal(big[:m], seq)
+        assert torch.equal(after_batched, after_seq)
