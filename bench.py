@@ -123,7 +123,7 @@ def dist_setup(n_gpus):
 
 # ------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
-    from prifit_b200 import _lib, dist as pdist, ops, pipeline, synthetic
+    from prifit_b200 import _lib, dist as pdist, graph_step, ops, pipeline, synthetic
     import prifit_b200.convex_loss as cl
     import torch.distributed as dist
 
@@ -152,10 +152,15 @@ def run_ours(args):
     ms_events = []
     last = {}
 
-    def step_resident(i, timed):
+    use_graph = not args.no_graph
+    if not use_graph:
+        os.environ["PRIFIT_GRAPH"] = "0"                    # the public convex_loss() of the end-to-end arm follows it
+
+    def step_resident(i, timed, graph=None):
         E = dev_E[i % N_SETS].detach().requires_grad_(True)
-        ops.TIMING = ms_events if timed else None
-        out = pipeline.fit_loss(E, dev_P[i % N_SETS], quantile=q, iterations=T, max_num_clusters=kmax)
+        graph = use_graph if graph is None else graph
+        ops.TIMING = ms_events if (timed and not graph) else None
+        out = pipeline.fit_loss(E, dev_P[i % N_SETS], quantile=q, iterations=T, max_num_clusters=kmax, graph=graph)
         ops.TIMING = None
         L, Lb = pdist.global_loss(out)
         Lb.backward()
@@ -242,6 +247,15 @@ def run_ours(args):
 
     ms_total, _ = timed_region(resident, args.steps, args.warmup)
     launches_total = _lib.launch_count()
+    # The dominant kernel is timed with CUDA events around its launch.  Inside a graph replay (parallel branches)
+    # a single kernel's duration is not observable, so when the timed region ran as graphs the kernel is timed in a
+    # second region of the same steps on the eager path (same kernel, same inputs, one stream).
+    eager_ms = None
+    if use_graph:
+        def eager(i, timed):
+            L, out = step_resident(i, timed, graph=False)
+        eager_total, _ = timed_region(eager, min(args.steps, 10), 3)
+        eager_ms = eager_total / min(args.steps, 10)
     n_ms_launch = len(ms_events)
     ms_kernel = sum(a.elapsed_time(b) for a, b in ms_events) / max(n_ms_launch, 1)
     e2e_last = args.warmup + args.steps - 1
@@ -271,16 +285,21 @@ def run_ours(args):
                    "shapes_per_gpu": B, "global_shapes": world * B, "clusters_found_mean": K_mean,
                    "guard_passes_mean": passes, "loss": float(last["L"]),
                    "l2": "rotating %d input sets (%.0f MB of embeddings) > 126 MB L2" % (N_SETS, N_SETS * B * N * D * 4 / 1e6),
-                   "parallelism": "shapes sharded %d/GPU, one 8-byte NCCL all-reduce per step" % B},
+                   "parallelism": "shapes sharded %d/GPU, one 8-byte NCCL all-reduce per step" % B,
+                   "execution": ("3 CUDA graphs per step, %d parallel branches of shapes" % graph_step.default_branches()) if use_graph
+                                else "eager launches on one stream",
+                   "eager_ms_per_step": None if eager_ms is None else round(eager_ms, 4)},
         "e2e": {"value": round(e2e_sps, 2), "unit": "shapes/s", "ms_per_step": round(e2e_ms / args.steps, 4),
                 "h2d_bytes_per_step": int(host_Xcf[0].numel() * 4 + host_Pcf[0].numel() * 4), "d2h_bytes_per_step": 4,
                 "api": "prifit_b200.convex_loss.convex_loss(points[B,3,N], chamfer[B,3,N], X[B,128,N]) + backward"},
-        "gpu_launches": int(round(launches_total / (args.steps + args.warmup) * args.steps)),
+        "gpu_launches": int(round(launches_total / (args.steps + args.warmup) * args.steps)),   # kernels + memset nodes, graph nodes included
         "gpu_launches_per_step": round(launches_total / (args.steps + args.warmup), 1),
         "roofline": {"bound": "tensor", "kernel": "meanshift_fwd (%s)" % args.engine, "achieved": round(achieved, 2),
                      "peak": round(tc_peak, 1), "unit": "TFLOP/s", "frac": round(achieved / tc_peak, 4),
                      "traffic": ncu_traffic(args.workload, "meanshift_tc_kernel") if engine == ops.MS_TF32_TCGEN05 else None,
                      "kernel_ms": round(ms_kernel, 4), "launches_timed": n_ms_launch,
+                     "kernel_timed_in": "eager steps after the timed region (graph replays run it in parallel branches)" if use_graph
+                                        else "the timed region",
                      "flops_per_launch": flops_launch,
                      "peak_source": "%s dense bf16 GEMM, sustained (%.0f TF/s; burst %.0f)" % (pk["source"], pk["bf16_tflops_sustained"], pk["bf16_tflops"]),
                      "whole_step_tflops": round(shapes_per_s / world * algorithmic_flops_per_shape(N, T, K_mean, passes) / 1e12, 2)},
@@ -359,6 +378,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "fp32"])
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

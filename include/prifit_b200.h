@@ -128,8 +128,11 @@ int prifit_fit_bwd(const float* P, const float* W, const int32_t* K, const float
 
 /* noise_out[B,Kcap,3,3] from the flat host stream of U[0,1) draws: cluster (b, k) takes draw number
  *   (sum_{b' < b} K[b']) + k  (src/ellipsoid_fitting.py:38: one torch.rand(3,3) per attempted cluster, shapes outer,
- *   clusters inner); entries k >= K[b] are zero.  flat[B*Kcap,3,3]. */
-int prifit_noise_scatter(const float* flat, const int32_t* K, int B, int Kcap, float* noise_out, void* stream);
+ *   clusters inner); entries k >= K[b] are zero.  flat[B*Kcap,3,3].
+ *   direct: optional device flag; when *direct != 0, flat is taken as already laid out [B,Kcap,3,3] (caller-supplied
+ *   noise) and only the k >= K[b] entries are zeroed -- lets one captured launch sequence serve both cases. */
+int prifit_noise_scatter(const float* flat, const int32_t* K, int B, int Kcap, const int32_t* direct,
+                         float* noise_out, void* stream);
 
 /* k8 -- SDF half of the fitting loss.  convex_loss.py:313-343 + src/utils.py:407-411.
  *   Q[B,M,3]; loss_out[B] = 0.5 * mean_j (min_k |sdf_kj|)^2 over valid ellipsoids (0 if none);

@@ -38,7 +38,7 @@ SIGNATURES = {
     "prifit_sdf_workspace_bytes": (_sz, [_i, _i]),
     "prifit_sdf_loss_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "prifit_sdf_loss_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
-    "prifit_noise_scatter": (_i, [_p, _p, _i, _i, _p, _p]),
+    "prifit_noise_scatter": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "prifit_masked_mean_fwd": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "prifit_masked_mean_bwd": (_i, [_p, _p, _p, _p, _i, _p, _p]),
     "prifit_debug_tc_probe": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),

@@ -25,9 +25,11 @@ def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, 
     per-shape lists of (s, V, center); `labels` a list of int64 [N] tensors."""
     if include_intersect_loss or include_pruning or include_entropy_loss or if_cuboid:
         raise NotImplementedError("intersection / pruning / entropy / cuboid terms are outside the accelerated path")
-    E = X.permute(0, 2, 1).contiguous()                       # reference :37
-    P = points.permute(0, 2, 1).contiguous()                  # reference :38
-    Q = None if evaluation else chamfer_points.permute(0, 2, 1).contiguous()   # reference :84
+    # channel-last views (reference :37,38,84); the pipeline copies them into its own row-major buffers, so the
+    # transposition costs no separate pass
+    E = X.permute(0, 2, 1)
+    P = points.permute(0, 2, 1)
+    Q = None if evaluation or chamfer_points is points else chamfer_points.permute(0, 2, 1)
     out = pipeline.fit_loss(E, P, quantile=quantile, iterations=iterations, max_num_clusters=max_num_clusters,
                             Q=Q, engine=meanshift.engine)
     res = out["cluster"]

@@ -35,6 +35,9 @@ extern "C" int prifit_device_ok(void) {
 // X = normalize(normalize(E)), F.normalize semantics: v / max(||v||, 1e-12).  One warp per row.
 // reference convex_loss.py:41,57
 // ---------------------------------------------------------------------------------------------
+// NVF > 0: the row length in float4 is the compile-time constant NVF (32 for d = 128: one float4 per lane, the
+// row is read once and stays in registers through every phase); NVF = 0: run-time d.
+template <int NVF>
 __global__ void __launch_bounds__(256) normalize_fwd_kernel(const float* __restrict__ E, int64_t rows, int d,
                                                             float* __restrict__ X) {
     const int lane = threadIdx.x & 31;
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(256) normalize_fwd_kernel(const float* __restr
     if (row >= rows) return;
     const float4* e4 = reinterpret_cast<const float4*>(E + row * d);
     float4* x4 = reinterpret_cast<float4*>(X + row * d);
-    const int nv = d >> 2;
+    const int nv = NVF > 0 ? NVF : d >> 2;
     float ss = 0.f;
     for (int c = lane; c < nv; c += 32) {
         float4 v = e4[c];
@@ -67,6 +70,7 @@ __global__ void __launch_bounds__(256) normalize_fwd_kernel(const float* __restr
 
 // backward of y = v / max(||v||, eps) applied twice: g1 = (g - x (x.g)) / n1 ; gE = (g1 - x1 (x1.g1)) / n0
 // (when the clamp is active, i.e. ||v|| < eps, the node is a plain division by eps.)
+template <int NVF>
 __global__ void __launch_bounds__(256) normalize_bwd_kernel(const float* __restrict__ E, const float* __restrict__ gX,
                                                             int64_t rows, int d, float* __restrict__ gE) {
     const int lane = threadIdx.x & 31;
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(256) normalize_bwd_kernel(const float* __restr
     const float4* e4 = reinterpret_cast<const float4*>(E + row * d);
     const float4* g4 = reinterpret_cast<const float4*>(gX + row * d);
     float4* o4 = reinterpret_cast<float4*>(gE + row * d);
-    const int nv = d >> 2;
+    const int nv = NVF > 0 ? NVF : d >> 2;
     float ss = 0.f;
     for (int c = lane; c < nv; c += 32) {
         float4 v = e4[c];
@@ -130,7 +134,9 @@ extern "C" int prifit_normalize_fwd(const float* E, int64_t rows, int d, float* 
     PF_CHECK_ARG(E && X, PRIFIT_E_BADARG, "null pointer");
     PF_CHECK_ARG(rows > 0 && d > 0 && d % 4 == 0, PRIFIT_E_SHAPE, "rows > 0 and d % 4 == 0 required");
     const int wpb = 8;
-    normalize_fwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, pf_stream(stream)>>>(E, rows, d, X);
+    const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+    if (d == 128) normalize_fwd_kernel<32><<<grid, wpb * 32, 0, pf_stream(stream)>>>(E, rows, d, X);
+    else normalize_fwd_kernel<0><<<grid, wpb * 32, 0, pf_stream(stream)>>>(E, rows, d, X);
     PF_LAUNCH_CHECK();
     return 0;
 }
@@ -139,7 +145,9 @@ extern "C" int prifit_normalize_bwd(const float* E, const float* gX, int64_t row
     PF_CHECK_ARG(E && gX && gE, PRIFIT_E_BADARG, "null pointer");
     PF_CHECK_ARG(rows > 0 && d > 0 && d % 4 == 0, PRIFIT_E_SHAPE, "rows > 0 and d % 4 == 0 required");
     const int wpb = 8;
-    normalize_bwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, pf_stream(stream)>>>(E, gX, rows, d, gE);
+    const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+    if (d == 128) normalize_bwd_kernel<32><<<grid, wpb * 32, 0, pf_stream(stream)>>>(E, gX, rows, d, gE);
+    else normalize_bwd_kernel<0><<<grid, wpb * 32, 0, pf_stream(stream)>>>(E, gX, rows, d, gE);
     PF_LAUNCH_CHECK();
     return 0;
 }

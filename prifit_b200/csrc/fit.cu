@@ -359,19 +359,24 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_bwd_kernel(
 // attempted cluster, shapes outer / clusters inner (src/ellipsoid_fitting.py:38), so cluster (b, k) owns draw number
 // prefix(b) + k of the host stream.  Done on the device so that the host need not know K to stage the draws.
 __global__ void noise_scatter_kernel(const float* __restrict__ flat, const int32_t* __restrict__ K, int Kcap,
-                                     float* __restrict__ noise) {
+                                     const int32_t* __restrict__ direct, float* __restrict__ noise) {
     const int b = blockIdx.x;
     int off = 0;
-    for (int q = 0; q < b; ++q) off += min(max(K[q], 0), Kcap);
+    if (direct && *direct) {
+        off = b * Kcap;                                  // flat is already laid out [B, Kcap, 3, 3]
+    } else {
+        for (int q = 0; q < b; ++q) off += min(max(K[q], 0), Kcap);
+    }
     const int Kb = min(max(K[b], 0), Kcap);
     for (int e = threadIdx.x; e < Kcap * 9; e += blockDim.x)
         noise[(size_t)b * Kcap * 9 + e] = e < Kb * 9 ? flat[(size_t)off * 9 + e] : 0.f;
 }
 
-extern "C" int prifit_noise_scatter(const float* flat, const int32_t* K, int B, int Kcap, float* noise_out, void* stream) {
+extern "C" int prifit_noise_scatter(const float* flat, const int32_t* K, int B, int Kcap, const int32_t* direct,
+                                    float* noise_out, void* stream) {
     PF_CHECK_ARG(flat && K && noise_out, PRIFIT_E_BADARG, "null pointer");
     PF_CHECK_ARG(B > 0 && Kcap > 0, PRIFIT_E_BADARG, "B, Kcap > 0 required");
-    noise_scatter_kernel<<<B, 128, 0, pf_stream(stream)>>>(flat, K, Kcap, noise_out);
+    noise_scatter_kernel<<<B, 128, 0, pf_stream(stream)>>>(flat, K, Kcap, direct, noise_out);
     PF_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,356 @@
+"""The whole hot path of one batch as three CUDA graphs over static buffers.
+
+    graph 1  (per branch)  normalise x2 -> bandwidth -> T mean-shift iterations -> NMS     | counts -> pinned host
+    graph 2  noise scatter | (per branch) K-seed trajectories -> membership -> fit -> SDF  | batch mean
+    graph 3  batch-mean backward | (per branch) SDF -> fit -> membership -> K-seed trajectories -> normalise backward
+
+Why.  The eager pipeline (pipeline.fit_loss with graph=False) enqueues ~40 launches per step from Python and runs
+them back to back on one stream, so (1) every kernel's partial last wave leaves SMs idle -- 24 shapes x 16 row
+tiles = 384 CTAs are 2.59 waves of 148 SMs -- and (2) the latency-bound stages (K-seed trajectories: 96 CTAs,
+membership backward: 96 CTAs, the microsecond-scale launches) hold the whole GPU.  Here the batch is cut into
+`branches` contiguous groups of shapes (shapes are independent units) that are captured as parallel
+branches of each graph: the groups drift apart, one group's latency-bound kernels and tails run beside the other
+group's tensor-core kernels, and a replay costs the host three graph launches.
+
+Every kernel is batch-invariant (a shape's result does not depend on the batch it is launched in), so the result
+is bit-identical to the eager path.  The host still makes the guard decision of src/ellipsoid_utils.py:19-26: the
+cluster counts land in pinned memory at the end of graph 1 and are read while graph 2 runs; if a shape exceeds
+max_num_clusters the step is redone on the eager path (quantile doubling, sub-batch re-clustering).
+
+Buffers are static: the tensors returned for a step stay valid until the next step on the same GraphStep; the
+small ones (losses, cluster lists, labels, ellipsoid parameters) are snapshotted with one copy and stay valid.
+"""
+import os
+
+import torch
+
+from . import _lib, ops
+from .ops import _ptr
+
+
+def _stream():
+    return ops._stream()
+
+
+class _Arena:
+    """Small per-step outputs in one allocation, so that one clone snapshots all of them."""
+
+    def __init__(self, device):
+        self.device = device
+        self.items = []          # (name, offset, nbytes, dtype, shape)
+        self.size = 0
+        self.buf = None
+
+    def add(self, name, shape, dtype):
+        n = 1
+        for v in shape:
+            n *= v
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        self.items.append((name, self.size, nbytes, dtype, tuple(shape)))
+        self.size += (nbytes + 255) // 256 * 256
+
+    def finish(self):
+        self.buf = torch.zeros(self.size, dtype=torch.uint8, device=self.device)
+        return self.views(self.buf)
+
+    def views(self, buf):
+        return {name: buf[off:off + nb].view(dtype).view(shape) for name, off, nb, dtype, shape in self.items}
+
+
+class GraphStep:
+    def __init__(self, B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches):
+        self.key = (B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches)
+        self.B, self.N, self.d, self.M, self.T = B, N, d, M, int(iterations)
+        self.quantile, self.kmax = float(quantile), int(max_num_clusters)
+        self.kcap = ops.kcap_for(max_num_clusters)
+        self.engine, self.rows_engine = engine, rows_engine
+        self.device = device
+        self.serial = 0
+        kth = int(self.quantile * N)                                  # src/mean_shift.py:155
+        if kth < 1:
+            raise _lib.PrifitError("int(quantile * num_samples) must be >= 1 (the reference's topk(k=0) fails too)")
+        nbr = max(1, min(int(branches), B))
+        base, rem = divmod(B, nbr)
+        self.ranges, lo = [], 0
+        for i in range(nbr):
+            hi = lo + base + (1 if i < rem else 0)
+            self.ranges.append((lo, hi))
+            lo = hi
+        self.streams = [torch.cuda.Stream(device=device) for _ in self.ranges]
+        lib = _lib.load()
+        kcap, T = self.kcap, self.T
+        f32, i32, u8 = torch.float32, torch.int32, torch.uint8
+
+        def buf(*shape, dtype=f32):
+            return torch.empty(*shape, dtype=dtype, device=device)
+
+        # ---- static inputs
+        self.E, self.P = buf(B, N, d), buf(B, N, 3)
+        self.Q = self.P if M is None else buf(B, M, 3)
+        self.Mq = N if M is None else M
+        self.flat = buf(B * kcap, 3, 3)
+        self.direct = torch.zeros(1, dtype=i32, device=device)
+        self.direct_host = 0
+        self.kth = torch.full((B,), min(kth, N), dtype=i32, device=device)
+        self.g_sum, self.g_mean = torch.zeros(1, device=device), torch.zeros(1, device=device)
+        self.g_zero = [True, True]
+        # ---- small outputs (snapshotted per step)
+        ar = self.arena = _Arena(device)
+        for name, shape, dt in (("stats", (3,), f32), ("has", (B,), f32), ("loss_b", (B,), f32), ("bw", (B,), f32),
+                                ("K", (B,), i32), ("nlab", (B,), i32), ("idx", (B, kcap), i32), ("s", (B, kcap, 3), f32),
+                                ("V", (B, kcap, 3, 3), f32), ("c", (B, kcap, 3), f32), ("valid", (B, kcap), u8),
+                                ("labels", (B, N), i32)):
+            ar.add(name, shape, dt)
+        self.small = ar.finish()
+        # ---- large static intermediates / outputs
+        self.X, self.newX = buf(B, N, d), buf(B, N, d)
+        self.traj, self.stat = buf(B, T + 1, kcap, d), buf(B, max(T, 1), kcap, 2)
+        self.C, self.W, self.smax = buf(B, kcap, d), buf(B, kcap, N), buf(B)
+        self.noise, self.fctx = buf(B, kcap, 3, 3), buf(B, kcap, _lib.FIT_CTX)
+        self.argmin, self.sdf = buf(B, self.Mq, dtype=i32), buf(B, self.Mq)
+        self.gloss, self.gs, self.gV, self.gc = buf(B), buf(B, kcap, 3), buf(B, kcap, 3, 3), buf(B, kcap, 3)
+        self.gW, self.gC, self.gX, self.gE = buf(B, kcap, N), buf(B, kcap, d), buf(B, N, d), buf(B, N, d)
+        self.counts = torch.zeros(2, B, dtype=i32).pin_memory()
+        # ---- per-branch workspaces
+        self.ws = []
+        for lo, hi in self.ranges:
+            Bb = hi - lo
+            sizes = {
+                "bw": lib.prifit_bandwidth_workspace_bytes(Bb, N, d, N),
+                "ms": lib.prifit_meanshift_workspace_bytes(Bb, N, d, engine),
+                "nms": lib.prifit_nms_workspace_bytes(Bb, N, d),
+                "rows": lib.prifit_meanshift_rows_workspace_bytes(Bb, N, d, rows_engine),
+                "memb": max(16, lib.prifit_membership_workspace_bytes(Bb, N, kcap)),
+                "sdf": max(16, lib.prifit_sdf_workspace_bytes(Bb, self.Mq)),
+            }
+            self.ws.append({k: (torch.empty(v, dtype=u8, device=device), v) for k, v in sizes.items()})
+        # ---- pinned staging of the host noise stream (two slots: the host may run ahead of the device)
+        self.flat_pinned = [[torch.empty(B * kcap, 3, 3).pin_memory(), None] for _ in range(2)]
+        self.flat_next = 0
+        self.launches = [0, 0, 0]
+        self._capture()
+
+    # ------------------------------------------------------------------------------------ launch sequences
+    def _fork_join(self, fn):
+        main = torch.cuda.current_stream()
+        for i, (lo, hi) in enumerate(self.ranges):
+            st = self.streams[i]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                fn(i, lo, hi)
+        for st in self.streams:
+            main.wait_stream(st)
+
+    def _seq_cluster(self):
+        N, d, T, kcap, sm = self.N, self.d, self.T, self.kcap, self.small
+
+        def branch(i, lo, hi):
+            Bb, ws, st = hi - lo, self.ws[i], _stream()
+            X, bw, newX = self.X[lo:hi], sm["bw"][lo:hi], self.newX[lo:hi]
+            _lib.call("prifit_normalize_fwd", _ptr(self.E[lo:hi]), Bb * N, d, _ptr(X), st)
+            _lib.call("prifit_bandwidth_fwd", _ptr(X), Bb, N, d, None, N, _ptr(self.kth[lo:hi]), _ptr(bw),
+                      _ptr(ws["bw"][0]), ws["bw"][1], st)
+            _lib.call("prifit_meanshift_fwd", _ptr(X), _ptr(bw), Bb, N, d, T, _ptr(newX), self.engine,
+                      _ptr(ws["ms"][0]), ws["ms"][1], st)
+            _lib.call("prifit_nms_fwd", _ptr(newX), _ptr(bw), Bb, N, d, kcap, _ptr(sm["idx"][lo:hi]), _ptr(sm["K"][lo:hi]),
+                      _ptr(sm["labels"][lo:hi]), _ptr(sm["nlab"][lo:hi]), _ptr(ws["nms"][0]), ws["nms"][1], st)
+
+        self._fork_join(branch)
+        self.counts[0].copy_(sm["K"], non_blocking=True)
+        self.counts[1].copy_(sm["nlab"], non_blocking=True)
+
+    def _seq_rest(self):
+        B, N, d, T, kcap, M, sm = self.B, self.N, self.d, self.T, self.kcap, self.Mq, self.small
+        _lib.call("prifit_noise_scatter", _ptr(self.flat), _ptr(sm["K"]), B, kcap, _ptr(self.direct), _ptr(self.noise), _stream())
+
+        def branch(i, lo, hi):
+            Bb, ws, st = hi - lo, self.ws[i], _stream()
+            X, bw, idx, K = self.X[lo:hi], sm["bw"][lo:hi], sm["idx"][lo:hi], sm["K"][lo:hi]
+            C, W = self.C[lo:hi], self.W[lo:hi]
+            s, V, c, valid = sm["s"][lo:hi], sm["V"][lo:hi], sm["c"][lo:hi], sm["valid"][lo:hi]
+            _lib.call("prifit_meanshift_rows_fwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), Bb, N, d, T, kcap,
+                      _ptr(self.traj[lo:hi]), _ptr(self.stat[lo:hi]), _ptr(C), self.rows_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
+            _lib.call("prifit_membership_fwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), Bb, N, d, kcap, _ptr(W), _ptr(self.smax[lo:hi]),
+                      _ptr(ws["memb"][0]), ws["memb"][1], st)
+            _lib.call("prifit_fit_fwd", _ptr(self.P[lo:hi]), _ptr(W), _ptr(K), _ptr(self.noise[lo:hi]), Bb, N, kcap,
+                      _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(self.fctx[lo:hi]), st)
+            _lib.call("prifit_sdf_loss_fwd", _ptr(self.Q[lo:hi]), _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(K), Bb, M, kcap,
+                      _ptr(sm["loss_b"][lo:hi]), _ptr(self.argmin[lo:hi]), _ptr(self.sdf[lo:hi]), _ptr(ws["sdf"][0]), ws["sdf"][1], st)
+
+        self._fork_join(branch)
+        _lib.call("prifit_masked_mean_fwd", _ptr(sm["loss_b"]), _ptr(sm["valid"]), B, kcap, _ptr(sm["has"]), _ptr(sm["stats"]), _stream())
+
+    def _seq_backward(self):
+        B, N, d, T, kcap, M, sm = self.B, self.N, self.d, self.T, self.kcap, self.Mq, self.small
+        _lib.call("prifit_masked_mean_bwd", _ptr(self.g_sum), _ptr(self.g_mean), _ptr(sm["has"]), _ptr(sm["stats"]), B,
+                  _ptr(self.gloss), _stream())
+
+        def branch(i, lo, hi):
+            Bb, ws, st = hi - lo, self.ws[i], _stream()
+            X, bw, idx, K = self.X[lo:hi], sm["bw"][lo:hi], sm["idx"][lo:hi], sm["K"][lo:hi]
+            C, W, gX = self.C[lo:hi], self.W[lo:hi], self.gX[lo:hi]
+            s, V, c, valid = sm["s"][lo:hi], sm["V"][lo:hi], sm["c"][lo:hi], sm["valid"][lo:hi]
+            gs, gV, gc, gW, gC = self.gs[lo:hi], self.gV[lo:hi], self.gc[lo:hi], self.gW[lo:hi], self.gC[lo:hi]
+            _lib.call("prifit_sdf_loss_bwd", _ptr(self.Q[lo:hi]), _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(K),
+                      _ptr(self.argmin[lo:hi]), _ptr(self.gloss[lo:hi]), Bb, M, kcap, _ptr(gs), _ptr(gV), _ptr(gc), None, st)
+            _lib.call("prifit_fit_bwd", _ptr(self.P[lo:hi]), _ptr(W), _ptr(K), _ptr(self.noise[lo:hi]), _ptr(self.fctx[lo:hi]),
+                      _ptr(valid), _ptr(gs), _ptr(gV), _ptr(gc), Bb, N, kcap, _ptr(gW), None, st)
+            gX.zero_()
+            _lib.call("prifit_membership_bwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), _ptr(W), _ptr(self.smax[lo:hi]), _ptr(gW),
+                      Bb, N, d, kcap, _ptr(gC), _ptr(gX), st)
+            _lib.call("prifit_meanshift_rows_bwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), _ptr(self.traj[lo:hi]),
+                      _ptr(self.stat[lo:hi]), _ptr(gC), Bb, N, d, T, kcap, _ptr(gX), self.rows_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
+            _lib.call("prifit_normalize_bwd", _ptr(self.E[lo:hi]), _ptr(gX), Bb * N, d, _ptr(self.gE[lo:hi]), st)
+
+        self._fork_join(branch)
+
+    def _capture(self):
+        seqs = (self._seq_cluster, self._seq_rest, self._seq_backward)
+        # eager warm-up on a side stream (first-call initialisation must not happen inside a capture)
+        self.E.normal_()
+        self.P.uniform_(-1, 1)
+        if self.Q is not self.P:
+            self.Q.uniform_(-1, 1)
+        self.flat.uniform_()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for seq in seqs:
+                seq()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graphs = []
+        for i, seq in enumerate(seqs):
+            g = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(g):
+                seq()
+            self.launches[i] = _lib.launch_count() - before
+            self.graphs.append(g)
+        _lib._launches -= sum(self.launches)          # capture enqueues nothing; replays are counted in run_*
+
+    # ------------------------------------------------------------------------------------------ per step
+    def run_forward(self, E, P, Q, noise):
+        """Returns the step's result dict, or None when the guard asks for a redo (caller: eager path).  The host
+        generator is left exactly where the reference would leave it in the first case and untouched in the second."""
+        self.serial += 1
+        self.E.copy_(E)
+        self.P.copy_(P)
+        if self.Q is not self.P:
+            self.Q.copy_(Q)
+        state = None
+        if noise is None:
+            state = torch.get_rng_state()
+            slot = self.flat_pinned[self.flat_next]
+            self.flat_next ^= 1
+            if slot[1] is not None:
+                slot[1].synchronize()
+            torch.rand(self.B * self.kcap, 3, 3, out=slot[0])
+            self.flat.copy_(slot[0], non_blocking=True)
+            slot[1] = torch.cuda.Event()
+            slot[1].record()
+            want_direct = 0
+        else:
+            self.flat.copy_(noise.reshape(self.B * self.kcap, 3, 3))
+            want_direct = 1
+        if want_direct != self.direct_host:
+            self.direct.fill_(want_direct)
+            self.direct_host = want_direct
+        self.graphs[0].replay()
+        ev = torch.cuda.Event()
+        ev.record()
+        self.graphs[1].replay()
+        _lib._launches += self.launches[0] + self.launches[1]
+        ev.synchronize()                                   # the step's one host synchronisation (2 B int32)
+        K_host, nlab_host = self.counts[0].tolist(), self.counts[1].tolist()
+        if state is not None:
+            torch.set_rng_state(state)
+        if max(nlab_host) > self.kmax:                     # src/ellipsoid_utils.py:23-24 -> redo on the eager path
+            return None
+        if max(K_host) > self.kcap:
+            raise _lib.PrifitError("%d cluster centres exceed the padded capacity %d" % (max(K_host), self.kcap))
+        if state is not None:
+            torch.rand(int(sum(K_host)), 3, 3)             # one rand(3, 3) per attempted cluster, like the reference
+        snap = self.arena.views(self.arena.buf.clone())
+        loss_sum, n_valid, loss = snap["stats"].unbind(0)
+        out = dict(snap)
+        out.update({"loss": loss, "loss_sum": loss_sum, "n_valid": n_valid, "K_host": K_host, "n_labels_host": nlab_host,
+                    "W": self.W, "C": self.C, "X": self.X, "noise": self.noise, "serial": self.serial})
+        return out
+
+    def run_backward(self, serial, g_sum, g_mean):
+        if serial != self.serial:
+            raise _lib.PrifitError("the graph-replayed step's buffers were overwritten by a later forward call before its "
+                                   "backward ran; call backward first, or use graph=False / PRIFIT_GRAPH=0")
+        for i, (g, dst) in enumerate(((g_sum, self.g_sum), (g_mean, self.g_mean))):
+            if g is None:
+                if not self.g_zero[i]:
+                    dst.zero_()
+                    self.g_zero[i] = True
+            else:
+                dst.copy_(g.reshape(1))
+                self.g_zero[i] = False
+        self.graphs[2].replay()
+        _lib._launches += self.launches[2]
+        return self.gE
+
+
+class _Attach(torch.autograd.Function):
+    """Autograd node of a graph-replayed step: (E) -> (loss_sum, loss_mean); backward replays graph 3."""
+
+    @staticmethod
+    def forward(ctx, E, step, serial, loss_sum, loss):
+        ctx.step, ctx.serial = step, serial
+        ctx.set_materialize_grads(False)
+        return loss_sum.view_as(loss_sum), loss.view_as(loss)
+
+    @staticmethod
+    def backward(ctx, g_sum, g_mean):
+        if g_sum is None and g_mean is None:
+            return None, None, None, None, None
+        return ctx.step.run_backward(ctx.serial, g_sum, g_mean), None, None, None, None
+
+
+_steps = {}
+
+
+def default_enabled():
+    return os.environ.get("PRIFIT_GRAPH", "1") != "0"
+
+
+def default_branches():
+    return int(os.environ.get("PRIFIT_GRAPH_BRANCHES", "2"))
+
+
+def get_step(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches):
+    key = (B, N, d, M, float(quantile), int(iterations), int(max_num_clusters), engine, rows_engine, device, branches)
+    st = _steps.get(key)
+    if st is None:
+        if len(_steps) >= 8:                               # static buffers are ~6 MB per shape: keep a few configurations
+            _steps.pop(next(iter(_steps)))
+        st = _steps[key] = GraphStep(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches)
+    return st
+
+
+def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, branches=None):
+    """Graph-replayed pipeline.fit_loss.  Returns None when the step has to be redone on the eager path."""
+    from . import pipeline
+
+    B, N, d = E.shape
+    engine = ops.DEFAULT_ENGINE if engine is None else engine
+    rows_engine = ops._rows_engine(None, d)
+    M = None if Q is None else Q.shape[1]
+    step = get_step(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, E.device,
+                    default_branches() if branches is None else int(branches))
+    res = step.run_forward(E.detach(), P.detach(), None if Q is None else Q.detach(), noise)
+    if res is None:
+        return None
+    cluster = pipeline.ClusterResult(bw=res["bw"], idx=res["idx"], K=res["K"], labels=res["labels"], K_host=res["K_host"],
+                                     n_labels_host=res["n_labels_host"], passes=[1] * B, quantiles=[float(quantile)] * B,
+                                     kcap=step.kcap, iterations=int(iterations))
+    loss_sum, loss = res["loss_sum"], res["loss"]
+    if E.requires_grad and torch.is_grad_enabled():
+        loss_sum, loss = _Attach.apply(E, step, res["serial"], loss_sum, loss)
+    return {"loss": loss, "loss_sum": loss_sum, "n_valid": res["n_valid"], "loss_b": res["loss_b"], "has": res["has"],
+            "s": res["s"], "V": res["V"], "c": res["c"], "valid": res["valid"], "cluster": cluster, "W": res["W"],
+            "C": res["C"], "X": res["X"], "noise": res["noise"], "graph": True}

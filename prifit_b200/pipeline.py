@@ -207,7 +207,7 @@ def scatter_noise(spec, K):
     B = K.numel()
     kcap = flat.shape[0] // B
     noise = torch.empty(B, kcap, 3, 3, dtype=torch.float32, device=flat.device)
-    _lib.call("prifit_noise_scatter", ops._ptr(flat), ops._ptr(K), B, kcap, ops._ptr(noise), ops._stream())
+    _lib.call("prifit_noise_scatter", ops._ptr(flat), ops._ptr(K), B, kcap, None, ops._ptr(noise), ops._stream())
     return noise
 
 
@@ -217,11 +217,34 @@ def masked_mean(loss_b, valid):
     return (loss_b * has).sum() / has.sum().clamp(min=1.0), has
 
 
-def fit_loss(E, P, quantile=0.05, iterations=10, max_num_clusters=25, noise=None, Q=None, engine=None,
-             num_samples=None):
-    """Whole hot path on a batch.  Returns dict(loss, loss_b, has, s, V, c, valid, cluster, W, C, X).
+def _graph_ok(E, P, Q, noise, num_samples, kcap):
+    if not (E.is_cuda and E.dtype == torch.float32 and P.is_cuda and E.dim() == 3):
+        return False
+    if num_samples is not None and num_samples < E.shape[1]:
+        return False                                   # sub-sampled bandwidth replays the host shuffle: eager path
+    if P.requires_grad or (Q is not None and Q.requires_grad):
+        return False                                   # point gradients: eager path
+    if noise is not None and tuple(noise.shape) != (E.shape[0], kcap, 3, 3):
+        return False
+    return True
 
-    `loss` is differentiable w.r.t. E (and P/Q if they require grad)."""
+
+def fit_loss(E, P, quantile=0.05, iterations=10, max_num_clusters=25, noise=None, Q=None, engine=None,
+             num_samples=None, graph=None):
+    """Whole hot path on a batch.  Returns dict(loss, loss_sum, n_valid, loss_b, has, s, V, c, valid, cluster, W, C, X).
+
+    `loss` is differentiable w.r.t. E (and P/Q if they require grad).  graph=None/True replays the step as CUDA
+    graphs over static buffers (graph_step.py; PRIFIT_GRAPH=0 disables): same kernels, same results, but W / C / X /
+    noise are then views of static buffers (valid until the next call) and gradients flow to E only through the
+    loss.  graph=False (or a guard redo, point gradients, a sub-sampled bandwidth) takes the eager autograd path."""
+    from . import graph_step
+
+    if graph is None:
+        graph = graph_step.default_enabled()
+    if graph and _graph_ok(E, P, Q, noise, num_samples, ops.kcap_for(max_num_clusters)):
+        out = graph_step.fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine)
+        if out is not None:
+            return out
     X = ops.NormalizeTwice.apply(E)
     # the differentiable stages that only need the device-side cluster lists are enqueued behind pass 1 before
     # the host learns the counts; in the rare guard-redo case they are recomputed on the final clustering

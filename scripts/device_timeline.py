@@ -19,10 +19,19 @@ def main():
         E, P, _ = synthetic.planted_shapes(B, n_points=N, n_clusters=16, seed=1000 + s * B)
         sets.append((E.to(dev), P.to(dev)))
 
+    cf = "--cf" in sys.argv            # the reference-shaped public API on channel-first tensors (convex_loss)
+    if cf:
+        import prifit_b200.convex_loss as cl
+        sets = [(E.permute(0, 2, 1).contiguous(), P.permute(0, 2, 1).contiguous()) for E, P in sets]
+
     def step(i):
         E, P = sets[i % 4]
         Ei = E.detach().requires_grad_(True)
-        out = pipeline.fit_loss(Ei, P, quantile=0.05, iterations=10, max_num_clusters=25)
+        if cf:
+            total, l, params, labels = cl.convex_loss(P, P, Ei, quantile=0.05, iterations=10, max_num_clusters=25)
+            total.backward()
+            return
+        out = pipeline.fit_loss(Ei, P, quantile=0.05, iterations=10, max_num_clusters=25, graph="--eager" not in sys.argv)
         L, Lb = pdist.global_loss(out)
         Lb.backward()
 
@@ -34,28 +43,44 @@ def main():
         for i in range(n_steps):
             step(i)
         torch.cuda.synchronize()
-    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-    evs.sort(key=lambda e: e.time_range.start)
-    # steps start at normalize_fwd_kernel
-    starts = [i for i, e in enumerate(evs) if "normalize_fwd" in e.name]
+    kin = prof.profiler.kineto_results.events()
+    evs = []
+    for e in kin:
+        if e.device_type() == torch.autograd.DeviceType.CUDA:
+            evs.append((e.start_ns() / 1e3, e.duration_ns() / 1e3, e.name(), e.device_resource_id()))
+    evs.sort()
+    # a step starts at the first normalize_fwd that follows a normalize_bwd
+    starts, seen_bwd = [], True
+    for i, e in enumerate(evs):
+        if "normalize_bwd" in e[2]:
+            seen_bwd = True
+        elif "normalize_fwd" in e[2] and seen_bwd:
+            starts.append(i)
+            seen_bwd = False
     if len(starts) < 4:
-        print("could not find step boundaries (%d kernels traced)" % len(evs))
+        print("could not find step boundaries (%d device activities traced)" % len(evs))
         return
     lo, hi = starts[2], starts[3]
-    t0 = evs[lo].time_range.start
-    prev_end = evs[lo - 1].time_range.end if lo > 0 else t0
-    busy = 0.0
-    print("%9s %8s %8s  %s" % ("start us", "dur us", "gap us", "kernel"))
-    for e in evs[lo:hi]:
-        s, d = e.time_range.start, e.time_range.end - e.time_range.start
-        gap = s - prev_end
-        busy += d
-        print("%9.1f %8.1f %8.1f  %s" % (s - t0, d, gap, e.name[:90]))
-        prev_end = max(prev_end, e.time_range.end)
-    span = evs[hi].time_range.start - t0
-    print("step span %.1f us, busy %.1f us, idle %.1f us, %d device activities" % (span, busy, span - busy, hi - lo))
+    t0 = evs[lo][0]
+    streams = sorted({e[3] for e in evs[lo:hi]})
+    print("%9s %8s %3s  %s" % ("start us", "dur us", "st", "kernel"))
+    # union of busy intervals = time with at least one kernel resident
+    busy, cur_s, cur_e, ksum = 0.0, None, None, 0.0
+    for s_, d_, name, st in evs[lo:hi]:
+        print("%9.1f %8.1f %3d  %s" % (s_ - t0, d_, streams.index(st), name[:90]))
+        ksum += d_
+        if cur_e is None or s_ > cur_e:
+            if cur_e is not None:
+                busy += cur_e - cur_s
+            cur_s, cur_e = s_, s_ + d_
+        else:
+            cur_e = max(cur_e, s_ + d_)
+    busy += cur_e - cur_s
+    span = evs[hi][0] - t0
+    print("step span %.1f us, some kernel resident %.1f us, idle %.1f us, sum of kernel durations %.1f us, %d activities on %d streams"
+          % (span, busy, span - busy, ksum, hi - lo, len(streams)))
     for k in range(1, len(starts) - 1):
-        print("step %d span %.1f us" % (k, evs[starts[k + 1]].time_range.start - evs[starts[k]].time_range.start))
+        print("step %d span %.1f us" % (k, evs[starts[k + 1]][0] - evs[starts[k]][0]))
 
 
 if __name__ == "__main__":

@@ -34,12 +34,12 @@ def _matched_noise(labels_ours, labels_ref, noise_ref, kcap):
     return out, maps
 
 
-def _run(E, P, cuda, q, T, kmax, noise=None, engine=None):
+def _run(E, P, cuda, q, T, kmax, noise=None, engine=None, graph=None):
     from prifit_b200 import pipeline
 
     Ec = E.to(cuda).requires_grad_(True)
     out = pipeline.fit_loss(Ec, P.to(cuda), quantile=q, iterations=T, max_num_clusters=kmax,
-                            noise=None if noise is None else noise.to(cuda), engine=engine)
+                            noise=None if noise is None else noise.to(cuda), engine=engine, graph=graph)
     out["loss"].backward()
     out["grad_E"] = Ec.grad
     return out
@@ -257,7 +257,7 @@ def test_fused_nodes_match_separate_nodes(cuda):
 
     E, P, _ = synthetic.planted_shapes(3, n_points=640, n_clusters=5, seed=77)
     noise = torch.rand(3, 32, 3, 3, generator=torch.Generator().manual_seed(5)).to(cuda)
-    fused = _run(E, P, cuda, 0.05, 8, 25, noise=noise)
+    fused = _run(E, P, cuda, 0.05, 8, 25, noise=noise, graph=False)
     res = fused["cluster"]
 
     Ec = E.to(cuda).requires_grad_(True)
@@ -277,7 +277,7 @@ def test_fused_nodes_match_separate_nodes(cuda):
 
     # gradient through loss_sum / n (the multi-GPU form) and through an external use of the centres
     Ec2 = E.to(cuda).requires_grad_(True)
-    out = pipeline.fit_loss(Ec2, P.to(cuda), quantile=0.05, iterations=8, max_num_clusters=25, noise=noise)
+    out = pipeline.fit_loss(Ec2, P.to(cuda), quantile=0.05, iterations=8, max_num_clusters=25, noise=noise, graph=False)
     (out["loss_sum"] / out["n_valid"] + 0.5 * out["C"].sum()).backward()
     Ec3 = E.to(cuda).requires_grad_(True)
     X3 = ops.NormalizeTwice.apply(Ec3)
@@ -333,3 +333,69 @@ def test_noise_staged_before_counts_equals_reference_stream(cuda):
     expect = pipeline.draw_noise(out["cluster"].K_host, out["cluster"].kcap, cuda)
     assert torch.equal(out["noise"], expect)
     assert torch.equal(torch.rand(3), after)
+
+
+@pytest.mark.parametrize("branches", [1, 2, 3])
+def test_graph_replayed_step_equals_eager_step(cuda, branches, monkeypatch):
+    """graph_step.py replays the same C-ABI calls as CUDA graphs over static buffers, the batch cut into parallel
+    branches: every output and the input gradient must be bit-identical to the eager path (batch invariance)."""
+    from prifit_b200 import graph_step, pipeline, synthetic
+
+    monkeypatch.setenv("PRIFIT_GRAPH_BRANCHES", str(branches))
+    E, P, _ = synthetic.planted_shapes(5, n_points=640, n_clusters=5, seed=31)
+    for explicit_noise in (False, True):
+        noise = torch.rand(5, 32, 3, 3, generator=torch.Generator().manual_seed(9)) if explicit_noise else None
+        torch.manual_seed(4)
+        eager = _run(E, P, cuda, 0.05, 8, 25, noise=noise, graph=False)
+        after_eager = torch.rand(3)
+        for rep in range(2):                                  # second pass = pure replay of the captured graphs
+            torch.manual_seed(4)
+            g = _run(E, P, cuda, 0.05, 8, 25, noise=noise, graph=True)
+            assert g.get("graph") is True
+            assert torch.equal(torch.rand(3), after_eager)     # host generator left in the same state
+            for k in ("loss", "loss_sum", "n_valid", "loss_b", "has", "s", "V", "c", "valid", "W", "C", "X"):
+                assert torch.equal(g[k], eager[k]), k
+            if not explicit_noise:                             # (explicit noise is passed through un-masked by the eager path)
+                assert torch.equal(g["noise"], eager["noise"])
+            for k in ("bw", "idx", "K", "labels"):
+                assert torch.equal(getattr(g["cluster"], k), getattr(eager["cluster"], k)), k
+            assert g["cluster"].K_host == eager["cluster"].K_host
+            assert torch.equal(g["grad_E"], eager["grad_E"])
+    # gradient through loss_sum with an upstream scale (the multi-GPU form)
+    Ec = E.to(cuda).requires_grad_(True)
+    torch.manual_seed(8)
+    out = pipeline.fit_loss(Ec, P.to(cuda), quantile=0.05, iterations=8, max_num_clusters=25, graph=True)
+    (out["loss_sum"] * 0.25).backward()
+    Ee = E.to(cuda).requires_grad_(True)
+    torch.manual_seed(8)
+    oute = pipeline.fit_loss(Ee, P.to(cuda), quantile=0.05, iterations=8, max_num_clusters=25, graph=False)
+    (oute["loss_sum"] * 0.25).backward()
+    assert torch.equal(Ec.grad, Ee.grad)
+
+
+def test_graph_step_guard_redo_and_stale_backward(cuda, golden_dir):
+    from prifit_b200 import _lib, pipeline, synthetic
+
+    # a shape over the cluster cap: the graph step hands over to the eager guard loop, same result
+    g = _g(golden_dir, "guard_small")
+    E, P = torch.from_numpy(g["E"]), torch.from_numpy(g["P"])
+    q, T, kmax = float(g["quantile"]), int(g["iterations"]), int(g["max_num_clusters"])
+    torch.manual_seed(1)
+    a = _run(E, P, cuda, q, T, kmax, graph=True)
+    torch.manual_seed(1)
+    b = _run(E, P, cuda, q, T, kmax, graph=False)
+    assert a["cluster"].passes == b["cluster"].passes == g["passes"].tolist()
+    assert max(a["cluster"].passes) > 1 and "graph" not in a
+    assert torch.equal(a["loss"], b["loss"]) and torch.equal(a["grad_E"], b["grad_E"])
+
+    # backward of a step whose static buffers were overwritten by a later forward must fail loudly
+    E, P, _ = synthetic.planted_shapes(2, n_points=512, n_clusters=4, seed=3)
+    E1 = E.to(cuda).requires_grad_(True)
+    o1 = pipeline.fit_loss(E1, P.to(cuda), quantile=0.05, iterations=4, max_num_clusters=25, graph=True)
+    l1 = float(o1["loss"])
+    o2 = pipeline.fit_loss(E.to(cuda).mul(1.5).requires_grad_(True), P.to(cuda).flip(1), quantile=0.05, iterations=4,
+                           max_num_clusters=25, graph=True)
+    assert float(o1["loss"]) == l1                            # the small outputs are snapshots
+    with pytest.raises(_lib.PrifitError):
+        o1["loss"].backward()
+    o2["loss"].backward()
