@@ -174,12 +174,17 @@ def run_ours(args):
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
     pending = {}
 
+    h2d_events = []
+
     def stage_inputs(i):
         with torch.cuda.stream(copy_stream):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record(copy_stream)
             X = host_Xcf[i % N_SETS].to(dev, non_blocking=True)
             pts = host_Pcf[i % N_SETS].to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
+            ev = torch.cuda.Event(enable_timing=True)
             ev.record(copy_stream)
+        h2d_events.append((e0, ev))
         staged[i] = (X, pts, ev)
 
     def drain_loss():
@@ -193,10 +198,12 @@ def run_ours(args):
         X, pts, ev = staged.pop(i)
         torch.cuda.current_stream().wait_event(ev)
         X.record_stream(torch.cuda.current_stream()); pts.record_stream(torch.cuda.current_stream())
-        if not last_step:
-            stage_inputs(i + 1)
         X = X.requires_grad_(True)
         total, l, params, labels = cl.convex_loss(pts, pts, X, quantile=q, iterations=T, max_num_clusters=kmax)
+        # prefetch the next step's inputs once this step's own small host->device copy (the staged noise draws) is
+        # through: the H2D copy engine serves one queue, and 25 MB in front of it would stall the step by ~0.2 ms
+        if not last_step:
+            stage_inputs(i + 1)
         if world > 1:
             valid = params.padded[3]
             n_local = (valid.sum(1) > 0).float().sum()
@@ -258,8 +265,32 @@ def run_ours(args):
         eager_ms = eager_total / min(args.steps, 10)
     n_ms_launch = len(ms_events)
     ms_kernel = sum(a.elapsed_time(b) for a, b in ms_events) / max(n_ms_launch, 1)
+    # diagnostic: the same public-API step on inputs already resident in HBM (what the H2D staging adds on top)
+    dev_Xcf = [x.to(dev) for x in host_Xcf[:2]]
+    dev_Pcf = [p.to(dev) for p in host_Pcf[:2]]
+
+    def step_api_resident(i, timed):
+        X = dev_Xcf[i % 2].detach().requires_grad_(True)
+        total, l, params, labels = cl.convex_loss(dev_Pcf[i % 2], dev_Pcf[i % 2], X, quantile=q, iterations=T, max_num_clusters=kmax)
+        total.backward()
+
+    api_ms = None
+    if world == 1:
+        api_total, _ = timed_region(step_api_resident, min(args.steps, 10), 3)
+        api_ms = api_total / min(args.steps, 10)
     e2e_last = args.warmup + args.steps - 1
     e2e_ms, _ = timed_region(lambda i, timed: step_e2e(i, i == e2e_last or i == args.warmup - 1), args.steps, args.warmup)
+    if args.trace_e2e and rank == 0:
+        # diagnostics only (after every measurement): device timeline of the end-to-end loop under CUPTI
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        from device_timeline import print_timeline
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for i in range(8):
+                step_e2e(i, i == 7)
+            torch.cuda.synchronize()
+        with open(args.trace_e2e, "w") as f:
+            print_timeline(prof, out=f, which=4)
     clocks = sampler.stop() if rank == 0 else None
 
     res = last["out"]["cluster"]
@@ -291,6 +322,8 @@ def run_ours(args):
                    "eager_ms_per_step": None if eager_ms is None else round(eager_ms, 4)},
         "e2e": {"value": round(e2e_sps, 2), "unit": "shapes/s", "ms_per_step": round(e2e_ms / args.steps, 4),
                 "h2d_bytes_per_step": int(host_Xcf[0].numel() * 4 + host_Pcf[0].numel() * 4), "d2h_bytes_per_step": 4,
+                "api_resident_ms_per_step": None if api_ms is None else round(api_ms, 4),
+                "h2d_copy_ms_per_step": round(statistics.median(a.elapsed_time(b) for a, b in h2d_events[-args.steps:]), 4),
                 "api": "prifit_b200.convex_loss.convex_loss(points[B,3,N], chamfer[B,3,N], X[B,128,N]) + backward"},
         "gpu_launches": int(round(launches_total / (args.steps + args.warmup) * args.steps)),   # kernels + memset nodes, graph nodes included
         "gpu_launches_per_step": round(launches_total / (args.steps + args.warmup), 1),
@@ -378,6 +411,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "fp32"])
+    ap.add_argument("--trace-e2e", default=None, metavar="FILE", help="write a device timeline of the end-to-end loop (diagnostics)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

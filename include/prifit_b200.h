@@ -52,6 +52,10 @@ int prifit_device_ok(void);
 int prifit_normalize_fwd(const float* E, int64_t rows, int d, float* X, void* stream);
 /* backward of the two stacked F.normalize nodes; gE may alias gX */
 int prifit_normalize_bwd(const float* E, const float* gX, int64_t rows, int d, float* gE, void* stream);
+/* channel-first variants (the layout convex_loss receives, convex_loss.py:27,37): Ecf[B,d,N] -> X[B,N,d] and
+ *   (Ecf[B,d,N], gX[B,N,d]) -> gEcf[B,d,N]; d = 128; same arithmetic as the row-major pair (bit-identical X). */
+int prifit_normalize_fwd_cf(const float* Ecf, int B, int N, int d, float* X, void* stream);
+int prifit_normalize_bwd_cf(const float* Ecf, const float* gX, int B, int N, int d, float* gEcf, void* stream);
 
 /* k1 -- bandwidth.  src/mean_shift.py:138-160 (compute_bandwidth)
  *   rows: optional [B, n_s] int32 subset (the first num_samples entries of the host shuffle,

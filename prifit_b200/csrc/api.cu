@@ -130,6 +130,81 @@ __global__ void __launch_bounds__(256) normalize_bwd_kernel(const float* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Channel-first variants for the reference's public layout (convex_loss takes X[B,128,N] and permutes it,
+// convex_loss.py:37): the transposition happens inside the kernel through a shared-memory tile of 32 points, and
+// the row arithmetic is the same code as the d = 128 row kernels (lane l owns dims 4l..4l+3), so
+// X is bit-identical to normalize_fwd on the permuted tensor.
+//   fwd: Ecf[B,128,N] -> X[B,N,128]          bwd: Ecf[B,128,N], gX[B,N,128] -> gEcf[B,128,N]
+// ---------------------------------------------------------------------------------------------
+constexpr int CF_D = 128, CF_PTS = 32;
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) normalize_cf_kernel(const float* __restrict__ Ecf, const float* __restrict__ gX, int N,
+                                                           float* __restrict__ out) {
+    __shared__ float tile[CF_D][CF_PTS + 1];
+    const int b = blockIdx.y, n0 = blockIdx.x * CF_PTS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* Eb = Ecf + (size_t)b * CF_D * N;
+    for (int c = warp; c < CF_D; c += 8) tile[c][lane] = n0 + lane < N ? Eb[(size_t)c * N + n0 + lane] : 0.f;
+    __syncthreads();
+    for (int p = warp * 4; p < warp * 4 + 4; ++p) {
+        const int n = n0 + p;
+        if (n >= N) break;                                           // warp-uniform
+        const float4 v = make_float4(tile[4 * lane][p], tile[4 * lane + 1][p], tile[4 * lane + 2][p], tile[4 * lane + 3][p]);
+        float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        ss = warp_sum(ss);
+        const float r0 = sqrtf(ss), nrm0 = fmaxf(r0, 1e-12f);
+        const float4 x1 = make_float4(v.x / nrm0, v.y / nrm0, v.z / nrm0, v.w / nrm0);
+        float ss1 = x1.x * x1.x + x1.y * x1.y + x1.z * x1.z + x1.w * x1.w;
+        ss1 = warp_sum(ss1);
+        const float r1 = sqrtf(ss1), nrm1 = fmaxf(r1, 1e-12f);
+        if (!BWD) {
+            reinterpret_cast<float4*>(out + ((size_t)b * N + n) * CF_D)[lane] =
+                make_float4(x1.x / nrm1, x1.y / nrm1, x1.z / nrm1, x1.w / nrm1);
+        } else {
+            const float4 g = reinterpret_cast<const float4*>(gX + ((size_t)b * N + n) * CF_D)[lane];
+            float xg = (x1.x / nrm1) * g.x + (x1.y / nrm1) * g.y + (x1.z / nrm1) * g.z + (x1.w / nrm1) * g.w;
+            xg = warp_sum(xg);
+            const bool proj1 = r1 >= 1e-12f, proj0 = r0 >= 1e-12f;
+            const float xv[4] = {x1.x, x1.y, x1.z, x1.w}, gv[4] = {g.x, g.y, g.z, g.w};
+            float g1[4], x1g1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                g1[i] = (gv[i] - (proj1 ? (xv[i] / nrm1) * xg : 0.f)) / nrm1;
+                x1g1 += xv[i] * g1[i];
+            }
+            x1g1 = warp_sum(x1g1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tile[4 * lane + i][p] = (g1[i] - (proj0 ? xv[i] * x1g1 : 0.f)) / nrm0;
+        }
+    }
+    if (BWD) {
+        __syncthreads();
+        float* Ob = out + (size_t)b * CF_D * N;
+        for (int c = warp; c < CF_D; c += 8)
+            if (n0 + lane < N) Ob[(size_t)c * N + n0 + lane] = tile[c][lane];
+    }
+}
+
+extern "C" int prifit_normalize_fwd_cf(const float* Ecf, int B, int N, int d, float* X, void* stream) {
+    PF_CHECK_ARG(Ecf && X, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(B > 0 && N > 0, PRIFIT_E_BADARG, "B, N > 0 required");
+    PF_CHECK_ARG(d == CF_D, PRIFIT_E_SHAPE, "the channel-first kernels are specialised for d = 128");
+    normalize_cf_kernel<false><<<dim3((N + CF_PTS - 1) / CF_PTS, B), 256, 0, pf_stream(stream)>>>(Ecf, nullptr, N, X);
+    PF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int prifit_normalize_bwd_cf(const float* Ecf, const float* gX, int B, int N, int d, float* gEcf, void* stream) {
+    PF_CHECK_ARG(Ecf && gX && gEcf, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(B > 0 && N > 0, PRIFIT_E_BADARG, "B, N > 0 required");
+    PF_CHECK_ARG(d == CF_D, PRIFIT_E_SHAPE, "the channel-first kernels are specialised for d = 128");
+    normalize_cf_kernel<true><<<dim3((N + CF_PTS - 1) / CF_PTS, B), 256, 0, pf_stream(stream)>>>(Ecf, gX, N, gEcf);
+    PF_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int prifit_normalize_fwd(const float* E, int64_t rows, int d, float* X, void* stream) {
     PF_CHECK_ARG(E && X, PRIFIT_E_BADARG, "null pointer");
     PF_CHECK_ARG(rows > 0 && d > 0 && d % 4 == 0, PRIFIT_E_SHAPE, "rows > 0 and d % 4 == 0 required");

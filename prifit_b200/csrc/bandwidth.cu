@@ -21,17 +21,22 @@ constexpr int BW_TILE = 64;  // keys per tile
 template <int R>
 __global__ void __launch_bounds__(BW_THREADS) bandwidth_rows_kernel(
     const float* __restrict__ X, int N, int d, const int32_t* __restrict__ rows, int n_s,
-    const int32_t* __restrict__ kth, float* __restrict__ rowval /*[B,n_s]*/, const int32_t* __restrict__ only_if) {
+    const int32_t* __restrict__ kth, float* __restrict__ rowval /*[B,n_s]*/, const int32_t* __restrict__ only_if,
+    int tiles_x, int items) {
     extern __shared__ __align__(16) float smem[];
     if (only_if && *only_if == 0) return;     // exact fallback of the tensor-core path: runs only on overflow
+    // work item = (shape, block of R rows); the fallback launch uses one CTA per SM looping over the items, so that
+    // the normal case (flag clear) costs 148 empty CTAs instead of one empty CTA per item
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    __syncthreads();
     const int ld = d + 4;
     float* dist = smem;                       // [R][n_s]
     float* ys = dist + (size_t)R * n_s;       // [R][ld]
     float* xs = ys + R * ld;                  // [BW_TILE][ld]
     uint32_t* hist = reinterpret_cast<uint32_t*>(xs + BW_TILE * ld);  // [8][256]
 
-    const int b = blockIdx.y;
-    const int r0 = blockIdx.x * R;
+    const int b = item / tiles_x;
+    const int r0 = (item - b * tiles_x) * R;
     const float* Xb = X + (size_t)b * N * d;
     const int32_t* rb = rows ? rows + (size_t)b * n_s : nullptr;
     const int tid = threadIdx.x;
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(BW_THREADS) bandwidth_rows_kernel(
             rowval[(size_t)b * n_s + i] = sqrtf(fmaxf(v, 1e-6f));     // guard_sqrt(., 1e-6), line 158
         }
     }
+    }
 }
 
 __global__ void __launch_bounds__(256) bandwidth_mean_kernel(const float* __restrict__ rowval, int n_s,
@@ -162,8 +168,9 @@ int launch_rows(const float* X, int B, int N, int d, const int32_t* rows, int n_
                 float* rowval, const int32_t* only_if, cudaStream_t st) {
     const size_t smem = bw_smem_bytes(R, n_s, d);
     PF_CUDA(cudaFuncSetAttribute(bandwidth_rows_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((n_s + R - 1) / R, B);
-    bandwidth_rows_kernel<R><<<grid, BW_THREADS, smem, st>>>(X, N, d, rows, n_s, kth, rowval, only_if);
+    const int tiles_x = (n_s + R - 1) / R, items = tiles_x * B;
+    const int grid = only_if ? (items < 148 ? items : 148) : items;
+    bandwidth_rows_kernel<R><<<grid, BW_THREADS, smem, st>>>(X, N, d, rows, n_s, kth, rowval, only_if, tiles_x, items);
     PF_LAUNCH_CHECK();
     return 0;
 }

@@ -319,7 +319,7 @@ def default_enabled():
 
 
 def default_branches():
-    return int(os.environ.get("PRIFIT_GRAPH_BRANCHES", "2"))
+    return int(os.environ.get("PRIFIT_GRAPH_BRANCHES", "3"))
 
 
 def get_step(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches):
