@@ -58,8 +58,9 @@ class _Arena:
 
 
 class GraphStep:
-    def __init__(self, B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches):
-        self.key = (B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches)
+    def __init__(self, B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches, cf=False):
+        self.key = (B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches, cf)
+        self.cf = bool(cf)           # embeddings arrive (and their gradient leaves) channel-first: [B, d, N]
         self.B, self.N, self.d, self.M, self.T = B, N, d, M, int(iterations)
         self.quantile, self.kmax = float(quantile), int(max_num_clusters)
         self.kcap = ops.kcap_for(max_num_clusters)
@@ -85,7 +86,7 @@ class GraphStep:
             return torch.empty(*shape, dtype=dtype, device=device)
 
         # ---- static inputs
-        self.E, self.P = buf(B, N, d), buf(B, N, 3)
+        self.E, self.P = (buf(B, d, N) if cf else buf(B, N, d)), buf(B, N, 3)
         self.Q = self.P if M is None else buf(B, M, 3)
         self.Mq = N if M is None else M
         self.flat = buf(B * kcap, 3, 3)
@@ -109,7 +110,8 @@ class GraphStep:
         self.noise, self.fctx = buf(B, kcap, 3, 3), buf(B, kcap, _lib.FIT_CTX)
         self.argmin, self.sdf = buf(B, self.Mq, dtype=i32), buf(B, self.Mq)
         self.gloss, self.gs, self.gV, self.gc = buf(B), buf(B, kcap, 3), buf(B, kcap, 3, 3), buf(B, kcap, 3)
-        self.gW, self.gC, self.gX, self.gE = buf(B, kcap, N), buf(B, kcap, d), buf(B, N, d), buf(B, N, d)
+        self.gW, self.gC, self.gX = buf(B, kcap, N), buf(B, kcap, d), buf(B, N, d)
+        self.gE = buf(B, d, N) if cf else buf(B, N, d)
         self.counts = torch.zeros(2, B, dtype=i32).pin_memory()
         # ---- per-branch workspaces
         self.ws = []
@@ -147,7 +149,10 @@ class GraphStep:
         def branch(i, lo, hi):
             Bb, ws, st = hi - lo, self.ws[i], _stream()
             X, bw, newX = self.X[lo:hi], sm["bw"][lo:hi], self.newX[lo:hi]
-            _lib.call("prifit_normalize_fwd", _ptr(self.E[lo:hi]), Bb * N, d, _ptr(X), st)
+            if self.cf:
+                _lib.call("prifit_normalize_fwd_cf", _ptr(self.E[lo:hi]), Bb, N, d, _ptr(X), st)
+            else:
+                _lib.call("prifit_normalize_fwd", _ptr(self.E[lo:hi]), Bb * N, d, _ptr(X), st)
             _lib.call("prifit_bandwidth_fwd", _ptr(X), Bb, N, d, None, N, _ptr(self.kth[lo:hi]), _ptr(bw),
                       _ptr(ws["bw"][0]), ws["bw"][1], st)
             _lib.call("prifit_meanshift_fwd", _ptr(X), _ptr(bw), Bb, N, d, T, _ptr(newX), self.engine,
@@ -200,7 +205,10 @@ class GraphStep:
                       Bb, N, d, kcap, _ptr(gC), _ptr(gX), st)
             _lib.call("prifit_meanshift_rows_bwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), _ptr(self.traj[lo:hi]),
                       _ptr(self.stat[lo:hi]), _ptr(gC), Bb, N, d, T, kcap, _ptr(gX), self.rows_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
-            _lib.call("prifit_normalize_bwd", _ptr(self.E[lo:hi]), _ptr(gX), Bb * N, d, _ptr(self.gE[lo:hi]), st)
+            if self.cf:
+                _lib.call("prifit_normalize_bwd_cf", _ptr(self.E[lo:hi]), _ptr(gX), Bb, N, d, _ptr(self.gE[lo:hi]), st)
+            else:
+                _lib.call("prifit_normalize_bwd", _ptr(self.E[lo:hi]), _ptr(gX), Bb * N, d, _ptr(self.gE[lo:hi]), st)
 
         self._fork_join(branch)
 
@@ -308,7 +316,12 @@ class _Attach(torch.autograd.Function):
     def backward(ctx, g_sum, g_mean):
         if g_sum is None and g_mean is None:
             return None, None, None, None, None
-        return ctx.step.run_backward(ctx.serial, g_sum, g_mean), None, None, None, None
+        gE = ctx.step.run_backward(ctx.serial, g_sum, g_mean)
+        # Row-major input: the static buffer itself is handed to autograd -- AccumulateGrad copies a gradient whose
+        # tensor object something else still references, every other consumer reads it before the next replay.
+        # Channel-first input: the gradient reaches the caller's leaf through view nodes (transpose / permute), whose
+        # fresh view objects AccumulateGrad would adopt without copying, so the copy is made here.
+        return (gE.clone() if ctx.step.cf else gE), None, None, None, None
 
 
 _steps = {}
@@ -322,13 +335,13 @@ def default_branches():
     return int(os.environ.get("PRIFIT_GRAPH_BRANCHES", "3"))
 
 
-def get_step(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches):
-    key = (B, N, d, M, float(quantile), int(iterations), int(max_num_clusters), engine, rows_engine, device, branches)
+def get_step(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches, cf=False):
+    key = (B, N, d, M, float(quantile), int(iterations), int(max_num_clusters), engine, rows_engine, device, branches, cf)
     st = _steps.get(key)
     if st is None:
         if len(_steps) >= 8:                               # static buffers are ~6 MB per shape: keep a few configurations
             _steps.pop(next(iter(_steps)))
-        st = _steps[key] = GraphStep(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches)
+        st = _steps[key] = GraphStep(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, device, branches, cf)
     return st
 
 
@@ -340,9 +353,13 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
     engine = ops.DEFAULT_ENGINE if engine is None else engine
     rows_engine = ops._rows_engine(None, d)
     M = None if Q is None else Q.shape[1]
+    # channel-first input (convex_loss hands over X[B,d,N].permute(0,2,1)): keep it channel-first, the normalisation
+    # kernels transpose on the fly and the gradient leaves in the caller's layout
+    cf = d == 128 and not E.is_contiguous() and E.transpose(1, 2).is_contiguous()
+    src = E.transpose(1, 2) if cf else E
     step = get_step(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, E.device,
-                    default_branches() if branches is None else int(branches))
-    res = step.run_forward(E.detach(), P.detach(), None if Q is None else Q.detach(), noise)
+                    default_branches() if branches is None else int(branches), cf)
+    res = step.run_forward(src.detach(), P.detach(), None if Q is None else Q.detach(), noise)
     if res is None:
         return None
     cluster = pipeline.ClusterResult(bw=res["bw"], idx=res["idx"], K=res["K"], labels=res["labels"], K_host=res["K_host"],
@@ -350,7 +367,7 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
                                      kcap=step.kcap, iterations=int(iterations))
     loss_sum, loss = res["loss_sum"], res["loss"]
     if E.requires_grad and torch.is_grad_enabled():
-        loss_sum, loss = _Attach.apply(E, step, res["serial"], loss_sum, loss)
+        loss_sum, loss = _Attach.apply(src, step, res["serial"], loss_sum, loss)
     return {"loss": loss, "loss_sum": loss_sum, "n_valid": res["n_valid"], "loss_b": res["loss_b"], "has": res["has"],
             "s": res["s"], "V": res["V"], "c": res["c"], "valid": res["valid"], "cluster": cluster, "W": res["W"],
             "C": res["C"], "X": res["X"], "noise": res["noise"], "graph": True}

@@ -399,3 +399,44 @@ def test_graph_step_guard_redo_and_stale_backward(cuda, golden_dir):
     with pytest.raises(_lib.PrifitError):
         o1["loss"].backward()
     o2["loss"].backward()
+
+
+def test_channel_first_public_api_graph_vs_eager(cuda, monkeypatch):
+    """convex_loss() takes the reference's channel-first tensors.  The graph path keeps them channel-first (the
+    normalisation kernels transpose on the fly, same row arithmetic), the eager path permutes + copies: identical
+    loss, labels, parameters and X.grad -- and X.grad must not alias the replayed step's static buffer."""
+    import prifit_b200.convex_loss as cl
+    from prifit_b200 import ops, synthetic
+
+    E, P, _ = synthetic.planted_shapes(4, n_points=700, n_clusters=5, seed=13)       # N not a multiple of 32
+    Xcf = E.permute(0, 2, 1).contiguous().to(cuda)
+    Pcf = P.permute(0, 2, 1).contiguous().to(cuda)
+    outs = []
+    for graph in ("1", "0", "1"):
+        monkeypatch.setenv("PRIFIT_GRAPH", graph)
+        X = Xcf.clone().requires_grad_(True)
+        torch.manual_seed(17)
+        total, l, params, labels = cl.convex_loss(Pcf, Pcf, X, quantile=0.05, iterations=6, max_num_clusters=25)
+        total.backward()
+        outs.append((total.detach().clone(), X.grad, [t.clone() for t in params.padded], [t.clone() for t in labels]))
+    g, e, g2 = outs
+    assert torch.equal(g[0], e[0]) and torch.equal(g[1], e[1])
+    for a, b in zip(g[2], e[2]):
+        assert torch.equal(a, b)
+    for a, b in zip(g[3], e[3]):
+        assert torch.equal(a, b)
+    assert torch.equal(g[1], g2[1]) and g[1].data_ptr() != g2[1].data_ptr()           # first step's grad survived the replay
+
+    # the channel-first kernels alone against the row-major pair
+    Ecl = E.to(cuda)
+    X_cl = ops.normalize_fwd(Ecl)
+    X_cf = torch.empty_like(X_cl)
+    from prifit_b200 import _lib
+    B, N, d = Ecl.shape
+    _lib.call("prifit_normalize_fwd_cf", ops._ptr(Xcf), B, N, d, ops._ptr(X_cf), ops._stream())
+    assert torch.equal(X_cf, X_cl)
+    gX = torch.randn_like(X_cl)
+    gE_cl = ops.normalize_bwd(Ecl, gX)
+    gE_cf = torch.empty_like(Xcf)
+    _lib.call("prifit_normalize_bwd_cf", ops._ptr(Xcf), ops._ptr(gX), B, N, d, ops._ptr(gE_cf), ops._stream())
+    assert float((gE_cf.permute(0, 2, 1) - gE_cl).abs().max()) <= 1e-6 * float(gE_cl.abs().max())
