@@ -160,7 +160,8 @@ def run_ours(args):
         E = dev_E[i % N_SETS].detach().requires_grad_(True)
         graph = use_graph if graph is None else graph
         ops.TIMING = ms_events if (timed and not graph) else None
-        out = pipeline.fit_loss(E, dev_P[i % N_SETS], quantile=q, iterations=T, max_num_clusters=kmax, graph=graph)
+        out = pipeline.fit_loss(E, dev_P[i % N_SETS], quantile=q, iterations=T, max_num_clusters=kmax, graph=graph,
+                                dist_reduce=world > 1)
         ops.TIMING = None
         L, Lb = pdist.global_loss(out)
         Lb.backward()

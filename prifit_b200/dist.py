@@ -39,7 +39,9 @@ def global_mean_from_local(local_mean, n_local, group=None):
 
 def global_loss(out, group=None):
     """Same reduction from pipeline.fit_loss()'s fused outputs (`loss_sum`, `n_valid`, `loss`): on one rank the
-    local mean is the global mean and nothing is enqueued."""
+    local mean is the global mean and nothing is enqueued.  fit_loss(dist_reduce=True) has already done it."""
+    if "loss_global" in out:
+        return out["loss_global"], out["loss_backward"]
     if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
         return out["loss"].detach(), out["loss"]
     tot = torch.stack([out["loss_sum"].detach(), out["n_valid"]])

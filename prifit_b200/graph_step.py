@@ -239,8 +239,8 @@ class GraphStep:
 
     # ------------------------------------------------------------------------------------------ per step
     def run_forward(self, E, P, Q, noise):
-        """Returns the step's result dict, or None when the guard asks for a redo (caller: eager path).  The host
-        generator is left exactly where the reference would leave it in the first case and untouched in the second."""
+        """Enqueues the step (input copies, noise staging, graphs 1 and 2, snapshot of the small outputs) without
+        waiting for anything and returns the result dict; finish_forward() then makes the guard decision."""
         self.serial += 1
         self.E.copy_(E)
         self.P.copy_(P)
@@ -265,26 +265,36 @@ class GraphStep:
             self.direct.fill_(want_direct)
             self.direct_host = want_direct
         self.graphs[0].replay()
-        ev = torch.cuda.Event()
-        ev.record()
+        self._ev = torch.cuda.Event()
+        self._ev.record()
         self.graphs[1].replay()
         _lib._launches += self.launches[0] + self.launches[1]
-        ev.synchronize()                                   # the step's one host synchronisation (2 B int32)
+        self._state = state
+        # snapshot of the small outputs: enqueued (and its views built) before the host waits, so that after the
+        # read-back the host only has the guard decision between itself and the backward launch
+        snap = self.arena.views(self.arena.buf.clone())
+        loss_sum, n_valid, loss = snap["stats"].unbind(0)
+        out = dict(snap)
+        out.update({"loss": loss, "loss_sum": loss_sum, "n_valid": n_valid, "W": self.W, "C": self.C, "X": self.X,
+                    "noise": self.noise, "serial": self.serial})
+        return out
+
+    def finish_forward(self, out):
+        """Host side of the guard (src/ellipsoid_utils.py:19-26): waits for graph 1 only (graph 2 keeps the device
+        busy), reads the counts, settles the host generator.  False = a shape exceeded the cap: redo eagerly."""
+        self._ev.synchronize()                             # the step's one host synchronisation (2 B int32)
         K_host, nlab_host = self.counts[0].tolist(), self.counts[1].tolist()
+        state = self._state
         if state is not None:
             torch.set_rng_state(state)
         if max(nlab_host) > self.kmax:                     # src/ellipsoid_utils.py:23-24 -> redo on the eager path
-            return None
+            return False
         if max(K_host) > self.kcap:
             raise _lib.PrifitError("%d cluster centres exceed the padded capacity %d" % (max(K_host), self.kcap))
         if state is not None:
             torch.rand(int(sum(K_host)), 3, 3)             # one rand(3, 3) per attempted cluster, like the reference
-        snap = self.arena.views(self.arena.buf.clone())
-        loss_sum, n_valid, loss = snap["stats"].unbind(0)
-        out = dict(snap)
-        out.update({"loss": loss, "loss_sum": loss_sum, "n_valid": n_valid, "K_host": K_host, "n_labels_host": nlab_host,
-                    "W": self.W, "C": self.C, "X": self.X, "noise": self.noise, "serial": self.serial})
-        return out
+        out["K_host"], out["n_labels_host"] = K_host, nlab_host
+        return True
 
     def run_backward(self, serial, g_sum, g_mean):
         if serial != self.serial:
@@ -345,7 +355,7 @@ def get_step(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_en
     return st
 
 
-def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, branches=None):
+def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, branches=None, dist_reduce=False):
     """Graph-replayed pipeline.fit_loss.  Returns None when the step has to be redone on the eager path."""
     from . import pipeline
 
@@ -360,14 +370,18 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
     step = get_step(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, E.device,
                     default_branches() if branches is None else int(branches), cf)
     res = step.run_forward(src.detach(), P.detach(), None if Q is None else Q.detach(), noise)
-    if res is None:
+    loss_sum, loss = res["loss_sum"], res["loss"]
+    if E.requires_grad and torch.is_grad_enabled():
+        loss_sum, loss = _Attach.apply(src, step, res["serial"], loss_sum, loss)
+    extra = {}
+    if dist_reduce:                  # the multi-GPU mean, enqueued while the host still has slack (before the read-back)
+        from . import dist as pdist
+        extra["loss_global"], extra["loss_backward"] = pdist.global_loss({"loss": loss, "loss_sum": loss_sum, "n_valid": res["n_valid"]})
+    if not step.finish_forward(res):
         return None
     cluster = pipeline.ClusterResult(bw=res["bw"], idx=res["idx"], K=res["K"], labels=res["labels"], K_host=res["K_host"],
                                      n_labels_host=res["n_labels_host"], passes=[1] * B, quantiles=[float(quantile)] * B,
                                      kcap=step.kcap, iterations=int(iterations))
-    loss_sum, loss = res["loss_sum"], res["loss"]
-    if E.requires_grad and torch.is_grad_enabled():
-        loss_sum, loss = _Attach.apply(src, step, res["serial"], loss_sum, loss)
     return {"loss": loss, "loss_sum": loss_sum, "n_valid": res["n_valid"], "loss_b": res["loss_b"], "has": res["has"],
             "s": res["s"], "V": res["V"], "c": res["c"], "valid": res["valid"], "cluster": cluster, "W": res["W"],
-            "C": res["C"], "X": res["X"], "noise": res["noise"], "graph": True}
+            "C": res["C"], "X": res["X"], "noise": res["noise"], "graph": True, **extra}

@@ -230,19 +230,21 @@ def _graph_ok(E, P, Q, noise, num_samples, kcap):
 
 
 def fit_loss(E, P, quantile=0.05, iterations=10, max_num_clusters=25, noise=None, Q=None, engine=None,
-             num_samples=None, graph=None):
+             num_samples=None, graph=None, dist_reduce=False):
     """Whole hot path on a batch.  Returns dict(loss, loss_sum, n_valid, loss_b, has, s, V, c, valid, cluster, W, C, X).
 
     `loss` is differentiable w.r.t. E (and P/Q if they require grad).  graph=None/True replays the step as CUDA
     graphs over static buffers (graph_step.py; PRIFIT_GRAPH=0 disables): same kernels, same results, but W / C / X /
     noise are then views of static buffers (valid until the next call) and gradients flow to E only through the
-    loss.  graph=False (or a guard redo, point gradients, a sub-sampled bandwidth) takes the eager autograd path."""
+    loss.  graph=False (or a guard redo, point gradients, a sub-sampled bandwidth) takes the eager autograd path.
+    dist_reduce=True also enqueues dist.global_loss() (the multi-GPU mean) and returns it as `loss_global` /
+    `loss_backward`."""
     from . import graph_step
 
     if graph is None:
         graph = graph_step.default_enabled()
     if graph and _graph_ok(E, P, Q, noise, num_samples, ops.kcap_for(max_num_clusters)):
-        out = graph_step.fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine)
+        out = graph_step.fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, dist_reduce=dist_reduce)
         if out is not None:
             return out
     X = ops.NormalizeTwice.apply(E)
@@ -269,5 +271,9 @@ def fit_loss(E, P, quantile=0.05, iterations=10, max_num_clusters=25, noise=None
             noise = draw_noise(res.K_host, res.kcap, X.device)
         outs = ops.FitSdfMean.apply(P, Qp, W, res.K, noise)
     loss_sum, loss, loss_b, s, V, c, valid, has, n_valid = outs
-    return {"loss": loss, "loss_sum": loss_sum, "n_valid": n_valid, "loss_b": loss_b, "has": has, "s": s, "V": V, "c": c,
-            "valid": valid, "cluster": res, "W": W, "C": C, "X": X, "noise": noise}
+    out = {"loss": loss, "loss_sum": loss_sum, "n_valid": n_valid, "loss_b": loss_b, "has": has, "s": s, "V": V, "c": c,
+           "valid": valid, "cluster": res, "W": W, "C": C, "X": X, "noise": noise}
+    if dist_reduce:
+        from . import dist as pdist
+        out["loss_global"], out["loss_backward"] = pdist.global_loss(out)
+    return out

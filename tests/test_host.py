@@ -151,6 +151,16 @@ Lb.backward()
 ref = (loss_all * has_all).sum() / has_all.sum()
 assert abs(float(L) - float(ref)) < 1e-12, (float(L), float(ref))
 assert torch.allclose(lb.grad, has_all[lo:hi] / has_all.sum()), lb.grad
+# the same reduction from the fused outputs of pipeline.fit_loss (loss_sum, n_valid, loss)
+lb2 = loss_all[lo:hi].clone().requires_grad_(True)
+h = has_all[lo:hi]
+out = {{"loss_sum": (lb2 * h).sum(), "n_valid": h.sum(), "loss": (lb2 * h).sum() / h.sum().clamp(min=1.0)}}
+L2, Lb2 = pdist.global_loss(out)
+Lb2.backward()
+assert abs(float(L2) - float(ref)) < 1e-12
+assert torch.allclose(lb2.grad, has_all[lo:hi] / has_all.sum()), lb2.grad
+out["loss_global"], out["loss_backward"] = L2, Lb2
+assert pdist.global_loss(out)[0] is L2
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
