@@ -72,7 +72,7 @@ template <int MODE> struct GCfg {
       : MODE == GM_HIST ? (size_t)G_BM * HIST_WORDS * 4
       : MODE == GM_COLLECT ? (size_t)G_EPI * CAND_Q * 2 + 16 * 4 * CAND_Q * sizeof(float) + 2 * G_EPI * sizeof(int)
       : 16;
-    static constexpr size_t smem = 1024 + (size_t)G_STAGES * G_STAGE_BYTES + G_HALF_BYTES /* A hi tile */ + 256 + scratch;
+    static constexpr size_t smem = 1024 + (size_t)G_STAGES * G_STAGE_BYTES + 256 + scratch;
 };
 
 struct GBars {
@@ -113,9 +113,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;
-    uint8_t* ahi = smem + (size_t)G_STAGES * G_STAGE_BYTES;      // A operand, hi half: [2 x 64-column block][128 rows][128 B], SWIZZLE_128B
-    GBars* bars = reinterpret_cast<GBars*>(ahi + G_HALF_BYTES);
-    uint8_t* scratch = ahi + G_HALF_BYTES + 256;
+    GBars* bars = reinterpret_cast<GBars*>(smem + (size_t)G_STAGES * G_STAGE_BYTES);
+    uint8_t* scratch = smem + (size_t)G_STAGES * G_STAGE_BYTES + 256;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nt = (N + G_BN - 1) / G_BN;
@@ -158,7 +157,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                 mbar_wait(&bars->x_full[st], xph);
                 mbar_wait(&bars->s_free[buf], ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t base = smem_u32(tiles + (size_t)st * G_STAGE_BYTES), abase = smem_u32(ahi);
+                const uint32_t base = smem_u32(tiles + (size_t)st * G_STAGE_BYTES);
                 const uint32_t acc = tmem + buf * 128;
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)
@@ -167,10 +166,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                         const uint32_t qo = kb * 32 + ks * 8;
                         const uint64_t bhi = smem_desc_sw128(base + kb * G_KBLOCK + ks * 32, 16, 1024);
                         const uint64_t blo = smem_desc_sw128(base + G_HALF_BYTES + kb * G_KBLOCK + ks * 32, 16, 1024);
-                        const uint64_t ah = smem_desc_sw128(abase + kb * G_KBLOCK + ks * 32, 16, 1024);
-                        mma_f16_ts(acc, tmem + GCOL_QLO + qo, bhi, idesc, (kb | ks) != 0);   // lo_a . hi_b   (A from tensor memory)
-                        mma_f16_ss(acc, ah, blo, idesc, true);                                // hi_a . lo_b   (A from shared memory)
-                        mma_f16_ss(acc, ah, bhi, idesc, true);                                // hi_a . hi_b
+                        mma_f16_ts(acc, tmem + GCOL_QLO + qo, bhi, idesc, (kb | ks) != 0);
+                        mma_f16_ts(acc, tmem + GCOL_QHI + qo, blo, idesc, true);
+                        mma_f16_ts(acc, tmem + GCOL_QHI + qo, bhi, idesc, true);
                     }
                 mma_commit(&bars->s_full[buf]);
                 mma_commit(&bars->x_empty[st]);
@@ -195,23 +193,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
             uint32_t h[16];
             const uint4* xhi = reinterpret_cast<const uint4*>(a.Xs + grow * G_D) + 4 * qt;
             const uint4* xlo = reinterpret_cast<const uint4*>(a.Xs + ((size_t)a.B * N + grow) * G_D) + 4 * qt;
-            // hi half -> shared memory (two of the three products read it: the tensor-memory read path, shared with
-            // the epilogue's tcgen05.ld, carried 96 KB of A fetches per key tile when both halves lived in TMEM);
-            // 16-byte chunk c of a row sits at c ^ (row & 7) inside the row's 128 bytes of its 64-column block
-            uint8_t* arow = ahi + (size_t)(qt >> 1) * G_KBLOCK + (size_t)row * 128;
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                *reinterpret_cast<uint4*>(arow + (((4 * (qt & 1) + e) ^ (row & 7)) << 4)) = row_ok ? xhi[e] : make_uint4(0u, 0u, 0u, 0u);
-            // lo half -> tensor memory (packed f16 pairs)
+            for (int part = 0; part < 2; ++part) {
+                const uint4* src = part == 0 ? xhi : xlo;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const uint4 f = row_ok ? xlo[e] : make_uint4(0u, 0u, 0u, 0u);
-                h[4 * e] = f.x; h[4 * e + 1] = f.y; h[4 * e + 2] = f.z; h[4 * e + 3] = f.w;
+                for (int e = 0; e < 4; ++e) {
+                    const uint4 f = row_ok ? src[e] : make_uint4(0u, 0u, 0u, 0u);
+                    h[4 * e] = f.x; h[4 * e + 1] = f.y; h[4 * e + 2] = f.z; h[4 * e + 3] = f.w;
+                }
+                tmem_st16(tmem + lane_base + (part == 0 ? GCOL_QHI : GCOL_QLO) + 16 * qt, h);
             }
-            tmem_st16(tmem + lane_base + GCOL_QLO + 16 * qt, h);
             tmem_wait_st();
             tc_fence_before();
-            fence_proxy_async();
             mbar_arrive(&bars->q_full);
         }
 
