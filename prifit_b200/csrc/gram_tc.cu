@@ -35,6 +35,7 @@
 // duplicates) raise the overflow flag and the exact CUDA-core kernel (bandwidth.cu) redoes the batch.
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <type_traits>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -55,7 +56,6 @@ constexpr uint32_t G_KBLOCK = G_BN * 128;                // one 64-column (128 B
 constexpr uint32_t GCOL_QHI = 256, GCOL_QLO = 320;
 constexpr float G_PRESCALE = 256.0f;                     // operands carry x * 2^8  ->  S = 2^16 <a, b>
 constexpr float G_DIST_MUL = -2.0f / 65536.0f;
-constexpr float G_DIST_MAX = 3.9999998f;                 // largest float below 4
 enum { GM_NEAREST = 0, GM_BEST = 1, GM_HIST = 2, GM_COLLECT = 3, GM_DUMP = 4 };
 
 constexpr int HIST_BINS = 256;
@@ -94,13 +94,18 @@ struct GramArgs {
     int32_t* overflow;       // [1]       (COLLECT out): candidate list overflow / window miss
     float* dump;             // [B,N,N]   (DUMP out)
     int N, B, level;
+    int dbg;                 // timing experiments only (PRIFIT_GRAM_DEBUG): 1 = hi.hi product only
 };
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-__device__ __forceinline__ float tc_dist(uint32_t sbits) {
-    // 2.0 - 2.0 * <a, b>, clamped to [0, 4): the same expression in every pass, so bins are consistent
-    return fminf(fmaxf(fmaf(__uint_as_float(sbits), G_DIST_MUL, 2.0f), 0.0f), G_DIST_MAX);
+// The epilogues work on q = dist / 4 = saturate(0.5 - <a, b> / 2) in [0, 1]: one FFMA.SAT on the FMA pipe instead of an
+// FFMA and two FMNMX on the half-rate ALU pipe, which is what bounds these kernels (ncu: ALU pipe, not issue slots, not
+// the tensor pipe).  Scaling by a power of two commutes with every rounding involved, so q * 4 is bit-identical to
+// clamp(2 - 2 <a, b>, 0, 4) and every comparison / bin below equals the one in distance units.  Same expression in every
+// pass, so the bins are consistent.
+__device__ __forceinline__ float tc_q(uint32_t sbits) {
+    return __saturatef(fmaf(__uint_as_float(sbits), 0.25f * G_DIST_MUL, 0.5f));
 }
 
 template <int MODE>
@@ -166,9 +171,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                         const uint32_t qo = kb * 32 + ks * 8;
                         const uint64_t bhi = smem_desc_sw128(base + kb * G_KBLOCK + ks * 32, 16, 1024);
                         const uint64_t blo = smem_desc_sw128(base + G_HALF_BYTES + kb * G_KBLOCK + ks * 32, 16, 1024);
-                        mma_f16_ts(acc, tmem + GCOL_QLO + qo, bhi, idesc, (kb | ks) != 0);
-                        mma_f16_ts(acc, tmem + GCOL_QHI + qo, blo, idesc, true);
-                        mma_f16_ts(acc, tmem + GCOL_QHI + qo, bhi, idesc, true);
+                        if (!(a.dbg & 1)) {
+                            mma_f16_ts(acc, tmem + GCOL_QLO + qo, bhi, idesc, (kb | ks) != 0);
+                            mma_f16_ts(acc, tmem + GCOL_QHI + qo, blo, idesc, true);
+                        }
+                        mma_f16_ts(acc, tmem + GCOL_QHI + qo, bhi, idesc, (a.dbg & 1) ? (kb | ks) != 0 : true);
                     }
                 mma_commit(&bars->s_full[buf]);
                 mma_commit(&bars->x_empty[st]);
@@ -216,12 +223,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
         int* cmb_i = reinterpret_cast<int*>(scratch) + 3 * G_BM;                           //               [3][128]
         float* vt = reinterpret_cast<float*>(scratch + (size_t)3 * G_BM * 8);              // BEST: [2][128]
         uint32_t* hist = reinterpret_cast<uint32_t*>(scratch) + (size_t)row * HIST_WORDS;  // HIST: own row
+        const uint32_t hist_s = smem_u32(hist);
         uint16_t* cand = reinterpret_cast<uint16_t*>(scratch) + (size_t)(row * 4 + qt) * CAND_Q;   // COLLECT
         float win_lo = 0.f, win_hi = 0.f, hscale = HIST_SCALE0;
         int below = 0, ncand = 0, krem = 1;
         float vnext = 0.f;
         if (MODE == GM_BEST) {
-            bwv = a.bw[b];
+            bwv = 0.25f * a.bw[b];                                 // threshold in q units
             vnext = et < G_BN && et < N ? (float)a.votes[(size_t)b * N + et] : 0.f;
         }
         if (MODE == GM_HIST) {
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
             krem = max(1, min(a.kth[b], N));
             if (a.level > 0 && row_ok) {
                 const int2 ri = a.rowinfo[grow];
-                win_lo = __int_as_float(ri.x);
+                win_lo = 0.25f * __int_as_float(ri.x);                // window start in q units (rowinfo keeps distance units)
                 krem = ri.y;
                 hscale = HIST_SCALE1;
             }
@@ -237,10 +245,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
         }
         if (MODE == GM_COLLECT && row_ok) {
             const float lo2 = __int_as_float(a.rowinfo[grow].x);
-            win_lo = lo2 - BW_MARGIN;
-            win_hi = lo2 + 1.0f / HIST_SCALE1 + BW_MARGIN;
+            win_lo = 0.25f * (lo2 - BW_MARGIN);
+            win_hi = 0.25f * (lo2 + 1.0f / HIST_SCALE1 + BW_MARGIN);
         }
 
+        const float hscale4 = 4.0f * hscale;                       // bins per unit of q
+        const uint32_t lo_bits = __float_as_uint(fmaxf(win_lo, 0.f));                 // COLLECT: window as bit patterns of q
+        const uint32_t win_bits = __float_as_uint(fmaxf(win_hi, 0.f)) - lo_bits;
         for (int j = 0; j < nt; ++j) {
             const uint32_t buf = j & 1, ph = (j >> 1) & 1;
             const int key0 = j * G_BN;
@@ -264,7 +275,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                     if (CHK && e >= ncols) break;
-                    const float dist = tc_dist(v[e]);
+                    const float dist = tc_q(v[e]);                       // distance / 4
                     const int col = key0 + 32 * qt + e;
                     if (MODE == GM_NEAREST) {
                         if (dist < best) { best = dist; besti = col; }
@@ -274,17 +285,28 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                     } else if (MODE == GM_HIST) {
                         // bin = floor((dist - lo) * scale); one unsigned compare covers 0 <= bin < 256; the
                         // update is a single predicated shared-memory atomic (no divergent region)
-                        const int bin = __float2int_rd((dist - win_lo) * hscale);
-                        const uint32_t inc = (bin & 1) ? 65536u : 1u;
-                        if ((uint32_t)bin < (uint32_t)HIST_BINS) atomicAdd(hist + (bin >> 1), inc);
+                        // Every element updates the histogram: the ones outside the window go to bin 256, the spare word
+                        // at the end of the row's histogram.  (A conditional update compiles to a BSSY / BRA / BSYNC region per
+                        // element, and the C++ atomicAdd on a generic pointer to a generic ATOM: 19.5 instructions per element.)
+                        // bin = floor((dist - lo) * scale) through a round-down FMA onto 2^23 (FMA pipe; F2I is an 8-cycle XU
+                        // instruction): the low mantissa bits of floor(y) + 2^23 are floor(y) for 0 <= y < 2^22, and anything
+                        // below the window wraps to a huge unsigned value, i.e. to the spare bin as well
+                        const float biased = __fmaf_rd(dist - win_lo, hscale4, 8388608.0f);
+                        const uint32_t ub = __float_as_uint(biased) - 0x4b000000u;
+                        const uint32_t sh = (ub & 1u) << 4;
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, 256;\n\t@p red.shared.add.u32 [%1], %2;\n\t}"
+                                     :: "r"(ub), "r"(hist_s + ((ub >> 1) << 2)), "r"(1u << sh) : "memory");
                     } else if (MODE == GM_COLLECT) {
-                        below += dist < win_lo ? 1 : 0;
-                        if (dist >= win_lo && dist <= win_hi) {
+                        // q >= 0, so its bit pattern orders like the value: two integer compares instead of three NaN-aware
+                        // float compares on the (half-rate) ALU pipe
+                        const uint32_t qb = __float_as_uint(dist);
+                        below += qb < lo_bits ? 1 : 0;
+                        if (qb - lo_bits <= win_bits) {
                             if (ncand < CAND_Q) cand[ncand] = (uint16_t)col;
                             ++ncand;
                         }
                     } else if (row_ok) {
-                        a.dump[grow * N + col] = dist;
+                        a.dump[grow * N + col] = 4.0f * dist;
                     }
                 }
             };
@@ -320,7 +342,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                     cum += c0 + c1;
                 }
                 if (!found) before = max(0, krem - 1);          // cannot happen (bins partition the window)
-                const float lo_new = win_lo + (float)bin / hscale;   // exact: multiples of 2^-6 / 2^-14 below 4
+                const float lo_new = 4.0f * win_lo + (float)bin / hscale;   // distance units; exact: multiples of 2^-6 / 2^-14 below 4
                 a.rowinfo[grow] = make_int2(__float_as_int(lo_new), krem - before);
             }
         } else if (MODE == GM_COLLECT) {
@@ -419,7 +441,9 @@ template <int MODE>
 int launch_gram(const CUtensorMap& map, const GramArgs& a, cudaStream_t st) {
     PF_CUDA(cudaFuncSetAttribute(gram_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GCfg<MODE>::smem));
     dim3 grid((a.N + G_BM - 1) / G_BM, a.B);
-    gram_tc_kernel<MODE><<<grid, G_THREADS, GCfg<MODE>::smem, st>>>(map, a);
+    GramArgs aa = a;
+    if (const char* e = getenv("PRIFIT_GRAM_DEBUG")) aa.dbg = atoi(e);
+    gram_tc_kernel<MODE><<<grid, G_THREADS, GCfg<MODE>::smem, st>>>(map, aa);
     PF_LAUNCH_CHECK();
     return 0;
 }
