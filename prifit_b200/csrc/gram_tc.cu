@@ -70,7 +70,7 @@ template <int MODE> struct GCfg {
         MODE == GM_NEAREST ? (size_t)3 * G_BM * 8
       : MODE == GM_BEST ? (size_t)3 * G_BM * 8 + 2 * G_BN * sizeof(float)
       : MODE == GM_HIST ? (size_t)G_BM * HIST_WORDS * 4
-      : MODE == GM_COLLECT ? (size_t)G_EPI * CAND_Q * 2 + 16 * 4 * CAND_Q * sizeof(float) + 2 * G_EPI * sizeof(int)
+      : MODE == GM_COLLECT ? (size_t)G_EPI * CAND_Q * 2 + 16 * 16 * CAND_Q * sizeof(float) + 2 * G_EPI * sizeof(int)
       : 16;
     static constexpr size_t smem = 1024 + (size_t)G_STAGES * G_STAGE_BYTES + 256 + scratch;
 };
@@ -346,57 +346,75 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                 a.rowinfo[grow] = make_int2(__float_as_int(lo_new), krem - before);
             }
         } else if (MODE == GM_COLLECT) {
-            // exact fp32 recompute of the candidates, one warp per row (8 rows per epilogue warp)
-            float* vals = reinterpret_cast<float*>(scratch + (size_t)G_EPI * CAND_Q * 2) + ew * 4 * CAND_Q;
-            int* below_s = reinterpret_cast<int*>(scratch + (size_t)G_EPI * CAND_Q * 2 + 16 * 4 * CAND_Q * sizeof(float));
+            // exact fp32 recompute of the candidates: every epilogue warp owns 8 rows and works on 4 of them at a time,
+            // 8 lanes per row (lane l8 of a group owns dims 16 l8 .. 16 l8 + 15), 4 candidates per row in flight -- the
+            // global-load latency of the candidate rows is what this tail costs, so it is paid twice per warp, not 8 times
+            float* vals_w = reinterpret_cast<float*>(scratch + (size_t)G_EPI * CAND_Q * 2) + ew * 16 * CAND_Q;
+            int* below_s = reinterpret_cast<int*>(scratch + (size_t)G_EPI * CAND_Q * 2 + 16 * 16 * CAND_Q * sizeof(float));
             int* ncand_s = below_s + G_EPI;
             below_s[row * 4 + qt] = below;
             ncand_s[row * 4 + qt] = ncand;
             epi_barrier();
             const int k = max(1, min(a.kth[b], N));
             const uint16_t* call = reinterpret_cast<const uint16_t*>(scratch);
-            for (int rr = 0; rr < 8; ++rr) {
-                const int r = 8 * ew + rr;
-                if (r0 + r >= N) break;                                         // warp-uniform
-                int n4[4], nc = 0, bel = 0;
+            const int grp = lane >> 3, l8 = lane & 7;
+            float* vals = vals_w + grp * 4 * CAND_Q;
+            for (int rr = 0; rr < 2; ++rr) {
+                const int r = 8 * ew + 4 * rr + grp;
+                const bool in_range = r0 + r < N;
+                int n4[4] = {0, 0, 0, 0}, nc = 0, bel = 0;
                 bool over = false;
+                if (in_range) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    n4[q] = ncand_s[4 * r + q];
-                    over |= n4[q] > CAND_Q;
-                    nc += n4[q];
-                    bel += below_s[4 * r + q];
+                    for (int q = 0; q < 4; ++q) {
+                        n4[q] = ncand_s[4 * r + q];
+                        over |= n4[q] > CAND_Q;
+                        nc += n4[q];
+                        bel += below_s[4 * r + q];
+                    }
                 }
                 const int m = k - bel;                                          // m-th smallest candidate (1-based)
-                if (over || m < 1 || m > nc) {
-                    if (lane == 0) { atomicExch(a.overflow, 1); a.rowval[(size_t)b * N + r0 + r] = 0.f; }
-                    continue;
-                }
-                // the whole warp works on one candidate at a time: lane l owns dims 4l..4l+3, so every
-                // candidate row is one coalesced 512-byte request (4 candidates in flight per step)
-                const float4 xr = __ldg(reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + r0 + r) * G_D) + lane);
+                const bool bad = in_range && (over || m < 1 || m > nc);
+                if (bad && l8 == 0) { atomicExch(a.overflow, 1); a.rowval[(size_t)b * N + r0 + r] = 0.f; }
+                if (!in_range || bad) nc = 0;
+                float4 xr[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    xr[e] = nc > 0 ? __ldg(reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + r0 + r) * G_D) + 4 * l8 + e)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
                 auto cand_of = [&](int ci) -> int {
                     int q = 0;
                     while (q < 3 && ci >= n4[q]) { ci -= n4[q]; ++q; }
                     return call[(size_t)(4 * r + q) * CAND_Q + ci];
                 };
-                for (int c0 = 0; c0 < nc; c0 += 4) {
+                int ncmax = nc;                                                 // warp-uniform trip count
+#pragma unroll
+                for (int o = 8; o < 32; o <<= 1) ncmax = max(ncmax, __shfl_xor_sync(0xffffffffu, ncmax, o));
+                for (int c0 = 0; c0 < ncmax; c0 += 4) {
                     float acc[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int ci = min(c0 + u, nc - 1);
-                        const float4 w = __ldg(reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + cand_of(ci)) * G_D) + lane);
-                        acc[u] = fmaf(xr.x, w.x, fmaf(xr.y, w.y, fmaf(xr.z, w.z, xr.w * w.w)));
+                        acc[u] = 0.f;
+                        if (c0 < nc) {
+                            const float4* wrow = reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + cand_of(min(c0 + u, nc - 1))) * G_D) + 4 * l8;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float4 w = __ldg(wrow + e);
+                                acc[u] = fmaf(xr[e].x, w.x, fmaf(xr[e].y, w.y, fmaf(xr[e].z, w.z, fmaf(xr[e].w, w.w, acc[u]))));
+                            }
+                        }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
-                    if (lane < 4 && c0 + lane < nc)
-                        vals[c0 + lane] = 2.0f - 2.0f * (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]);
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int o = 4; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+                    if (l8 < 4 && c0 + l8 < nc)
+                        vals[c0 + l8] = 2.0f - 2.0f * (l8 == 0 ? acc[0] : l8 == 1 ? acc[1] : l8 == 2 ? acc[2] : acc[3]);
                 }
                 __syncwarp();
                 float found = 0.f;
                 bool have = false;
-                for (int ci = lane; ci < nc; ci += 32) {
+                for (int ci = l8; ci < nc; ci += 8) {
                     const float vi = vals[ci];
                     int rank = 0;
                     for (int cj = 0; cj < nc; ++cj) {
@@ -405,12 +423,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                     }
                     if (rank == m - 1) { found = vi; have = true; }
                 }
-                const unsigned ball = __ballot_sync(0xffffffffu, have);
-                if (ball) {
-                    const float res = __shfl_sync(0xffffffffu, found, __ffs(ball) - 1);
-                    if (lane == 0) a.rowval[(size_t)b * N + r0 + r] = sqrtf(fmaxf(res, 1e-6f));   // guard_sqrt(., 1e-6)
-                } else if (lane == 0) {
-                    atomicExch(a.overflow, 1);
+                const unsigned ball = (__ballot_sync(0xffffffffu, have) >> (8 * grp)) & 0xffu;
+                const float res = __shfl_sync(0xffffffffu, found, ball ? 8 * grp + __ffs(ball) - 1 : lane);   // every lane takes part
+                if (nc > 0 && l8 == 0) {
+                    if (ball) a.rowval[(size_t)b * N + r0 + r] = sqrtf(fmaxf(res, 1e-6f));           // guard_sqrt(., 1e-6)
+                    else atomicExch(a.overflow, 1);
                 }
                 __syncwarp();
             }
