@@ -161,6 +161,17 @@ int prifit_masked_mean_fwd(const float* loss_b, const uint8_t* valid, int B, int
 int prifit_masked_mean_bwd(const float* g_sum, const float* g_mean, const float* has, const float* stats, int B,
                            float* gloss_out, void* stream);
 
+/* f3 -- entropy regulariser.  convex_loss.py:209-225 (entropy) on the sub-sample of convex_loss.py:59-62.
+ *   X[B,N,d] unit rows (d = 64 or 128), idx[n] int32 = the sampled point indices (shared by all shapes, unique; NULL = all
+ *   N points), loss_b_out[B] = sum_ij (1 + <x_i, x_j>)^2 / n^2 over the sample, computed from the second moments
+ *   (n^2 + 2 |sum x|^2 + |sum x x^T|_F^2) -- the caller applies mean over shapes, margin 1.8 and relu.
+ *   The moments stay in `ws` for the backward call: gX_inout[b, idx[i], :] += gloss_b[b] * (4 / n^2) (m + M x_i). */
+size_t prifit_entropy_workspace_bytes(int B, int d);
+int prifit_entropy_fwd(const float* X, const int32_t* idx, int B, int N, int d, int n, float* loss_b_out,
+                       void* ws, size_t ws_bytes, void* stream);
+int prifit_entropy_bwd(const float* X, const int32_t* idx, const float* gloss_b, int B, int N, int d, int n,
+                       const void* ws, float* gX_inout, void* stream);
+
 /* diagnostics -- hardware self-test of the tcgen05 / TMA descriptor encodings the tensor-core engine
  *   uses: D[128,128] = A . B^T (mode 0: B K-major in shared memory) or A . B (mode 1: B MN-major), A staged
  *   in tensor memory, B fetched by TMA with SWIZZLE_128B; lbo/sbo = descriptor byte offsets under test.

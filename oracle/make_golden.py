@@ -190,9 +190,39 @@ def stage_case(ns):
                         membership=mem.numpy(), bw_sub=np.float64(bw_sub), perm=perm.astype(np.int32))
 
 
+def entropy_case(ns):
+    """Entropy regulariser (convex_loss.py:59-62,209-225) through the reference's own entropy(): one batch whose
+    embeddings are similar enough for the hinge to be active, one (random embeddings) where it is not."""
+    out = {}
+    for tag, sigma in (("active", 0.05), ("inactive", None)):
+        if sigma is None:
+            E, _ = synthetic.random_shapes(3, n_points=96, seed=41)
+        else:
+            E, _, _ = synthetic.planted_shapes(3, n_points=96, n_clusters=2, sigma=sigma, seed=40)
+        np.random.seed(9)
+        idx = np.random.choice(E.shape[1], E.shape[1] // 4, replace=False)          # convex_loss.py:61
+        for dt, name in ((torch.float32, "32"), (torch.float64, "64")):
+            Ei = E.to(dt).clone().requires_grad_(True)
+            X = torch.nn.functional.normalize(Ei, dim=2, p=2)
+            X = torch.nn.functional.normalize(X, dim=2, p=2)
+            loss = ns.convex_loss.entropy(X[:, idx])
+            loss.backward()
+            out["loss%s_%s" % (name, tag)] = np.float64(loss.detach())
+            out["grad%s_%s" % (name, tag)] = Ei.grad.numpy()
+            o = R.entropy_term(E.to(dt).clone().requires_grad_(True), idx)
+            print("[entropy %s fp%s] reference %.9g oracle %.9g" % (tag, name, float(loss), float(o)))
+        out["E_" + tag] = E.numpy()
+        out["idx_" + tag] = idx.astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, "entropy.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
+    if "--only-entropy" in sys.argv:          # added after the other fixtures were committed: leaves them untouched
+        entropy_case(ns)
+        return
+    entropy_case(ns)
     stage_case(ns)
     svd_backward_case(ns)
     fit_kat_case(ns)

@@ -14,6 +14,7 @@ runs, fp64 = the gradient acceptance oracle of SURVEY.md 0.9), the algorithm of
     src/fitting_utils.py:67-139               custom SVD backward
     convex_loss.py:37-41,57,313-343           double normalisation, approximate ellipsoid SDF
     src/utils.py:407-425                      SDF half of analytic_chamfer_distance
+    convex_loss.py:59-62,209-225              entropy regulariser on an N/4 sub-sample
 
 Pinning: the reference ships no tests or golden vectors.  ``oracle/make_golden.py``
 runs the unmodified reference (through ``oracle/ref_loader.py``) in the build container, checks
@@ -265,3 +266,19 @@ def fit_loss(E, P, quantile=0.05, iterations=10, max_num_clusters=25, noise=None
         loss.sum().backward()
         grad = E.grad.detach()
     return {"loss": loss.detach(), "grad_E": grad, "params": params, "labels": labels, "weights": weights}
+
+
+# ----------------------------------------------------------------------------- entropy regulariser
+def entropy(X):
+    """convex_loss.py:209-225: relu(mean_b sum_ij (1 + <x_i, x_j>)^2 / n^2 - 1.8) on X[B,n,d] (unit rows)."""
+    margin = 1.8
+    per_shape = []
+    for b in range(X.shape[0]):
+        D = (1 + X[b] @ X[b].T) ** 2
+        per_shape.append(torch.sum(D) / X.shape[1] ** 2)
+    return torch.relu(torch.stack(per_shape).mean() - margin)
+
+
+def entropy_term(E, sub_sample_indices):
+    """convex_loss.py:41,57,59-62: double normalisation, sub-sample of the points, entropy()."""
+    return entropy(normalize_twice(E)[:, sub_sample_indices])

@@ -6,9 +6,10 @@
 Scope: the fitting loss computed here is the analytic SDF half of
 `analytic_chamfer_distance` (src/utils.py:407-411,418,425) evaluated on `chamfer_points`.  The other
 half needs trimesh surface sampling + an sklearn KD-tree on the CPU (src/utils.py:413-416,
-src/sample_ellipsoid.py) and is a "next" row; the optional entropy / intersection / pruning terms
-are likewise out of scope and raise if requested.
+src/sample_ellipsoid.py) and is a "next" row; the entropy regulariser (include_entropy_loss, :59-62,
+:209-225) is built (csrc/entropy.cu); the intersection / pruning / cuboid terms are out of scope and raise.
 """
+import numpy as np
 import torch
 
 from . import ops, pipeline
@@ -23,21 +24,37 @@ def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, 
 
     Same signature, defaults and return structure as the reference.  `params` is a lazy sequence of
     per-shape lists of (s, V, center); `labels` a list of int64 [N] tensors."""
-    if include_intersect_loss or include_pruning or include_entropy_loss or if_cuboid:
-        raise NotImplementedError("intersection / pruning / entropy / cuboid terms are outside the accelerated path")
+    if include_intersect_loss or include_pruning or if_cuboid:
+        raise NotImplementedError("intersection / pruning / cuboid terms are outside the accelerated path")
     # channel-last views (reference :37,38,84); the pipeline copies them into its own row-major buffers, so the
     # transposition costs no separate pass
     E = X.permute(0, 2, 1)
     P = points.permute(0, 2, 1)
     Q = None if evaluation or chamfer_points is points else chamfer_points.permute(0, 2, 1)
+    entropy_loss = None
+    if include_entropy_loss:                                  # reference :59-62 (same host RNG call), entropy() :209-225
+        sub_sample_indices = np.random.choice(X.shape[2], X.shape[2] // 4, replace=False)
+        entropy_loss = entropy(ops.NormalizeTwice.apply(E.contiguous()), sub_sample_indices)      # reference :41,57
+    # the regulariser reaches X beside the fitting loss, so this case takes the eager autograd path
     out = pipeline.fit_loss(E, P, quantile=quantile, iterations=iterations, max_num_clusters=max_num_clusters,
-                            Q=Q, engine=meanshift.engine)
+                            Q=Q, engine=meanshift.engine, graph=False if include_entropy_loss else None)
     res = out["cluster"]
     params = ParamsBatch(out["s"], out["V"], out["c"], out["valid"], res.K, res.K_host)
     labels = list(res.labels.long().unbind(0))
     l = out["loss"] if not evaluation else torch.zeros(1, device=E.device, requires_grad=True)   # reference :92-94
-    total = l
+    total = l if entropy_loss is None else l + beta * entropy_loss       # reference :100 (intersection term not built)
     return total.view(1, 1), l.view(1, 1), params, labels
+
+
+def entropy(X, sub_sample_indices=None):
+    """Entropy regulariser, reference :209-225: X[B,n,d] unit rows -> relu(mean_b sum_ij (1 + <x_i,x_j>)^2 / n^2 - 1.8).
+    `sub_sample_indices` (not in the reference's signature) restricts the sum to those rows without materialising
+    X[:, idx] (reference :61-62 indexes first)."""
+    idx = None
+    if sub_sample_indices is not None:
+        idx = torch.as_tensor(np.asarray(sub_sample_indices), dtype=torch.int32).to(X.device)
+    l_b = ops.EntropyLoss.apply(X if X.is_contiguous() else X.contiguous(), idx)
+    return torch.relu(l_b.mean() - 1.8)
 
 
 def compute_sdf_ellipsoid(points, center, r, V):

@@ -412,3 +412,32 @@ class FitSdfMean(torch.autograd.Function):
             gc = gc + g_c
         gW, gP = fit_bwd(P, W, K, noise, fctx, valid, gs, gV, gc, ctx.needs_input_grad[0])
         return gP, gQ, gW, None, None
+
+
+# ------------------------------------------------------------------------------- entropy regulariser
+class EntropyLoss(torch.autograd.Function):
+    """convex_loss.py:209-225 per shape: X[B,N,d] (unit rows), idx int32[n] -> l_b[B] = sum_ij (1 + <x_i,x_j>)^2 / n^2
+    over the sampled points, from second moments (no n x n matrix).  mean / margin / relu are the caller's."""
+
+    @staticmethod
+    def forward(ctx, X, idx):
+        X = _chk(X)
+        B, N, d = X.shape
+        idx = None if idx is None else _chk(idx, torch.int32)
+        n = N if idx is None else idx.numel()
+        nbytes = _lib.load().prifit_entropy_workspace_bytes(B, d)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=X.device)
+        loss_b = torch.empty(B, dtype=torch.float32, device=X.device)
+        _lib.call("prifit_entropy_fwd", _ptr(X), _ptr(idx), B, N, d, n, _ptr(loss_b), _ptr(ws), nbytes, _stream())
+        ctx.save_for_backward(X, ws, *([] if idx is None else [idx]))
+        ctx.n = n
+        return loss_b
+
+    @staticmethod
+    def backward(ctx, gl):
+        X, ws = ctx.saved_tensors[:2]
+        idx = ctx.saved_tensors[2] if len(ctx.saved_tensors) > 2 else None
+        B, N, d = X.shape
+        gX = torch.zeros_like(X)
+        _lib.call("prifit_entropy_bwd", _ptr(X), _ptr(idx), _ptr(gl.contiguous()), B, N, d, ctx.n, _ptr(ws), _ptr(gX), _stream())
+        return gX, None

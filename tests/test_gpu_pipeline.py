@@ -440,3 +440,36 @@ def test_channel_first_public_api_graph_vs_eager(cuda, monkeypatch):
     gE_cf = torch.empty_like(Xcf)
     _lib.call("prifit_normalize_bwd_cf", ops._ptr(Xcf), ops._ptr(gX), B, N, d, ops._ptr(gE_cf), ops._stream())
     assert float((gE_cf.permute(0, 2, 1) - gE_cl).abs().max()) <= 1e-6 * float(gE_cl.abs().max())
+
+
+def test_convex_loss_with_entropy_term(cuda):
+    """include_entropy_loss (reference convex_loss.py:59-62,100): total = l + beta * entropy on an N/4 sub-sample drawn
+    with the same np.random.choice call; checked against the oracle (fit loss + entropy_term), loss and X.grad."""
+    import prifit_b200.convex_loss as cl
+    from oracle import restatement as R
+    from prifit_b200 import synthetic
+
+    E, P, _ = synthetic.planted_shapes(2, n_points=512, n_clusters=2, sigma=0.02, seed=50)   # 2 tight modes: hinge active
+    Xcf = E.permute(0, 2, 1).contiguous().to(cuda).requires_grad_(True)
+    Pcf = P.permute(0, 2, 1).contiguous().to(cuda)
+    np.random.seed(12)
+    torch.manual_seed(12)
+    total, l, params, labels = cl.convex_loss(Pcf, Pcf, Xcf, quantile=0.05, iterations=6, max_num_clusters=25,
+                                              include_entropy_loss=True, beta=0.7)
+    total.backward()
+    np.random.seed(12)
+    idx = np.random.choice(512, 128, replace=False)
+    E64 = E.double().requires_grad_(True)
+    ent = R.entropy_term(E64, idx)
+    assert float(ent) > 0.1
+    assert abs(float(total) - float(l) - 0.7 * float(ent)) <= 1e-5 * float(total)
+    # gradient of the entropy part alone = total gradient minus the fitting-loss gradient (same noise draws)
+    X2 = E.permute(0, 2, 1).contiguous().to(cuda).requires_grad_(True)
+    np.random.seed(12)
+    torch.manual_seed(12)
+    t2, l2, _, _ = cl.convex_loss(Pcf, Pcf, X2, quantile=0.05, iterations=6, max_num_clusters=25)
+    t2.backward()
+    assert abs(float(l2) - float(l)) <= 1e-6 * float(l)
+    (0.7 * ent).backward()
+    got = (Xcf.grad - X2.grad).permute(0, 2, 1).cpu().double()
+    assert float((got - E64.grad).abs().max()) <= 1e-4 * float(E64.grad.abs().max())

@@ -543,3 +543,43 @@ def test_tensor_core_gram_error_is_far_inside_the_candidate_margin(cuda, n):
     ref = (2.0 - 2.0 * Xd @ Xd.transpose(1, 2)).clamp(min=0.0)
     err = float((dist.cpu().double() - ref).abs().max())
     assert err < 2.5e-6, err
+
+
+@pytest.mark.parametrize("tag", ["active", "inactive"])
+def test_entropy_kernels_against_reference_fixture(cuda, golden_dir, tag):
+    """Moment-form entropy kernels (no n x n matrix) vs the reference's convex_loss.entropy: loss 1e-5, gradient 1e-4."""
+    from prifit_b200 import convex_loss as cl, ops
+
+    g = np.load(os.path.join(golden_dir, "entropy.npz"))
+    E = torch.from_numpy(g["E_" + tag]).to(cuda).requires_grad_(True)
+    X = ops.NormalizeTwice.apply(E)
+    loss = cl.entropy(X, g["idx_" + tag])
+    loss.backward()
+    ref = float(g["loss64_" + tag])
+    assert abs(float(loss) - ref) <= 1e-5 * max(1.0, ref)
+    scale = float(np.abs(g["grad64_active"]).max())
+    assert float(np.abs(E.grad.cpu().numpy() - g["grad64_" + tag]).max()) <= 1e-4 * scale
+
+
+@pytest.mark.parametrize("n_pts,d,frac", [(2048, 128, 4), (300, 128, 1), (500, 64, 3)])
+def test_entropy_kernels_vs_oracle(cuda, n_pts, d, frac):
+    """Full-size sub-sample (N/4 of 2048), all points, and d = 64, against the dense oracle in fp64."""
+    from oracle import restatement as R
+    from prifit_b200 import ops
+
+    gen = torch.Generator().manual_seed(n_pts)
+    base = torch.nn.functional.normalize(torch.randn(3, 1, d, generator=gen), dim=2)
+    E = base + 0.03 * torch.randn(3, n_pts, d, generator=gen)            # similar rows: hinge active
+    idx = None if frac == 1 else np.random.RandomState(1).choice(n_pts, n_pts // frac, replace=False)
+    Ec = E.to(cuda).requires_grad_(True)
+    X = ops.NormalizeTwice.apply(Ec)
+    l_b = ops.EntropyLoss.apply(X, None if idx is None else torch.from_numpy(idx.astype(np.int32)).to(cuda))
+    loss = torch.relu(l_b.mean() - 1.8)
+    loss.backward()
+    E64 = E.double().requires_grad_(True)
+    ref = R.entropy_term(E64, slice(None) if idx is None else idx)
+    ref.backward()
+    assert float(ref) > 0.05
+    assert abs(float(loss) - float(ref)) <= 1e-5 * float(ref) + 1e-6
+    scale = float(E64.grad.abs().max())
+    assert float((Ec.grad.cpu().double() - E64.grad).abs().max()) <= 1e-4 * scale

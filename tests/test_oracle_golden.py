@@ -104,3 +104,18 @@ def test_oracle_fp64_matches_reference_fp64(golden_dir):
     out = _fit_loss_matched(g, E, P, g["labels64"])
     assert rel_err(out["loss"], g["loss64"]) < 1e-10
     assert rel_err(out["grad_E"], g["grad64"]) < 1e-7
+
+
+@pytest.mark.parametrize("tag", ["active", "inactive"])
+def test_entropy_regulariser_against_reference(golden_dir, tag):
+    """oracle.entropy_term vs the reference's convex_loss.entropy (hinge active / inactive), fp32 and fp64."""
+    g = _load(golden_dir, "entropy")
+    idx = g["idx_" + tag]
+    for dt, name, tol in ((torch.float32, "32", 1e-6), (torch.float64, "64", 1e-12)):
+        E = torch.from_numpy(g["E_" + tag]).to(dt).requires_grad_(True)
+        loss = R.entropy_term(E, idx)
+        loss.backward()
+        assert abs(float(loss) - float(g["loss%s_%s" % (name, tag)])) <= tol * max(1.0, float(g["loss%s_%s" % (name, tag)]))
+        scale = max(float(np.abs(g["grad64_" + tag]).max()), 1e-30)
+        assert float(np.abs(E.grad.numpy() - g["grad%s_%s" % (name, tag)]).max()) <= max(tol * 10 * scale, 0.0)
+    assert (float(g["loss64_active"]) > 0.1) and float(g["loss64_inactive"]) == 0.0
