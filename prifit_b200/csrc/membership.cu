@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(RG_THREADS) membership_sim_kernel(
     rg_load_rows<D>(xs, RG_KEYS, X + (size_t)b * N * D, [&](int r) -> long long { return j0 + r < N ? (long long)(j0 + r) : -1; });
     __syncthreads();
     float acc[4][4];
-    rg_dot_32x128<D>(ys, xs, acc);
+    rg_dot_32x128<D>(ys, xs, acc, nrows);
     float mx = -INFINITY;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(RG_THREADS) membership_bwd_kernel(
             }
             __syncthreads();
             float acc[4][4];
-            rg_dot_32x128<D>(ys, xs, acc);
+            rg_dot_32x128<D>(ys, xs, acc, nrows);
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const int r = ty + 8 * a;
@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(RG_THREADS) membership_bwd_kernel(
                 }
             }
             __syncthreads();
-            rg_accum_rows<D>(ps, xs, o);
-            rg_accum_keys<D, false>(ps, ys, nullptr, nullptr, gXb + (size_t)j0 * D, min(RG_KEYS, jend - j0));
+            rg_accum_rows<D>(ps, xs, o, nrows);
+            rg_accum_keys<D, false>(ps, ys, nullptr, nullptr, gXb + (size_t)j0 * D, min(RG_KEYS, jend - j0), nrows);
         }
 #pragma unroll
         for (int a = 0; a < 4; ++a)

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(RG_THREADS) nms_label_kernel(
         rg_load_rows<D>(ys, RG_ROWS, Xb, [&](int r) -> long long { return k0 + r < Kb ? (long long)idx_b[k0 + r] : -1; });
         __syncthreads();
         float acc[4][4];
-        rg_dot_32x128<D>(ys, xs, acc);
+        rg_dot_32x128<D>(ys, xs, acc, min(RG_ROWS, Kb - k0));
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int k = k0 + ty + 8 * a;

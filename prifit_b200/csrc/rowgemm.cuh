@@ -29,31 +29,36 @@ __device__ __forceinline__ void rg_load_rows(float* dst, int nrows, const float*
     }
 }
 
-// acc[a][c] = <ys[ty + 8a], xs[tx + 32c]>
+// acc[a][c] = <ys[ty + 8a], xs[tx + 32c]>.  `nrows` = live rows of the rows tile (rows >= nrows are zero): row group a
+// (rows 8a .. 8a + 7) is skipped when it holds no live row -- with K = 16 clusters in a 32-row tile that halves the work.
 template <int D>
-__device__ __forceinline__ void rg_dot_32x128(const float* __restrict__ ys, const float* __restrict__ xs, float (&acc)[4][4]) {
+__device__ __forceinline__ void rg_dot_32x128(const float* __restrict__ ys, const float* __restrict__ xs, float (&acc)[4][4],
+                                              int nrows = RG_ROWS) {
     constexpr int LD = D + 4;
     const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+    const int na = (nrows + 7) >> 3;                  // live row groups (uniform over the CTA)
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
 #pragma unroll 4
     for (int i = 0; i < D; i += 4) {
-        float4 y[4], x[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) y[a] = *reinterpret_cast<const float4*>(ys + (ty + 8 * a) * LD + i);
+        float4 x[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) x[c] = *reinterpret_cast<const float4*>(xs + (tx + 32 * c) * LD + i);
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a) {
+            if (a < na) {
+                const float4 y = *reinterpret_cast<const float4*>(ys + (ty + 8 * a) * LD + i);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                acc[a][c] = fmaf(y[a].x, x[c].x, acc[a][c]);
-                acc[a][c] = fmaf(y[a].y, x[c].y, acc[a][c]);
-                acc[a][c] = fmaf(y[a].z, x[c].z, acc[a][c]);
-                acc[a][c] = fmaf(y[a].w, x[c].w, acc[a][c]);
+                for (int c = 0; c < 4; ++c) {
+                    acc[a][c] = fmaf(y.x, x[c].x, acc[a][c]);
+                    acc[a][c] = fmaf(y.y, x[c].y, acc[a][c]);
+                    acc[a][c] = fmaf(y.z, x[c].z, acc[a][c]);
+                    acc[a][c] = fmaf(y.w, x[c].w, acc[a][c]);
+                }
             }
+        }
     }
 }
 
@@ -93,17 +98,19 @@ __device__ __forceinline__ void rg_dot2_32x128(const float* __restrict__ y1s, co
     }
 }
 
-// o[a][4h+q] += sum_key ps[ty + 8a][key] * xs[key][4 tx + 128 h + q]   (32 x D += [32 x 128] . [128 x D])
+// o[a][4h+q] += sum_key ps[ty + 8a][key] * xs[key][4 tx + 128 h + q]   (32 x D += [32 x 128] . [128 x D]); row groups
+// without a live row (see rg_dot_32x128) are skipped
 template <int D>
 __device__ __forceinline__ void rg_accum_rows(const float* __restrict__ ps, const float* __restrict__ xs,
-                                              float (&o)[4][4 * ((D + 127) / 128)]) {
+                                              float (&o)[4][4 * ((D + 127) / 128)], int nrows = RG_ROWS) {
     constexpr int LD = D + 4;
     constexpr int NH = (D + 127) / 128;
     const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+    const int na = (nrows + 7) >> 3;
     for (int c0 = 0; c0 < RG_KEYS; c0 += 4) {
         float4 p[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) p[a] = *reinterpret_cast<const float4*>(ps + (ty + 8 * a) * RG_LDP + c0);
+        for (int a = 0; a < 4; ++a) p[a] = a < na ? *reinterpret_cast<const float4*>(ps + (ty + 8 * a) * RG_LDP + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
 #pragma unroll
@@ -112,11 +119,13 @@ __device__ __forceinline__ void rg_accum_rows(const float* __restrict__ ps, cons
                     const float4 x = *reinterpret_cast<const float4*>(xs + (c0 + cc) * LD + 4 * tx + 128 * h);
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        const float pv = cc == 0 ? p[a].x : cc == 1 ? p[a].y : cc == 2 ? p[a].z : p[a].w;
-                        o[a][4 * h + 0] = fmaf(pv, x.x, o[a][4 * h + 0]);
-                        o[a][4 * h + 1] = fmaf(pv, x.y, o[a][4 * h + 1]);
-                        o[a][4 * h + 2] = fmaf(pv, x.z, o[a][4 * h + 2]);
-                        o[a][4 * h + 3] = fmaf(pv, x.w, o[a][4 * h + 3]);
+                        if (a < na) {
+                            const float pv = cc == 0 ? p[a].x : cc == 1 ? p[a].y : cc == 2 ? p[a].z : p[a].w;
+                            o[a][4 * h + 0] = fmaf(pv, x.x, o[a][4 * h + 0]);
+                            o[a][4 * h + 1] = fmaf(pv, x.y, o[a][4 * h + 1]);
+                            o[a][4 * h + 2] = fmaf(pv, x.z, o[a][4 * h + 2]);
+                            o[a][4 * h + 3] = fmaf(pv, x.w, o[a][4 * h + 3]);
+                        }
                     }
                 }
             }
@@ -131,7 +140,7 @@ __device__ __forceinline__ void rg_accum_rows(const float* __restrict__ ps, cons
 template <int D, bool TWO>
 __device__ __forceinline__ void rg_accum_keys(const float* __restrict__ p1, const float* __restrict__ y1,
                                               const float* __restrict__ p2, const float* __restrict__ y2,
-                                              float* __restrict__ gX_tile /* &gX[key0][0] */, int nvalid) {
+                                              float* __restrict__ gX_tile /* &gX[key0][0] */, int nvalid, int nrows = RG_ROWS) {
     constexpr int LD = D + 4;
     constexpr int NH = D / 64;
     static_assert(D % 64 == 0, "D must be a multiple of 64");
@@ -141,7 +150,7 @@ __device__ __forceinline__ void rg_accum_keys(const float* __restrict__ p1, cons
     for (int k = 0; k < 8; ++k)
 #pragma unroll
         for (int c = 0; c < 4 * NH; ++c) acc[k][c] = 0.f;
-    for (int r = 0; r < RG_ROWS; ++r) {
+    for (int r = 0; r < nrows; ++r) {                  // rows >= nrows carry zero coefficients
         const float4 pa = *reinterpret_cast<const float4*>(p1 + r * RG_LDP + 8 * tj);
         const float4 pb = *reinterpret_cast<const float4*>(p1 + r * RG_LDP + 8 * tj + 4);
         const float pk[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
