@@ -200,19 +200,14 @@ def run_ours(args):
         torch.cuda.current_stream().wait_event(ev)
         X.record_stream(torch.cuda.current_stream()); pts.record_stream(torch.cuda.current_stream())
         X = X.requires_grad_(True)
-        total, l, params, labels = cl.convex_loss(pts, pts, X, quantile=q, iterations=T, max_num_clusters=kmax)
+        total, l, params, labels = cl.convex_loss(pts, pts, X, quantile=q, iterations=T, max_num_clusters=kmax,
+                                                  dist_reduce=world > 1)
         # prefetch the next step's inputs once this step's own small host->device copy (the staged noise draws) is
         # through: the H2D copy engine serves one queue, and 25 MB in front of it would stall the step by ~0.2 ms
         if not last_step:
             stage_inputs(i + 1)
-        if world > 1:
-            valid = params.padded[3]
-            n_local = (valid.sum(1) > 0).float().sum()
-            L, Lb = pdist.global_mean_from_local(total, n_local)
-            Lb.backward()
-        else:
-            L = total
-            total.backward()
+        L = l                                       # global mean (one 8-byte all-reduce inside convex_loss when N > 1)
+        total.backward()
         drain_loss()                                # the previous step's result, read while this one runs
         slot = i & 1
         loss_host[slot:slot + 1].copy_(L.detach().reshape(1), non_blocking=True)

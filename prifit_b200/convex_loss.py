@@ -19,11 +19,16 @@ from .ellipsoid_utils import meanshift
 
 def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, quantile=0.01, iterations=5,
                 visualize=False, max_num_clusters=25, class_list=[], include_intersect_loss=False, alpha=1, beta=1,
-                if_cuboid=False, include_pruning=False, include_entropy_loss=False, evaluation=False):
+                if_cuboid=False, include_pruning=False, include_entropy_loss=False, evaluation=False, dist_reduce=False):
     """points[B,3,N], chamfer_points[B,3,M], X[B,128,N] -> (total[1,1], l[1,1], params, labels).
 
     Same signature, defaults and return structure as the reference.  `params` is a lazy sequence of
-    per-shape lists of (s, V, center); `labels` a list of int64 [N] tensors."""
+    per-shape lists of (s, V, center); `labels` a list of int64 [N] tensors.
+
+    dist_reduce (extension, one process per GPU): the batch mean runs over the shapes of every rank (one 8-byte
+    all-reduce, train_partseg_shapenet.py:445 takes the mean of the replica losses); `total` is then this rank's share
+    sum_local / n_global -- calling backward() on it on every rank gives the gradient of the global mean -- and `l` the
+    global mean itself."""
     if include_intersect_loss or include_pruning or if_cuboid:
         raise NotImplementedError("intersection / pruning / cuboid terms are outside the accelerated path")
     # channel-last views (reference :37,38,84); the pipeline copies them into its own row-major buffers, so the
@@ -37,12 +42,17 @@ def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, 
         entropy_loss = entropy(ops.NormalizeTwice.apply(E.contiguous()), sub_sample_indices)      # reference :41,57
     # the regulariser reaches X beside the fitting loss, so this case takes the eager autograd path
     out = pipeline.fit_loss(E, P, quantile=quantile, iterations=iterations, max_num_clusters=max_num_clusters,
-                            Q=Q, engine=meanshift.engine, graph=False if include_entropy_loss else None)
+                            Q=Q, engine=meanshift.engine, graph=False if include_entropy_loss else None,
+                            dist_reduce=dist_reduce)
     res = out["cluster"]
     params = ParamsBatch(out["s"], out["V"], out["c"], out["valid"], res.K, res.K_host)
     labels = list(res.labels.long().unbind(0))
     l = out["loss"] if not evaluation else torch.zeros(1, device=E.device, requires_grad=True)   # reference :92-94
-    total = l if entropy_loss is None else l + beta * entropy_loss       # reference :100 (intersection term not built)
+    total = l
+    if dist_reduce and not evaluation:
+        total, l = out["loss_backward"], out["loss_global"]
+    if entropy_loss is not None:
+        total = total + beta * entropy_loss                            # reference :100 (intersection term not built)
     return total.view(1, 1), l.view(1, 1), params, labels
 
 

@@ -373,12 +373,14 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
     loss_sum, loss = res["loss_sum"], res["loss"]
     if E.requires_grad and torch.is_grad_enabled():
         loss_sum, loss = _Attach.apply(src, step, res["serial"], loss_sum, loss)
-    extra = {}
-    if dist_reduce:                  # the multi-GPU mean, enqueued while the host still has slack (before the read-back)
-        from . import dist as pdist
-        extra["loss_global"], extra["loss_backward"] = pdist.global_loss({"loss": loss, "loss_sum": loss_sum, "n_valid": res["n_valid"]})
     if not step.finish_forward(res):
         return None
+    extra = {}
+    if dist_reduce:
+        # The multi-GPU mean.  After the guard decision on purpose: a rank that has to redo its step on the eager path
+        # reduces there, and every rank must issue exactly one collective per step.
+        from . import dist as pdist
+        extra["loss_global"], extra["loss_backward"] = pdist.global_loss({"loss": loss, "loss_sum": loss_sum, "n_valid": res["n_valid"]})
     cluster = pipeline.ClusterResult(bw=res["bw"], idx=res["idx"], K=res["K"], labels=res["labels"], K_host=res["K_host"],
                                      n_labels_host=res["n_labels_host"], passes=[1] * B, quantiles=[float(quantile)] * B,
                                      kcap=step.kcap, iterations=int(iterations))

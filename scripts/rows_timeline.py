@@ -42,7 +42,7 @@ def main():
     res = pipeline.cluster_batch(X, N, 0.05, 10, 25)
     gC = torch.randn(B, res.kcap, 128, device=dev)
     gX = torch.zeros_like(X)
-    os.environ["PRIFIT_ROWS_TIMELINE"] = "1"
+    os.environ["PRIFIT_ROWS_TIMELINE"] = os.environ.get("ROWS_DBG", "1")
     traj, stat, C = ops.rows_fwd(X, res.bw, res.idx, res.K, 10, res.kcap, 0)
     torch.cuda.synchronize()
     dump("forward")
