@@ -89,7 +89,7 @@ def check(rc, what):
 
 # kernels (and memset nodes) each entry point enqueues; bench.py reports the sum as `gpu_launches`
 LAUNCHES = {
-    "prifit_normalize_fwd": 1, "prifit_normalize_bwd": 1, "prifit_normalize_fwd_cf": 1, "prifit_normalize_bwd_cf": 1, "prifit_bandwidth_fwd": 6, "prifit_meanshift_fwd": 1,
+    "prifit_normalize_fwd": 1, "prifit_normalize_bwd": 1, "prifit_normalize_fwd_cf": 1, "prifit_normalize_bwd_cf": 1, "prifit_bandwidth_fwd": 6, "prifit_meanshift_fwd": 3,
     "prifit_nms_fwd": 10, "prifit_meanshift_rows_fwd": 2, "prifit_meanshift_rows_bwd": 2,
     "prifit_membership_fwd": 2, "prifit_membership_bwd": 1, "prifit_fit_fwd": 1, "prifit_fit_bwd": 1,
     "prifit_sdf_loss_fwd": 2, "prifit_sdf_loss_bwd": 1,

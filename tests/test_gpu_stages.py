@@ -107,10 +107,13 @@ def _tc_or_skip(fn):
         raise
 
 
+@pytest.mark.parametrize("units", ["0", "1"])
 @pytest.mark.parametrize("n", [320, 2048, 1000])
-def test_meanshift_tcgen05_vs_fp32(cuda, golden_dir, n):
+def test_meanshift_tcgen05_vs_fp32(cuda, golden_dir, n, units, monkeypatch):
     """TF32 tensor-core engine against the fp32 engine: TF32 rounding of the 128-term dot products,
-    amplified by 1/bw^2 in the exponent, bounds the seed error by ~1e-4 absolute."""
+    amplified by 1/bw^2 in the exponent, bounds the seed error by ~1e-4 absolute.
+    units = 1: the experimental work-unit kernel (dynamic (row tile, iteration) units, pipelined boundary)."""
+    monkeypatch.setenv("PRIFIT_MS_UNITS", units)
     from prifit_b200 import ops, synthetic
 
     if n == 320:
