@@ -161,6 +161,17 @@ int prifit_masked_mean_fwd(const float* loss_b, const uint8_t* valid, int B, int
 int prifit_masked_mean_bwd(const float* g_sum, const float* g_mean, const float* has, const float* stats, int B,
                            float* gloss_out, void* stream);
 
+/* f1 -- sampled-surface half of analytic_chamfer_distance.  src/utils.py:413-418 (KD-tree query on the host in the
+ *   reference): S[B,Smax,3] source points (nS[b] valid rows per shape, NULL = all), T[B,M,3] target cloud.
+ *   idx_out[B,Smax] = nearest target of every source point (lowest index on ties, -1 for padding),
+ *   loss_out[b] = mean_i |s_i - t_idx(i)|^2 (0 when nS[b] == 0).
+ *   Backward: gS_out[B,Smax,3] = 2 gloss[b] (s - t_idx) / nS[b]; gT_inout[B,M,3] optional accumulation of the opposite. */
+size_t prifit_nn_workspace_bytes(int B, int Smax);
+int prifit_nn_loss_fwd(const float* S, const int32_t* nS, const float* T, int B, int Smax, int M,
+                       int32_t* idx_out, float* loss_out, void* ws, size_t ws_bytes, void* stream);
+int prifit_nn_loss_bwd(const float* S, const int32_t* nS, const float* T, const int32_t* idx, const float* gloss,
+                       int B, int Smax, int M, float* gS_out, float* gT_inout, void* stream);
+
 /* f3 -- entropy regulariser.  convex_loss.py:209-225 (entropy) on the sub-sample of convex_loss.py:59-62.
  *   X[B,N,d] unit rows (d = 64 or 128), idx[n] int32 = the sampled point indices (shared by all shapes, unique; NULL = all
  *   N points), loss_b_out[B] = sum_ij (1 + <x_i, x_j>)^2 / n^2 over the sample, computed from the second moments

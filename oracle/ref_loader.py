@@ -72,4 +72,5 @@ def load():
     ns.ellipsoid_fitting = importlib.import_module("src.ellipsoid_fitting")
     ns.ellipsoid_utils = importlib.import_module("src.ellipsoid_utils")
     ns.convex_loss = importlib.import_module("convex_loss")
+    ns.utils = importlib.import_module("src.utils")
     return ns

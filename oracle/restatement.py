@@ -15,6 +15,7 @@ runs, fp64 = the gradient acceptance oracle of SURVEY.md 0.9), the algorithm of
     convex_loss.py:37-41,57,313-343           double normalisation, approximate ellipsoid SDF
     src/utils.py:407-425                      SDF half of analytic_chamfer_distance
     convex_loss.py:59-62,209-225              entropy regulariser on an N/4 sub-sample
+    src/utils.py:384-426                      analytic_chamfer_distance, both halves (KD-tree -> brute-force nearest neighbour)
 
 Pinning: the reference ships no tests or golden vectors.  ``oracle/make_golden.py``
 runs the unmodified reference (through ``oracle/ref_loader.py``) in the build container, checks
@@ -282,3 +283,24 @@ def entropy(X):
 def entropy_term(E, sub_sample_indices):
     """convex_loss.py:41,57,59-62: double normalisation, sub-sample of the points, entropy()."""
     return entropy(normalize_twice(E)[:, sub_sample_indices])
+
+
+# ----------------------------------------------------------------------------- full analytic chamfer distance
+def analytic_chamfer_distance(params_batch, source_points, target_points):
+    """src/utils.py:384-426.  params_batch: list (B) of lists of (r, V, c); source_points: list (B) of [S_b,3] tensors
+    (non-tensor entries skip the shape, :403-406); target_points[B,M,3].  The reference's KD-tree query (:413-414)
+    is restated as an exhaustive arg-min over squared distances (identical except at exact ties)."""
+    distances = []
+    for b in range(target_points.shape[0]):
+        if not torch.is_tensor(source_points[b]):
+            continue
+        sdf = torch.stack([compute_sdf_ellipsoid(target_points[b], c, r, V) for (r, V, c) in params_batch[b]], 1)
+        sdf_ts = torch.min(torch.abs(sdf), 1)[0] ** 2
+        with torch.no_grad():
+            d2 = ((source_points[b].detach()[:, None, :].double() - target_points[b].detach()[None, :, :].double()) ** 2).sum(-1)
+            idx = torch.argmin(d2, 1)
+        dist_st = torch.sum((source_points[b] - target_points[b][idx]) ** 2, 1)
+        distances.append((torch.mean(dist_st) + torch.mean(sdf_ts)) / 2.0)
+    if not distances:
+        return torch.zeros(1, dtype=target_points.dtype, requires_grad=True)
+    return torch.stack(distances).mean()

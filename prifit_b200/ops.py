@@ -441,3 +441,36 @@ class EntropyLoss(torch.autograd.Function):
         gX = torch.zeros_like(X)
         _lib.call("prifit_entropy_bwd", _ptr(X), _ptr(idx), _ptr(gl.contiguous()), B, N, d, ctx.n, _ptr(ws), _ptr(gX), _stream())
         return gX, None
+
+
+# ------------------------------------------------------- sampled-surface half of the analytic chamfer distance
+class NearestSqDist(torch.autograd.Function):
+    """src/utils.py:413-418: S[B,Smax,3] source points (nS[b] valid rows), T[B,M,3] targets ->
+    loss_b[B] = mean_i |s_i - nearest target|^2.  The neighbour search is a brute-force device kernel (the reference
+    copies both clouds to the host for a KD-tree).  Gradients flow to S and, when it requires grad, to T."""
+
+    @staticmethod
+    def forward(ctx, S, nS, T):
+        S, T = _chk(S), _chk(T)
+        B, Smax, _ = S.shape
+        M = T.shape[1]
+        nS = None if nS is None else _chk(nS, torch.int32)
+        nbytes = max(16, _lib.load().prifit_nn_workspace_bytes(B, Smax))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=S.device)
+        idx = torch.empty(B, Smax, dtype=torch.int32, device=S.device)
+        loss = torch.empty(B, dtype=torch.float32, device=S.device)
+        _lib.call("prifit_nn_loss_fwd", _ptr(S), _ptr(nS), _ptr(T), B, Smax, M, _ptr(idx), _ptr(loss), _ptr(ws), nbytes, _stream())
+        ctx.save_for_backward(S, T, idx, *([] if nS is None else [nS]))
+        ctx.mark_non_differentiable(idx)
+        return loss, idx
+
+    @staticmethod
+    def backward(ctx, gloss, _gidx):
+        S, T, idx = ctx.saved_tensors[:3]
+        nS = ctx.saved_tensors[3] if len(ctx.saved_tensors) > 3 else None
+        B, Smax, _ = S.shape
+        gS = torch.empty_like(S)
+        gT = torch.zeros_like(T) if ctx.needs_input_grad[2] else None
+        _lib.call("prifit_nn_loss_bwd", _ptr(S), _ptr(nS), _ptr(T), _ptr(idx), _ptr(gloss.contiguous()), B, Smax, T.shape[1],
+                  _ptr(gS), _ptr(gT), _stream())
+        return gS, None, gT

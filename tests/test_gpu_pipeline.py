@@ -473,3 +473,60 @@ def test_convex_loss_with_entropy_term(cuda):
     (0.7 * ent).backward()
     got = (Xcf.grad - X2.grad).permute(0, 2, 1).cpu().double()
     assert float((got - E64.grad).abs().max()) <= 1e-4 * float(E64.grad.abs().max())
+
+
+def test_analytic_chamfer_distance_device_vs_reference_fixture(cuda, golden_dir):
+    """prifit_b200.utils.analytic_chamfer_distance (SDF kernel + brute-force nearest-neighbour kernel) against the
+    reference's own function (KD-tree on the host): loss 1e-5, gradients w.r.t. the sampled points and the ellipsoid
+    parameters 1e-4, middle shape skipped."""
+    from prifit_b200 import utils as pu
+
+    g = _g(golden_dir, "chamfer")
+    B = g["target"].shape[0]
+    params = [[(torch.from_numpy(g["s_%d" % b][k]).to(cuda).requires_grad_(True),
+                torch.from_numpy(g["V_%d" % b][k]).to(cuda).requires_grad_(True),
+                torch.from_numpy(g["c_%d" % b][k]).to(cuda).requires_grad_(True)) for k in range(int(g["n_ell"][b]))]
+              for b in range(B)]
+    sources = [torch.from_numpy(g["src_%d" % b]).to(cuda).requires_grad_(True) if int(g["n_src"][b]) > 0 else None
+               for b in range(B)]
+    loss = pu.analytic_chamfer_distance(params, sources, torch.from_numpy(g["target"]).to(cuda))
+    loss.backward()
+    assert rel_err(loss, g["loss64"]) < 1e-5
+    for b in (0, 2):
+        assert rel_err(sources[b].grad, g["gS64_%d" % b]) < 1e-4
+        assert rel_err(torch.stack([p[0].grad for p in params[b]]), g["gs64_%d" % b]) < 1e-4
+        assert rel_err(torch.stack([p[2].grad for p in params[b]]), g["gc64_%d" % b]) < 1e-4
+        assert rel_err(torch.stack([p[1].grad for p in params[b]]), g["gV64_%d" % b]) < 1e-4
+    assert all(p[0].grad is None or float(p[0].grad.abs().max()) == 0.0 for p in params[1])     # skipped shape: no gradient
+    # no tensor source at all -> zeros(1) like the reference
+    z = pu.analytic_chamfer_distance(params, [None] * B, torch.from_numpy(g["target"]).to(cuda))
+    assert float(z) == 0.0 and z.requires_grad
+
+
+def test_nearest_neighbour_kernel_full_size(cuda):
+    """10000 sampled points against a 5000-point cloud per shape (the training sizes, src/utils.py:413): indices and loss
+    against an exhaustive float64 search; target gradients through the gather."""
+    from prifit_b200 import ops
+
+    gen = torch.Generator().manual_seed(4)
+    B, S, M = 2, 10000, 5000
+    src = (torch.rand(B, S, 3, generator=gen) * 2 - 1)
+    tgt = (torch.rand(B, M, 3, generator=gen) * 2 - 1)
+    nS = torch.tensor([S, 7321], dtype=torch.int32)
+    Sc, Tc = src.to(cuda).requires_grad_(True), tgt.to(cuda).requires_grad_(True)
+    loss, idx = ops.NearestSqDist.apply(Sc, nS.to(cuda), Tc)
+    (loss * torch.tensor([1.0, 2.0], device=cuda)).sum().backward()
+    for b in range(B):
+        n = int(nS[b])
+        d2 = ((src[b, :n, None, :].double() - tgt[b][None].double()) ** 2).sum(-1)
+        best = d2.min(1)[0]
+        got = d2[torch.arange(n), idx[b, :n].cpu().long()]
+        assert float((got - best).max()) <= 1e-6 * float(best.max())          # a nearest neighbour (ties / rounding aside)
+        assert abs(float(loss[b]) - float(best.mean())) <= 1e-5 * float(best.mean())
+        assert int(idx[b, n:].max() if n < S else -1) == -1
+        w = (1.0, 2.0)[b]
+        ref_gS = 2.0 * w * (src[b, :n] - tgt[b][idx[b, :n].cpu().long()]) / n
+        assert float((Sc.grad[b, :n].cpu() - ref_gS).abs().max()) <= 1e-6
+        assert float(Sc.grad[b, n:].abs().max() if n < S else 0.0) == 0.0
+        ref_gT = torch.zeros(M, 3).index_add_(0, idx[b, :n].cpu().long(), -ref_gS)
+        assert float((Tc.grad[b].cpu() - ref_gT).abs().max()) <= 1e-5

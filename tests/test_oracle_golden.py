@@ -119,3 +119,31 @@ def test_entropy_regulariser_against_reference(golden_dir, tag):
         scale = max(float(np.abs(g["grad64_" + tag]).max()), 1e-30)
         assert float(np.abs(E.grad.numpy() - g["grad%s_%s" % (name, tag)]).max()) <= max(tol * 10 * scale, 0.0)
     assert (float(g["loss64_active"]) > 0.1) and float(g["loss64_inactive"]) == 0.0
+
+
+def _chamfer_inputs(g, dtype):
+    B = g["target"].shape[0]
+    params = [[(torch.from_numpy(g["s_%d" % b][k]).to(dtype).requires_grad_(True),
+                torch.from_numpy(g["V_%d" % b][k]).to(dtype).requires_grad_(True),
+                torch.from_numpy(g["c_%d" % b][k]).to(dtype).requires_grad_(True)) for k in range(int(g["n_ell"][b]))]
+              for b in range(B)]
+    sources = [torch.from_numpy(g["src_%d" % b]).to(dtype).requires_grad_(True) if int(g["n_src"][b]) > 0 else None
+               for b in range(B)]
+    return params, sources, torch.from_numpy(g["target"]).to(dtype)
+
+
+def test_analytic_chamfer_distance_against_reference(golden_dir):
+    """oracle.analytic_chamfer_distance (exhaustive nearest neighbour) vs the reference's function (scikit-learn KD-tree),
+    one shape skipped, ragged source counts: loss and every gradient, fp32 and fp64."""
+    g = _load(golden_dir, "chamfer")
+    for dt, name, tol in ((torch.float32, "32", 1e-5), (torch.float64, "64", 1e-11)):
+        params, sources, target = _chamfer_inputs(g, dt)
+        loss = R.analytic_chamfer_distance(params, sources, target)
+        loss.backward()
+        assert rel_err(loss, g["loss" + name]) < tol
+        for b in (0, 2):
+            assert rel_err(sources[b].grad, g["gS%s_%d" % (name, b)]) < 10 * tol
+            assert rel_err(torch.stack([p[0].grad for p in params[b]]), g["gs%s_%d" % (name, b)]) < 100 * tol
+            assert rel_err(torch.stack([p[2].grad for p in params[b]]), g["gc%s_%d" % (name, b)]) < 100 * tol
+            assert rel_err(torch.stack([p[1].grad for p in params[b]]), g["gV%s_%d" % (name, b)]) < 100 * tol
+        assert sources[1] is None
