@@ -231,7 +231,8 @@ class GraphStep:
         for i, seq in enumerate(seqs):
             g = torch.cuda.CUDAGraph()
             before = _lib.launch_count()
-            with torch.cuda.graph(g):
+            # thread_local: another host thread (a data loader pinning memory, ...) may issue CUDA calls during the capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 seq()
             self.launches[i] = _lib.launch_count() - before
             self.graphs.append(g)
