@@ -36,6 +36,18 @@ def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, 
     E = X.permute(0, 2, 1)
     P = points.permute(0, 2, 1)
     Q = None if evaluation or chamfer_points is points else chamfer_points.permute(0, 2, 1)
+    if visualize:
+        # reference :68 -> src/ellipsoid_utils.py:48-54: one-hot arg-max memberships instead of the soft ones; the
+        # stage-by-stage route (clustering -> fit -> SDF loss) handles it, no gradient reaches X through one-hot weights
+        from .ellipsoid_fitting import weighted_ellipsoid_fitting_batch
+        from .ellipsoid_utils import clustering
+        Xn = ops.NormalizeTwice.apply(E.contiguous())
+        weights, labels = clustering(Xn, quantile=quantile, iterations=iterations, visualize=True,
+                                     max_num_clusters=max_num_clusters, num_samples=Xn.shape[1])
+        params = weighted_ellipsoid_fitting_batch(P.contiguous(), weights)
+        l = sdf_fitting_loss((P if Q is None else Q).contiguous(), params) if not evaluation else \
+            torch.zeros(1, device=E.device, requires_grad=True)
+        return l.view(1, 1), l.view(1, 1), params, labels
     entropy_loss = None
     if include_entropy_loss:                                  # reference :59-62 (same host RNG call), entropy() :209-225
         sub_sample_indices = np.random.choice(X.shape[2], X.shape[2] // 4, replace=False)

@@ -530,3 +530,25 @@ def test_nearest_neighbour_kernel_full_size(cuda):
         assert float(Sc.grad[b, n:].abs().max() if n < S else 0.0) == 0.0
         ref_gT = torch.zeros(M, 3).index_add_(0, idx[b, :n].cpu().long(), -ref_gS)
         assert float((Tc.grad[b].cpu() - ref_gT).abs().max()) <= 1e-5
+
+
+def test_convex_loss_visualize_uses_one_hot_memberships(cuda):
+    """visualize=True (reference convex_loss.py:68 -> src/ellipsoid_utils.py:48-54): the fit runs on one-hot arg-max
+    memberships; loss against the oracle's fit + SDF loss on the same one-hot weights."""
+    import prifit_b200.convex_loss as cl
+    from oracle import restatement as R
+    from prifit_b200 import synthetic
+
+    E, P, _ = synthetic.planted_shapes(2, n_points=512, n_clusters=4, sigma=0.02, seed=60)
+    Xcf = E.permute(0, 2, 1).contiguous().to(cuda)
+    Pcf = P.permute(0, 2, 1).contiguous().to(cuda)
+    torch.manual_seed(3)
+    total, l, params, labels = cl.convex_loss(Pcf, Pcf, Xcf, quantile=0.05, iterations=8, max_num_clusters=25, visualize=True)
+    # oracle: one-hot weights from the hard labels of our clustering (= arg-max of the soft memberships for converged modes)
+    K = [int(lb.max()) + 1 for lb in labels]
+    onehot = [torch.nn.functional.one_hot(lb.cpu().long(), k).double() for lb, k in zip(labels, K)]
+    torch.manual_seed(3)
+    ref_params = R.weighted_ellipsoid_fitting_batch(P.double(), onehot)
+    ref = R.sdf_loss(P.double(), ref_params)
+    assert [len(p) for p in params] == [len(p) for p in ref_params] == [4, 4]
+    assert abs(float(total) - float(ref)) <= 1e-4 * float(ref)
