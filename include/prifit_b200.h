@@ -85,6 +85,9 @@ int prifit_nms_fwd(const float* newX, const float* bw, int B, int N, int d, int 
 /* engines of the K-seed trajectory kernels */
 #define PRIFIT_ROWS_SPLIT_TCGEN05 0 /* tensor cores, split-fp16 (hi + lo) operands, 3 tcgen05.mma per product: fp32-class; d == 128 */
 #define PRIFIT_ROWS_FP32_SIMT     1 /* CUDA-core fp32 (cross-check; d in {64, 128, 256}) */
+/* flag OR-ed into `engine` of prifit_meanshift_rows_bwd: the workspace still holds the split fp16 rows of this X, left there
+ * by the prifit_meanshift_rows_fwd call with the same (X, B, N, ws) -- the backward then skips its own split pass */
+#define PRIFIT_ROWS_WS_HOLDS_SPLIT 0x100
 
 /* k2 rows -- fp32 trajectories of the K selected seeds (center = new_X[indices],
  *   src/mean_shift.py:46): traj_out[B, T+1, Kcap, d] (y^0..y^T), stat_out[B, T, Kcap, 2] =

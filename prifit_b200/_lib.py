@@ -58,6 +58,7 @@ MS_TF32_TCGEN05 = 0
 MS_FP32_SIMT = 1
 ROWS_SPLIT_TCGEN05 = 0
 ROWS_FP32_SIMT = 1
+ROWS_WS_HOLDS_SPLIT = 0x100
 
 _lib = None
 

@@ -957,10 +957,12 @@ int prifit_rows_tc_fwd(const float* X, const float* bw, const int32_t* idx, cons
 }
 
 int prifit_rows_tc_bwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K, const float* traj,
-                       const float* stat, const float* gC, int B, int N, int T, int Kcap, float* gX, void* ws, cudaStream_t st) {
+                       const float* stat, const float* gC, int B, int N, int T, int Kcap, float* gX, void* ws, bool ws_holds_split,
+                       cudaStream_t st) {
     __half* Xs = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
     CUtensorMap map;
-    int rc = prifit_tc_split_rows(X, Xs, B, N, &map, st);
+    // the forward call left the split rows of the same X in this workspace: only the tile map is rebuilt (host side)
+    int rc = ws_holds_split ? prifit_tc_make_tile_map(&map, Xs, 2 * B, N) : prifit_tc_split_rows(X, Xs, B, N, &map, st);
     if (rc) return rc;
     RowsArgs a = {};
     a.X = X; a.bw = bw; a.idx = idx; a.K = K; a.N = N; a.B = B; a.T = T; a.Kcap = Kcap;

@@ -65,6 +65,9 @@ class GraphStep:
         self.quantile, self.kmax = float(quantile), int(max_num_clusters)
         self.kcap = ops.kcap_for(max_num_clusters)
         self.engine, self.rows_engine = engine, rows_engine
+        # the rows workspace of a branch is touched by nothing but its K-seed forward and backward, and X is static: the
+        # backward reuses the split fp16 rows the forward left there
+        self.rows_bwd_engine = rows_engine | _lib.ROWS_WS_HOLDS_SPLIT if rows_engine == _lib.ROWS_SPLIT_TCGEN05 else rows_engine
         self.device = device
         self.serial = 0
         kth = int(self.quantile * N)                                  # src/mean_shift.py:155
@@ -204,7 +207,7 @@ class GraphStep:
             _lib.call("prifit_membership_bwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), _ptr(W), _ptr(self.smax[lo:hi]), _ptr(gW),
                       Bb, N, d, kcap, _ptr(gC), _ptr(gX), st)
             _lib.call("prifit_meanshift_rows_bwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), _ptr(self.traj[lo:hi]),
-                      _ptr(self.stat[lo:hi]), _ptr(gC), Bb, N, d, T, kcap, _ptr(gX), self.rows_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
+                      _ptr(self.stat[lo:hi]), _ptr(gC), Bb, N, d, T, kcap, _ptr(gX), self.rows_bwd_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
             if self.cf:
                 _lib.call("prifit_normalize_bwd_cf", _ptr(self.E[lo:hi]), _ptr(gX), Bb, N, d, _ptr(self.gE[lo:hi]), st)
             else:
