@@ -186,6 +186,21 @@ int prifit_entropy_fwd(const float* X, const int32_t* idx, int B, int N, int d, 
 int prifit_entropy_bwd(const float* X, const int32_t* idx, const float* gloss_b, int B, int N, int d, int n,
                        const void* ws, float* gX_inout, void* stream);
 
+/* f4 -- PointNet++ geometric operators (models/pointnet_util.py), index semantics of the reference (first index on ties).
+ *   prifit_fps            :63-84   xyz[B,N,3], start[B] int64 (the reference's torch.randint draw) -> idx_out[B,npoint] int64; N <= 16384
+ *   prifit_ball_query     :87-107  first nsample indices (ascending) with square_distance <= radius^2, padded with the first hit
+ *                                  (N when a query has none) -> idx_out[B,S,nsample] int64
+ *   prifit_three_nn       :287-293 three nearest xyz2 points of every xyz1 point and their normalised inverse-distance weights
+ *   prifit_interpolate_*  :294     out[B,N,D] = sum_k weight_k points2[idx_k]; backward accumulates into gpoints2_inout[B,S,D] */
+int prifit_fps(const float* xyz, const int64_t* start, int B, int N, int npoint, int64_t* idx_out, void* stream);
+int prifit_ball_query(const float* xyz, const float* new_xyz, int B, int N, int S, float radius, int nsample,
+                      int64_t* idx_out, void* stream);
+int prifit_three_nn(const float* xyz1, const float* xyz2, int B, int N, int S, int32_t* idx_out, float* weight_out, void* stream);
+int prifit_interpolate_fwd(const float* points2, const int32_t* idx, const float* weight, int B, int N, int S, int D,
+                           float* out, void* stream);
+int prifit_interpolate_bwd(const float* gout, const int32_t* idx, const float* weight, int B, int N, int S, int D,
+                           float* gpoints2_inout, void* stream);
+
 /* diagnostics -- hardware self-test of the tcgen05 / TMA descriptor encodings the tensor-core engine
  *   uses: D[128,128] = A . B^T (mode 0: B K-major in shared memory) or A . B (mode 1: B MN-major), A staged
  *   in tensor memory, B fetched by TMA with SWIZZLE_128B; lbo/sbo = descriptor byte offsets under test.

@@ -256,6 +256,42 @@ def chamfer_case(ns):
     np.savez_compressed(os.path.join(OUT, "chamfer.npz"), **out)
 
 
+def pointnet_case():
+    """models/pointnet_util.py (imported unmodified: torch + numpy only): farthest point sampling, ball query and the 3-NN
+    interpolation of PointNetFeaturePropagation on a seeded cloud."""
+    import importlib
+    sys.path.insert(0, ref_loader.REFERENCE_ROOT)
+    pu = importlib.import_module("models.pointnet_util")
+    torch.manual_seed(23)
+    B, N, npoint, nsample, D = 2, 384, 48, 16, 10
+    xyz = torch.rand(B, N, 3) * 2 - 1
+    torch.manual_seed(5)
+    start = torch.randint(0, N, (B,), dtype=torch.long)                # the draw farthest_point_sample makes at :74
+    torch.manual_seed(5)
+    fps = pu.farthest_point_sample(xyz, npoint)
+    assert torch.equal(fps[:, 0], start)
+    assert torch.equal(R.farthest_point_sample(xyz, npoint, start), fps)
+    new_xyz = pu.index_points(xyz, fps)
+    ball = pu.query_ball_point(0.35, nsample, xyz, new_xyz)
+    assert torch.equal(R.query_ball_point(0.35, nsample, xyz, new_xyz)[0], ball)
+    feats = torch.randn(B, npoint, D, requires_grad=True)
+    fp = pu.PointNetFeaturePropagation(D, [D])                          # only its interpolation is exercised
+    dists = pu.square_distance(xyz, new_xyz)
+    dists, idx = dists.sort(dim=-1)
+    dists, idx = dists[:, :, :3], idx[:, :, :3]
+    dist_recip = 1.0 / (dists + 1e-8)
+    weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
+    interp = torch.sum(pu.index_points(feats, idx) * weight.view(B, N, 3, 1), dim=2)     # :287-294 verbatim
+    gout = torch.randn(B, N, D)
+    (interp * gout).sum().backward()
+    o_int, o_idx, o_w = R.three_interpolate(xyz, new_xyz, feats.detach())
+    print("[pointnet] fps/ball identical; interpolation oracle-ref %.2e" % rel(o_int, interp.detach()))
+    np.savez_compressed(os.path.join(OUT, "pointnet.npz"), xyz=xyz.numpy(), start=start.numpy(), fps=fps.numpy(),
+                        ball=ball.numpy(), radius=np.float64(0.35), nsample=np.int32(nsample), feats=feats.detach().numpy(),
+                        nn_idx=idx.numpy(), nn_weight=weight.numpy(), interp=interp.detach().numpy(), gout=gout.numpy(),
+                        gfeats=feats.grad.numpy(), sqd_ball=pu.square_distance(new_xyz, xyz).numpy())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
@@ -265,8 +301,12 @@ def main():
     if "--only-chamfer" in sys.argv:
         chamfer_case(ns)
         return
+    if "--only-pointnet" in sys.argv:
+        pointnet_case()
+        return
     entropy_case(ns)
     chamfer_case(ns)
+    pointnet_case()
     stage_case(ns)
     svd_backward_case(ns)
     fit_kat_case(ns)

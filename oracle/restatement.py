@@ -16,6 +16,7 @@ runs, fp64 = the gradient acceptance oracle of SURVEY.md 0.9), the algorithm of
     src/utils.py:407-425                      SDF half of analytic_chamfer_distance
     convex_loss.py:59-62,209-225              entropy regulariser on an N/4 sub-sample
     src/utils.py:384-426                      analytic_chamfer_distance, both halves (KD-tree -> brute-force nearest neighbour)
+    models/pointnet_util.py:18-107,283-295    square_distance, farthest point sampling, ball query, 3-NN interpolation
 
 Pinning: the reference ships no tests or golden vectors.  ``oracle/make_golden.py``
 runs the unmodified reference (through ``oracle/ref_loader.py``) in the build container, checks
@@ -304,3 +305,59 @@ def analytic_chamfer_distance(params_batch, source_points, target_points):
     if not distances:
         return torch.zeros(1, dtype=target_points.dtype, requires_grad=True)
     return torch.stack(distances).mean()
+
+
+# ----------------------------------------------------------------------------- PointNet++ geometric operators
+def square_distance(src, dst):
+    """models/pointnet_util.py:18-41."""
+    B, N, _ = src.shape
+    _, M, _ = dst.shape
+    dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))
+    dist += torch.sum(src ** 2, -1).view(B, N, 1)
+    dist += torch.sum(dst ** 2, -1).view(B, 1, M)
+    return dist
+
+
+def farthest_point_sample(xyz, npoint, start):
+    """models/pointnet_util.py:63-84 with the torch.randint draw of :74 passed in as `start`[B]."""
+    B, N, _ = xyz.shape
+    centroids = torch.zeros(B, npoint, dtype=torch.long)
+    distance = torch.ones(B, N, dtype=xyz.dtype) * 1e10
+    farthest = start.clone()
+    batch = torch.arange(B)
+    for i in range(npoint):
+        centroids[:, i] = farthest
+        centroid = xyz[batch, farthest, :].view(B, 1, 3)
+        dist = torch.sum((xyz - centroid) ** 2, -1)
+        mask = dist < distance
+        distance[mask] = dist[mask]
+        farthest = torch.max(distance, -1)[1]
+    return centroids
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """models/pointnet_util.py:87-107."""
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    group_idx = torch.arange(N, dtype=torch.long).view(1, 1, N).repeat([B, S, 1])
+    sqrdists = square_distance(new_xyz, xyz)
+    group_idx[sqrdists > radius ** 2] = N
+    group_idx = group_idx.sort(dim=-1)[0][:, :, :nsample]
+    group_first = group_idx[:, :, 0].view(B, S, 1).repeat([1, 1, nsample])
+    mask = group_idx == N
+    group_idx[mask] = group_first[mask]
+    return group_idx, sqrdists
+
+
+def three_interpolate(xyz1, xyz2, points2):
+    """models/pointnet_util.py:287-294 (S > 1 branch): returns (interpolated [B,N,D], idx [B,N,3], weight [B,N,3])."""
+    B, N, _ = xyz1.shape
+    dists = square_distance(xyz1, xyz2)
+    dists, idx = dists.sort(dim=-1)
+    dists, idx = dists[:, :, :3], idx[:, :, :3]
+    dist_recip = 1.0 / (dists + 1e-8)
+    norm = torch.sum(dist_recip, dim=2, keepdim=True)
+    weight = dist_recip / norm
+    batch = torch.arange(B).view(B, 1, 1).repeat(1, N, 3)
+    interpolated = torch.sum(points2[batch, idx, :] * weight.view(B, N, 3, 1), dim=2)
+    return interpolated, idx, weight

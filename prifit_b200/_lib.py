@@ -49,6 +49,11 @@ SIGNATURES = {
     "prifit_entropy_workspace_bytes": (_sz, [_i, _i]),
     "prifit_entropy_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "prifit_entropy_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "prifit_fps": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "prifit_ball_query": (_i, [_p, _p, _i, _i, _i, ctypes.c_float, _i, _p, _p]),
+    "prifit_three_nn": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "prifit_interpolate_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "prifit_interpolate_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "prifit_debug_tc_probe": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "prifit_debug_tc_gram": (_i, [_p, _i, _i, _p, _p, _p]),
 }

@@ -36,5 +36,19 @@ def main():
     print("nearest fwd+bwd   %7.1f us" % timeit(lambda: ops.NearestSqDist.apply(S, None, T)[0].sum().backward()))
 
 
+def pointnet():
+    from prifit_b200 import pointnet_util as pu
+    dev = torch.device("cuda:0")
+    xyz = torch.rand(24, 2048, 3, device=dev) * 2 - 1
+    start = torch.zeros(24, dtype=torch.long)
+    print("fps 2048 -> 512   %7.1f us" % timeit(lambda: pu.farthest_point_sample(xyz, 512, start=start)))
+    new_xyz = pu.index_points(xyz, pu.farthest_point_sample(xyz, 512, start=start))
+    print("ball query r=0.2  %7.1f us" % timeit(lambda: pu.query_ball_point(0.2, 32, xyz, new_xyz)))
+    feats = torch.randn(24, 512, 128, device=dev, requires_grad=True)
+    print("3-NN interp fwd   %7.1f us" % timeit(lambda: pu.three_interpolate(xyz, new_xyz, feats)))
+    print("3-NN interp f+b   %7.1f us" % timeit(lambda: pu.three_interpolate(xyz, new_xyz, feats).sum().backward()))
+
+
 if __name__ == "__main__":
     main()
+    pointnet()

@@ -586,3 +586,62 @@ def test_entropy_kernels_vs_oracle(cuda, n_pts, d, frac):
     assert abs(float(loss) - float(ref)) <= 1e-5 * float(ref) + 1e-6
     scale = float(E64.grad.abs().max())
     assert float((Ec.grad.cpu().double() - E64.grad).abs().max()) <= 1e-4 * scale
+
+
+# ---------------------------------------------------------------------------- PointNet++ geometric operators (8f4)
+def test_pointnet_ops_against_reference_fixture(cuda, golden_dir):
+    """FPS, ball query, 3-NN interpolation kernels vs the outputs of the unmodified models/pointnet_util.py: indices
+    identical (ball query: except where a squared distance is within rounding of radius^2), values 1e-5."""
+    from prifit_b200 import pointnet_util as pu
+
+    g = np.load(os.path.join(golden_dir, "pointnet.npz"))
+    xyz = torch.from_numpy(g["xyz"]).to(cuda)
+    fps = pu.farthest_point_sample(xyz, g["fps"].shape[1], start=torch.from_numpy(g["start"]))
+    assert torch.equal(fps.cpu(), torch.from_numpy(g["fps"]))
+    new_xyz = pu.index_points(xyz, fps)
+    ball = pu.query_ball_point(float(g["radius"]), int(g["nsample"]), xyz, new_xyz).cpu()
+    ref_ball = torch.from_numpy(g["ball"])
+    r2 = float(g["radius"]) ** 2
+    near_edge = (np.abs(g["sqd_ball"] - r2) < 1e-5).any(-1)                    # queries with a point on the radius, numerically
+    rows_ok = (ball == ref_ball).all(-1).numpy()
+    assert (rows_ok | near_edge).all() and rows_ok.mean() > 0.98
+    feats = torch.from_numpy(g["feats"]).to(cuda).requires_grad_(True)
+    idx, w = pu.three_nn(xyz, new_xyz)
+    same = (idx.cpu().long() == torch.from_numpy(g["nn_idx"])).all(-1)
+    assert float(same.float().mean()) > 0.99                                    # exact-tie / rounding swaps aside
+    interp = pu.three_interpolate(xyz, new_xyz, feats)
+    (interp * torch.from_numpy(g["gout"]).to(cuda)).sum().backward()
+    assert float((interp.detach().cpu() - torch.from_numpy(g["interp"])).abs().max()) <= 1e-4 * float(np.abs(g["interp"]).max())
+    assert float((feats.grad.cpu() - torch.from_numpy(g["gfeats"])).abs().max()) <= 1e-4 * float(np.abs(g["gfeats"]).max())
+
+
+def test_pointnet_ops_full_size_vs_oracle(cuda):
+    """Training sizes (24 clouds x 2048 points -> 512 centroids, radius 0.2 / 32 samples, D = 128 features)."""
+    from prifit_b200 import pointnet_util as pu
+
+    gen = torch.Generator().manual_seed(8)
+    B, N, S, D = 4, 2048, 512, 128
+    xyz = torch.rand(B, N, 3, generator=gen) * 2 - 1
+    start = torch.randint(0, N, (B,), generator=gen)
+    fps = pu.farthest_point_sample(xyz.to(cuda), S, start=start).cpu()
+    assert torch.equal(fps, R.farthest_point_sample(xyz, S, start))
+    new_xyz = xyz[torch.arange(B)[:, None], fps]
+    ball = pu.query_ball_point(0.2, 32, xyz.to(cuda), new_xyz.to(cuda)).cpu()
+    ref_ball, sqd = R.query_ball_point(0.2, 32, xyz, new_xyz)
+    near_edge = ((sqd - 0.04).abs() < 1e-5).any(-1)
+    rows_ok = (ball == ref_ball).all(-1)
+    assert bool((rows_ok | near_edge).all()) and float(rows_ok.float().mean()) > 0.98
+    feats = torch.randn(B, S, D, generator=gen)
+    fc = feats.to(cuda).requires_grad_(True)
+    out = pu.three_interpolate(xyz.to(cuda), new_xyz.to(cuda), fc)
+    gout = torch.randn(B, N, D, generator=gen)
+    (out * gout.to(cuda)).sum().backward()
+    fr = feats.clone().requires_grad_(True)
+    ref, _, _ = R.three_interpolate(xyz, new_xyz, fr)
+    (ref * gout).sum().backward()
+    bad = (out.detach().cpu() - ref.detach()).abs().amax(-1) > 1e-4 * float(ref.abs().max())
+    assert float(bad.float().mean()) < 0.005                                    # rows whose 3rd / 4th neighbour swap by rounding
+    assert float((fc.grad.cpu() - fr.grad).abs().max()) <= 2e-2 * float(fr.grad.abs().max())
+    # S == 1: the single feature row is repeated (reference :285-286)
+    one = pu.three_interpolate(xyz.to(cuda), new_xyz[:, :1].to(cuda), feats[:, :1].to(cuda))
+    assert torch.equal(one.cpu(), feats[:, :1].repeat(1, N, 1))

@@ -147,3 +147,20 @@ def test_analytic_chamfer_distance_against_reference(golden_dir):
             assert rel_err(torch.stack([p[2].grad for p in params[b]]), g["gc%s_%d" % (name, b)]) < 100 * tol
             assert rel_err(torch.stack([p[1].grad for p in params[b]]), g["gV%s_%d" % (name, b)]) < 100 * tol
         assert sources[1] is None
+
+
+def test_pointnet_geometric_ops_against_reference(golden_dir):
+    """oracle restatements of models/pointnet_util.py (FPS, ball query, 3-NN interpolation) vs the reference's outputs."""
+    g = _load(golden_dir, "pointnet")
+    xyz = torch.from_numpy(g["xyz"])
+    fps = R.farthest_point_sample(xyz, g["fps"].shape[1], torch.from_numpy(g["start"]))
+    assert torch.equal(fps, torch.from_numpy(g["fps"]))
+    new_xyz = xyz[torch.arange(xyz.shape[0])[:, None], fps]
+    ball, _ = R.query_ball_point(float(g["radius"]), int(g["nsample"]), xyz, new_xyz)
+    assert torch.equal(ball, torch.from_numpy(g["ball"]))
+    feats = torch.from_numpy(g["feats"]).requires_grad_(True)
+    interp, idx, w = R.three_interpolate(xyz, new_xyz, feats)
+    (interp * torch.from_numpy(g["gout"])).sum().backward()
+    assert torch.equal(idx, torch.from_numpy(g["nn_idx"]))
+    assert rel_err(w, g["nn_weight"]) < 1e-6 and rel_err(interp, g["interp"]) < 1e-6
+    assert rel_err(feats.grad, g["gfeats"]) < 1e-6
