@@ -175,6 +175,17 @@ int prifit_nn_loss_fwd(const float* S, const int32_t* nS, const float* T, int B,
 int prifit_nn_loss_bwd(const float* S, const int32_t* nS, const float* T, const int32_t* idx, const float* gloss,
                        int B, int Smax, int M, float* gS_out, float* gT_inout, void* stream);
 
+/* f2 -- surface sampling of the fitted ellipsoids.  src/ellipsoid_utils.py:76-130, src/sample_ellipsoid.py:17-63.
+ *   prifit_sample_counts : counts_out[B,Kcap] = round(total_points * area_k / sum area) (half to even; min_points where
+ *                          <= 0; 0 for dropped / padded clusters), offsets_out[B,Kcap+1] = exclusive prefix sums.
+ *   prifit_sample_surface: for slot i < offsets[b,Kcap] of shape b: owner_out = its ellipsoid, (U_out, V_out) = parameters of
+ *                          a point drawn uniformly over that ellipsoid's surface (Philox stream `seed`, rejection from the
+ *                          sphere); padding slots get owner -1.  x = a cos U sin V, y = b sin U sin V, z = c cos V. */
+int prifit_sample_counts(const float* s, const uint8_t* valid, const int32_t* K, int B, int Kcap, int total_points,
+                         int min_points, int32_t* counts_out, int32_t* offsets_out, void* stream);
+int prifit_sample_surface(const float* s, const int32_t* offsets, int B, int Kcap, int Smax, uint64_t seed,
+                          float* U_out, float* V_out, int32_t* owner_out, void* stream);
+
 /* f3 -- entropy regulariser.  convex_loss.py:209-225 (entropy) on the sub-sample of convex_loss.py:59-62.
  *   X[B,N,d] unit rows (d = 64 or 128), idx[n] int32 = the sampled point indices (shared by all shapes, unique; NULL = all
  *   N points), loss_b_out[B] = sum_ij (1 + <x_i, x_j>)^2 / n^2 over the sample, computed from the second moments

@@ -17,6 +17,8 @@ runs, fp64 = the gradient acceptance oracle of SURVEY.md 0.9), the algorithm of
     convex_loss.py:59-62,209-225              entropy regulariser on an N/4 sub-sample
     src/utils.py:384-426                      analytic_chamfer_distance, both halves (KD-tree -> brute-force nearest neighbour)
     models/pointnet_util.py:18-107,283-295    square_distance, farthest point sampling, ball query, 3-NN interpolation
+    src/ellipsoid_utils.py:76-130,157-159     per-ellipsoid point counts of the surface sampler
+    src/sample_ellipsoid.py:45-63             (U, V) parameters -> differentiable surface points
 
 Pinning: the reference ships no tests or golden vectors.  ``oracle/make_golden.py``
 runs the unmodified reference (through ``oracle/ref_loader.py``) in the build container, checks
@@ -361,3 +363,24 @@ def three_interpolate(xyz1, xyz2, points2):
     batch = torch.arange(B).view(B, 1, 1).repeat(1, N, 3)
     interpolated = torch.sum(points2[batch, idx, :] * weight.view(B, N, 3, 1), dim=2)
     return interpolated, idx, weight
+
+
+# ----------------------------------------------------------------------------- surface sampler (deterministic parts)
+def sample_counts(params):
+    """src/ellipsoid_utils.py:91-107,157-159: points per ellipsoid of one shape, params = list of (s, V, c)."""
+    areas = []
+    for (r, V, c) in params:
+        a, b, cc = r[0], r[1], r[2]
+        areas.append((4 * 3.142 * ((a * b) ** 1.585 + (b * cc) ** 1.585 + (cc * a) ** 1.585) ** (1 / 1.585)).item())
+    weights = np.asarray(areas) / np.sum(areas)
+    num = np.round(10000 * weights).astype(int)
+    num[num <= 0] = 100
+    return num
+
+
+def surface_points(U, Vang, r, V, centre):
+    """src/sample_ellipsoid.py:50-53,56-63: parameters (U, Vang) -> points on the ellipsoid (r, V, centre)."""
+    x = r[0] * torch.cos(U) * torch.sin(Vang)
+    y = r[1] * torch.sin(U) * torch.sin(Vang)
+    z = r[2] * torch.cos(Vang)
+    return torch.stack([x, y, z], 1) @ V.T + centre

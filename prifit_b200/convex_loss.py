@@ -3,12 +3,14 @@
     convex_loss                     reference :27-103   normalise -> cluster -> fit -> loss
     compute_sdf_ellipsoid[s][_batch] reference :313-343
 
-Scope: the fitting loss computed here is the analytic SDF half of
-`analytic_chamfer_distance` (src/utils.py:407-411,418,425) evaluated on `chamfer_points`.  The other
-half needs trimesh surface sampling + an sklearn KD-tree on the CPU (src/utils.py:413-416,
-src/sample_ellipsoid.py) and is a "next" row; the entropy regulariser (include_entropy_loss, :59-62,
+Scope: by default the fitting loss computed here is the analytic SDF half of
+`analytic_chamfer_distance` (src/utils.py:407-411,418,425) evaluated on `chamfer_points`; `full_chamfer=True` adds the
+sampled-surface half (device sampler + nearest-neighbour kernel in place of trimesh + an sklearn KD-tree on the CPU,
+src/utils.py:413-416, src/sample_ellipsoid.py); the entropy regulariser (include_entropy_loss, :59-62,
 :209-225) is built (csrc/entropy.cu); the intersection / pruning / cuboid terms are out of scope and raise.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -19,7 +21,8 @@ from .ellipsoid_utils import meanshift
 
 def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, quantile=0.01, iterations=5,
                 visualize=False, max_num_clusters=25, class_list=[], include_intersect_loss=False, alpha=1, beta=1,
-                if_cuboid=False, include_pruning=False, include_entropy_loss=False, evaluation=False, dist_reduce=False):
+                if_cuboid=False, include_pruning=False, include_entropy_loss=False, evaluation=False, dist_reduce=False,
+                full_chamfer=None):
     """points[B,3,N], chamfer_points[B,3,M], X[B,128,N] -> (total[1,1], l[1,1], params, labels).
 
     Same signature, defaults and return structure as the reference.  `params` is a lazy sequence of
@@ -28,7 +31,12 @@ def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, 
     dist_reduce (extension, one process per GPU): the batch mean runs over the shapes of every rank (one 8-byte
     all-reduce, train_partseg_shapenet.py:445 takes the mean of the replica losses); `total` is then this rank's share
     sum_local / n_global -- calling backward() on it on every rank gives the gradient of the global mean -- and `l` the
-    global mean itself."""
+    global mean itself.
+
+    full_chamfer (extension; default from PRIFIT_FULL_CHAMFER, off): the fitting loss becomes the reference's complete
+    analytic_chamfer_distance (:68-89) -- surface points sampled on the predicted ellipsoids on the device
+    (ellipsoid_utils.sample_from_pred_params) and their nearest chamfer points, plus the SDF half -- instead of the SDF half
+    alone.  Eager path; the sampler's random stream differs from trimesh's."""
     if include_intersect_loss or include_pruning or if_cuboid:
         raise NotImplementedError("intersection / pruning / cuboid terms are outside the accelerated path")
     # channel-last views (reference :37,38,84); the pipeline copies them into its own row-major buffers, so the
@@ -36,6 +44,22 @@ def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, 
     E = X.permute(0, 2, 1)
     P = points.permute(0, 2, 1)
     Q = None if evaluation or chamfer_points is points else chamfer_points.permute(0, 2, 1)
+    if full_chamfer is None:
+        full_chamfer = os.environ.get("PRIFIT_FULL_CHAMFER", "0") == "1"
+    if full_chamfer and not evaluation and not visualize:
+        from .ellipsoid_utils import sample_from_pred_params
+        from .utils import analytic_chamfer_distance
+        out = pipeline.fit_loss(E, P, quantile=quantile, iterations=iterations, max_num_clusters=max_num_clusters,
+                                Q=Q, engine=meanshift.engine, graph=False)
+        res = out["cluster"]
+        params = ParamsBatch(out["s"], out["V"], out["c"], out["valid"], res.K, res.K_host)
+        resampled = sample_from_pred_params(params, N, batch_id=batch_id, seed=seed)                    # reference :71
+        l = analytic_chamfer_distance(params, resampled, (P if Q is None else Q).contiguous())          # reference :89
+        total = l
+        if include_entropy_loss:
+            sub = np.random.choice(X.shape[2], X.shape[2] // 4, replace=False)
+            total = l + beta * entropy(ops.NormalizeTwice.apply(E.contiguous()), sub)
+        return total.view(1, 1), l.view(1, 1), params, list(res.labels.long().unbind(0))
     if visualize:
         # reference :68 -> src/ellipsoid_utils.py:48-54: one-hot arg-max memberships instead of the soft ones; the
         # stage-by-stage route (clustering -> fit -> SDF loss) handles it, no gradient reaches X through one-hot weights

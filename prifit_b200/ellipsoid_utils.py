@@ -54,10 +54,63 @@ def clustering(X, num_samples=1000, quantile=0.01, iterations=5, visualize=False
     return weights, labels
 
 
-def sample_from_pred_params(*args, **kwargs):
-    raise NotImplementedError(
-        "surface sampling of the fitted ellipsoids (reference src/ellipsoid_utils.py:76-130, trimesh on the CPU) is "
-        "outside the accelerated path; the fitting loss here is the analytic SDF half (see DESIGN.md)")
+class SampledPoints(list):
+    """list (B) of [n_b,3] tensors (or -1 for a shape without ellipsoids, like the reference) + the padded tensors behind them
+    (`.padded` = (S[B,Smax,3], nS int32[B])) so that utils.analytic_chamfer_distance need not re-pack them."""
+
+    def __init__(self, S, nS, totals):
+        self.padded = (S, nS)
+        super().__init__(S[b, :n] if n > 0 else -1 for b, n in enumerate(totals))
 
 
-sample_from_pred_params_cuboid = sample_from_pred_params
+def compute_approximate_ellipsoid_area(a, b, c, p):
+    """reference :157-159."""
+    area = 4 * 3.142 * ((a * b) ** p + (b * c) ** p + (c * a) ** p) ** (1 / p)
+    return area.item()
+
+
+def sample_from_pred_params(ellipse_params_batch, N, batch_id=0, seed=0, visualize=False, class_list=[], quantile=0.05):
+    """Points on the surfaces of the predicted ellipsoids, differentiable w.r.t. (s, V, center) -- reference :76-130 and
+    src/sample_ellipsoid.py:17-63.  Like the reference, every shape gets ~10000 points split over its ellipsoids in proportion
+    to their approximate areas (100 where the share rounds to nothing); `N` is accepted and ignored, as there.
+
+    Deviation: the reference samples a subdivided icosphere mesh with trimesh on the CPU (NumPy generator, "even"
+    spacing); here the (U, V) parameters are drawn on the device, i.i.d. uniform over each surface, from a Philox stream
+    seeded from NumPy's global generator (one np.random.randint per call).  Same distribution, different samples."""
+    import numpy as np
+
+    from . import _lib, utils as putils
+
+    if isinstance(ellipse_params_batch, putils.ParamsBatch):
+        dev = ellipse_params_batch.padded[0].device
+    else:
+        dev = next((p[0].device for per in ellipse_params_batch for p in per), torch.device("cuda", torch.cuda.current_device()))
+    s, V, c, valid, K = putils._pad_params(ellipse_params_batch, dev)
+    B, kcap = valid.shape
+    counts = torch.empty(B, kcap, dtype=torch.int32, device=dev)
+    offsets = torch.empty(B, kcap + 1, dtype=torch.int32, device=dev)
+    sd = ops._chk(s.detach())
+    _lib.call("prifit_sample_counts", ops._ptr(sd), ops._ptr(valid), ops._ptr(K), B, kcap, 10000, 100,
+              ops._ptr(counts), ops._ptr(offsets), ops._stream())
+    nS = offsets[:, kcap].contiguous()
+    totals = nS.tolist()                                   # the list structure needs the lengths on the host
+    smax = max(max(totals), 1)
+    U = torch.empty(B, smax, dtype=torch.float32, device=dev)
+    Vang = torch.empty(B, smax, dtype=torch.float32, device=dev)
+    owner = torch.empty(B, smax, dtype=torch.int32, device=dev)
+    stream_seed = int(np.random.randint(0, 2 ** 31 - 1))
+    _lib.call("prifit_sample_surface", ops._ptr(sd), ops._ptr(offsets), B, kcap, smax, stream_seed,
+              ops._ptr(U), ops._ptr(Vang), ops._ptr(owner), ops._stream())
+    # differentiable map (src/sample_ellipsoid.py:50-63): x = a cos U sin V, y = b sin U sin V, z = c cos V, rotate, translate
+    own = owner.clamp(min=0).long()
+    bidx = torch.arange(B, device=dev)[:, None].expand(B, smax)
+    abc, rot, cen = s[bidx, own], V[bidx, own], c[bidx, own]
+    sinV = torch.sin(Vang)
+    local = torch.stack([abc[..., 0] * torch.cos(U) * sinV, abc[..., 1] * torch.sin(U) * sinV, abc[..., 2] * torch.cos(Vang)], -1)
+    pts = torch.einsum("bni,bnji->bnj", local, rot) + cen            # sampled_points @ transformation.T + center
+    pts = pts * (owner >= 0).unsqueeze(-1).to(pts.dtype)
+    return SampledPoints(pts, nS, totals)
+
+
+def sample_from_pred_params_cuboid(*args, **kwargs):
+    raise NotImplementedError("the cuboid sampler (reference src/ellipsoid_utils.py:162-215) is outside the accelerated path")

@@ -55,6 +55,12 @@ def analytic_chamfer_distance(ellipsoid_params_batch, source_points, target_poin
         return torch.zeros(1, requires_grad=True, device=dev)          # reference :421-423
     s, V, c, valid, K = _pad_params(ellipsoid_params_batch, dev)
     sdf_half = ops.SdfLoss.apply(target_points, s, V, c, valid, K)      # 0.5 * mean_j (min_k |sdf|)^2 per shape
+    padded = getattr(source_points, "padded", None)
+    if padded is not None:                                              # ellipsoid_utils.sample_from_pred_params' own output
+        S, nS = padded
+        nn_half, _ = ops.NearestSqDist.apply(S, nS, target_points)
+        keep_t = torch.tensor(keep, dtype=torch.float32, device=dev)
+        return ((0.5 * nn_half + sdf_half) * keep_t).sum() / keep_t.sum()
     n_src = [int(sp.shape[0]) if k else 0 for sp, k in zip(source_points, keep)]
     smax = max(max(n_src), 1)
     rows = []

@@ -552,3 +552,104 @@ def test_convex_loss_visualize_uses_one_hot_memberships(cuda):
     ref = R.sdf_loss(P.double(), ref_params)
     assert [len(p) for p in params] == [len(p) for p in ref_params] == [4, 4]
     assert abs(float(total) - float(ref)) <= 1e-4 * float(ref)
+
+
+def _ellipsoids(B, K, cuda, seed):
+    gen = torch.Generator().manual_seed(seed)
+    params = []
+    for b in range(B):
+        per = []
+        for k in range(K + b):
+            Q, _ = torch.linalg.qr(torch.randn(3, 3, generator=gen))
+            per.append((0.05 + torch.rand(3, generator=gen), Q.contiguous(), torch.rand(3, generator=gen) - 0.5))
+        params.append(per)
+    return params
+
+
+def test_surface_sampler_counts_surface_and_gradient(cuda):
+    """On-device sampler: per-ellipsoid counts follow the reference's area rule, every point lies on its
+    ellipsoid, and the differentiable map (U, V) -> points has the reference's gradients (same expressions as the oracle)."""
+    from prifit_b200 import ellipsoid_utils as eu
+
+    params = _ellipsoids(3, 2, cuda, seed=1)
+    dev_params = [[(r.to(cuda).requires_grad_(True), V.to(cuda).requires_grad_(True), c.to(cuda).requires_grad_(True))
+                   for (r, V, c) in per] for per in params]
+    np.random.seed(3)
+    pts = eu.sample_from_pred_params(dev_params, 500)
+    S, nS = pts.padded
+    for b, per in enumerate(params):
+        want = R.sample_counts(per)
+        assert int(nS[b]) == len(pts[b]) and abs(int(nS[b]) - int(want.sum())) <= len(per)
+        off = 0
+        for k, (r, V, c) in enumerate(per):
+            n = int(want[k])
+            local = (pts[b][off:off + n].detach().cpu() - c) @ V                      # back to the axis-aligned frame
+            resid = ((local / r) ** 2).sum(-1) - 1.0
+            assert float(resid.abs().max()) < 1e-3, (b, k)
+            off += n
+    # gradients of sum(points * w) w.r.t. the parameters against the oracle's expression on the same (U, V) parameters
+    w = torch.randn_like(S)
+    (S * w).sum().backward()
+    b, k = 1, 2
+    r, V, c = [t.double().requires_grad_(True) for t in params[b][k]]
+    want = R.sample_counts(params[b])
+    off = int(want[:k].sum())
+    sel = S[b, off:off + int(want[k])].detach().cpu().double()
+    local = (sel - c.detach()) @ V.detach()
+    Vang = torch.acos(torch.clamp(local[:, 2] / (r.detach()[2] + 1e-6), -1, 1))
+    U = torch.atan2(local[:, 1] / (r.detach()[1] + 1e-6), local[:, 0] / (r.detach()[0] + 1e-6))
+    ref = R.surface_points(U, Vang, r, V, c)
+    assert float((ref.detach() - sel).abs().max()) < 3e-3          # (acos near the poles: the parameters are re-derived from fp32 points)
+    (ref * w[b, off:off + int(want[k])].cpu().double()).sum().backward()
+    gr, gV, gc = dev_params[b][k][0].grad.cpu().double(), dev_params[b][k][1].grad.cpu().double(), dev_params[b][k][2].grad.cpu().double()
+    assert float((gr - r.grad).abs().max()) <= 5e-3 * float(r.grad.abs().max())
+    assert float((gV - V.grad).abs().max()) <= 5e-3 * float(V.grad.abs().max())
+    assert float((gc - c.grad).abs().max()) <= 1e-4 * float(c.grad.abs().max())
+
+
+def test_surface_sampler_is_uniform_over_the_surface(cuda):
+    """200 k samples on a (1, 0.5, 0.25) ellipsoid: the share of points per slab of the polar parameter matches the share of
+    surface area (numerical quadrature) within 4 standard errors."""
+    from prifit_b200 import ellipsoid_utils as eu
+
+    a, b, c = 1.0, 0.5, 0.25
+    per = [(torch.tensor([a, b, c], device=cuda), torch.eye(3, device=cuda), torch.zeros(3, device=cuda))]
+    z = []
+    np.random.seed(5)
+    for _ in range(20):
+        z.append(eu.sample_from_pred_params([per], 0)[0][:, 2].cpu().numpy() / c)
+    z = np.concatenate(z)
+    edges = np.linspace(-1, 1, 9)
+    got = np.histogram(z, edges)[0] / z.size
+    # area element over the unit sphere parametrised by (zs, phi): g = sqrt((bc x)^2 + (ac y)^2 + (ab zs)^2)
+    zs = (np.arange(4000) + 0.5) / 4000 * 2 - 1
+    phi = (np.arange(720) + 0.5) / 720 * 2 * np.pi
+    rad = np.sqrt(1 - zs ** 2)[:, None]
+    g = np.sqrt((b * c * rad * np.cos(phi)) ** 2 + (a * c * rad * np.sin(phi)) ** 2 + (a * b * zs[:, None]) ** 2).sum(1)
+    want = np.array([g[(zs >= lo) & (zs < hi)].sum() for lo, hi in zip(edges[:-1], edges[1:])]) / g.sum()
+    se = np.sqrt(want * (1 - want) / z.size)
+    assert np.all(np.abs(got - want) < 4 * se + 1e-4), (got, want)
+
+
+def test_convex_loss_full_chamfer_matches_oracle_on_the_same_samples(cuda):
+    """convex_loss(full_chamfer=True): sampled-surface half + SDF half.  The sampler's stream differs from trimesh's, so
+    the check feeds the points it drew to the oracle's analytic_chamfer_distance: identical loss given identical samples."""
+    import prifit_b200.convex_loss as cl
+    from prifit_b200 import ellipsoid_utils as eu, synthetic, utils as pu
+
+    E, P, _ = synthetic.planted_shapes(2, n_points=512, n_clusters=4, sigma=0.02, seed=70)
+    Xcf = E.permute(0, 2, 1).contiguous().to(cuda).requires_grad_(True)
+    Pcf = P.permute(0, 2, 1).contiguous().to(cuda)
+    np.random.seed(21); torch.manual_seed(21)
+    total, l, params, labels = cl.convex_loss(Pcf, Pcf, Xcf, quantile=0.05, iterations=8, max_num_clusters=25, full_chamfer=True)
+    total.backward()
+    assert torch.isfinite(Xcf.grad).all() and float(Xcf.grad.abs().max()) > 0
+    np.random.seed(21)                                       # same Philox seed -> same samples
+    pts = eu.sample_from_pred_params(params, 0)
+    again = pu.analytic_chamfer_distance(params, pts, P.to(cuda))
+    assert abs(float(again) - float(l)) <= 1e-6 * float(l)
+    ref_params = [[(s.detach().cpu().double(), V.detach().cpu().double(), c.detach().cpu().double()) for (s, V, c) in per] for per in params]
+    ref = R.analytic_chamfer_distance(ref_params, [p.detach().cpu().double() for p in pts], P.double())
+    assert abs(float(l) - float(ref)) <= 1e-4 * float(ref)
+    total_sdf, _, _, _ = cl.convex_loss(Pcf, Pcf, Xcf.detach(), quantile=0.05, iterations=8, max_num_clusters=25)
+    assert float(l) > float(total_sdf)                       # the sampled half adds a positive term
