@@ -49,6 +49,24 @@ def pointnet():
     print("3-NN interp f+b   %7.1f us" % timeit(lambda: pu.three_interpolate(xyz, new_xyz, feats).sum().backward()))
 
 
+def full_chamfer():
+    import prifit_b200.convex_loss as cl
+    from prifit_b200 import synthetic
+    dev = torch.device("cuda:0")
+    E, P, _ = synthetic.planted_shapes(24, n_points=2048, n_clusters=16, seed=1000)
+    X = E.permute(0, 2, 1).contiguous().to(dev)
+    Pc = P.permute(0, 2, 1).contiguous().to(dev)
+
+    def step(full):
+        Xi = X.detach().requires_grad_(True)
+        total, _, _, _ = cl.convex_loss(Pc, Pc, Xi, quantile=0.05, iterations=10, max_num_clusters=25, full_chamfer=full)
+        total.backward()
+
+    print("convex_loss + backward, SDF half (graph path)       %7.1f us" % timeit(lambda: step(False), n=10))
+    print("convex_loss + backward, full chamfer (eager path)   %7.1f us" % timeit(lambda: step(True), n=10))
+
+
 if __name__ == "__main__":
     main()
     pointnet()
+    full_chamfer()
