@@ -185,6 +185,13 @@ int prifit_sample_counts(const float* s, const uint8_t* valid, const int32_t* K,
                          int min_points, int32_t* counts_out, int32_t* offsets_out, void* stream);
 int prifit_sample_surface(const float* s, const int32_t* offsets, int B, int Kcap, int Smax, uint64_t seed,
                           float* U_out, float* V_out, int32_t* owner_out, void* stream);
+/* the differentiable map of src/sample_ellipsoid.py:50-63: pts_out[B,Smax,3] = (a cos U sin V, b sin U sin V, c cos V) V^T + centre
+ *   (zero for padding slots), and its backward: gs/gV/gc [B,Kcap,...] overwritten (one CTA per ellipsoid, fixed order). */
+int prifit_surface_points_fwd(const float* s, const float* V, const float* c, const float* U, const float* Vang,
+                              const int32_t* owner, int B, int Kcap, int Smax, float* pts_out, void* stream);
+int prifit_surface_points_bwd(const float* s, const float* V, const float* U, const float* Vang, const int32_t* offsets,
+                              const float* gpts, int B, int Kcap, int Smax, float* gs_out, float* gV_out, float* gc_out,
+                              void* stream);
 
 /* f3 -- entropy regulariser.  convex_loss.py:209-225 (entropy) on the sub-sample of convex_loss.py:59-62.
  *   X[B,N,d] unit rows (d = 64 or 128), idx[n] int32 = the sampled point indices (shared by all shapes, unique; NULL = all

@@ -45,6 +45,8 @@ SIGNATURES = {
     "prifit_masked_mean_bwd": (_i, [_p, _p, _p, _p, _i, _p, _p]),
     "prifit_sample_counts": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "prifit_sample_surface": (_i, [_p, _p, _i, _i, _i, ctypes.c_uint64, _p, _p, _p, _p]),
+    "prifit_surface_points_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "prifit_surface_points_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "prifit_nn_workspace_bytes": (_sz, [_i, _i]),
     "prifit_nn_loss_fwd": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "prifit_nn_loss_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),

@@ -63,6 +63,32 @@ class SampledPoints(list):
         super().__init__(S[b, :n] if n > 0 else -1 for b, n in enumerate(totals))
 
 
+class _SurfacePoints(torch.autograd.Function):
+    """(s, V, c)[B,Kcap,...] + sampled parameters -> points [B,Smax,3]; backward reduces per ellipsoid (csrc/sample.cu)."""
+
+    @staticmethod
+    def forward(ctx, s, V, c, U, Vang, owner, offsets):
+        from . import _lib
+        s, V, c = ops._chk(s), ops._chk(V), ops._chk(c)
+        B, kcap, _ = s.shape
+        smax = U.shape[1]
+        pts = torch.empty(B, smax, 3, dtype=torch.float32, device=s.device)
+        _lib.call("prifit_surface_points_fwd", ops._ptr(s), ops._ptr(V), ops._ptr(c), ops._ptr(U), ops._ptr(Vang), ops._ptr(owner),
+                  B, kcap, smax, ops._ptr(pts), ops._stream())
+        ctx.save_for_backward(s, V, U, Vang, offsets)
+        return pts
+
+    @staticmethod
+    def backward(ctx, gpts):
+        from . import _lib
+        s, V, U, Vang, offsets = ctx.saved_tensors
+        B, kcap, _ = s.shape
+        gs, gV, gc = torch.empty_like(s), torch.empty_like(V), torch.empty(B, kcap, 3, dtype=torch.float32, device=s.device)
+        _lib.call("prifit_surface_points_bwd", ops._ptr(s), ops._ptr(V), ops._ptr(U), ops._ptr(Vang), ops._ptr(offsets),
+                  ops._ptr(gpts.contiguous()), B, kcap, U.shape[1], ops._ptr(gs), ops._ptr(gV), ops._ptr(gc), ops._stream())
+        return gs, gV, gc, None, None, None, None
+
+
 def compute_approximate_ellipsoid_area(a, b, c, p):
     """reference :157-159."""
     area = 4 * 3.142 * ((a * b) ** p + (b * c) ** p + (c * a) ** p) ** (1 / p)
@@ -102,13 +128,7 @@ def sample_from_pred_params(ellipse_params_batch, N, batch_id=0, seed=0, visuali
     _lib.call("prifit_sample_surface", ops._ptr(sd), ops._ptr(offsets), B, kcap, smax, stream_seed,
               ops._ptr(U), ops._ptr(Vang), ops._ptr(owner), ops._stream())
     # differentiable map (src/sample_ellipsoid.py:50-63): x = a cos U sin V, y = b sin U sin V, z = c cos V, rotate, translate
-    own = owner.clamp(min=0).long()
-    bidx = torch.arange(B, device=dev)[:, None].expand(B, smax)
-    abc, rot, cen = s[bidx, own], V[bidx, own], c[bidx, own]
-    sinV = torch.sin(Vang)
-    local = torch.stack([abc[..., 0] * torch.cos(U) * sinV, abc[..., 1] * torch.sin(U) * sinV, abc[..., 2] * torch.cos(Vang)], -1)
-    pts = torch.einsum("bni,bnji->bnj", local, rot) + cen            # sampled_points @ transformation.T + center
-    pts = pts * (owner >= 0).unsqueeze(-1).to(pts.dtype)
+    pts = _SurfacePoints.apply(s, V, c, U, Vang, owner, offsets)
     return SampledPoints(pts, nS, totals)
 
 
