@@ -111,10 +111,12 @@ size_t prifit_membership_workspace_bytes(int B, int N, int Kcap);
 int prifit_membership_fwd(const float* C, const float* X, const float* bw, const int32_t* K,
                           int B, int N, int d, int Kcap, float* W_out, float* smax_out,
                           void* ws, size_t ws_bytes, void* stream);
-/* gC_out[B,Kcap,d] is overwritten; dL/dX is accumulated into gX_inout[B,N,d] */
+/* gC_out[B,Kcap,d] is overwritten; dL/dX is accumulated into gX_inout[B,N,d]; ws: partial centre gradients of the key slices */
+size_t prifit_membership_bwd_workspace_bytes(int B, int Kcap, int d);
 int prifit_membership_bwd(const float* C, const float* X, const float* bw, const int32_t* K,
                           const float* W, const float* smax, const float* gW,
-                          int B, int N, int d, int Kcap, float* gC_out, float* gX_inout, void* stream);
+                          int B, int N, int d, int Kcap, float* gC_out, float* gX_inout,
+                          void* ws, size_t ws_bytes, void* stream);
 
 /* k5-k7 -- weighted ellipsoid fit.  src/ellipsoid_fitting.py:19-69,119-141 and the SVD of
  *   src/fitting_utils.py:108-139.

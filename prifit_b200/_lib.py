@@ -34,7 +34,8 @@ SIGNATURES = {
     "prifit_meanshift_rows_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _sz, _p]),
     "prifit_membership_workspace_bytes": (_sz, [_i, _i, _i]),
     "prifit_membership_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
-    "prifit_membership_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "prifit_membership_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "prifit_membership_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "prifit_fit_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "prifit_fit_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "prifit_sdf_workspace_bytes": (_sz, [_i, _i]),
@@ -104,7 +105,7 @@ def check(rc, what):
 LAUNCHES = {
     "prifit_normalize_fwd": 1, "prifit_normalize_bwd": 1, "prifit_normalize_fwd_cf": 1, "prifit_normalize_bwd_cf": 1, "prifit_bandwidth_fwd": 6, "prifit_meanshift_fwd": 3,
     "prifit_nms_fwd": 10, "prifit_meanshift_rows_fwd": 2, "prifit_meanshift_rows_bwd": 2,
-    "prifit_membership_fwd": 2, "prifit_membership_bwd": 1, "prifit_fit_fwd": 1, "prifit_fit_bwd": 1,
+    "prifit_membership_fwd": 2, "prifit_membership_bwd": 2, "prifit_fit_fwd": 1, "prifit_fit_bwd": 1,
     "prifit_sdf_loss_fwd": 2, "prifit_sdf_loss_bwd": 1,
     "prifit_masked_mean_fwd": 1, "prifit_masked_mean_bwd": 1, "prifit_noise_scatter": 1,
     "prifit_entropy_fwd": 2, "prifit_entropy_bwd": 1, "prifit_nn_loss_fwd": 2, "prifit_nn_loss_bwd": 1,

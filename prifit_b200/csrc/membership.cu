@@ -2,7 +2,6 @@
 // reference src/mean_shift.py:230-247 (membership):
 //     sim = C X^T / bw^2 ; sim -= sim.max().detach() ; e = guard_exp(sim) ; mem = e / sum_k e
 // Output layout is the reference's [K, N] (cluster-major), padded to [B, Kcap, N].
-#include <stdlib.h>
 #include "rowgemm.cuh"
 
 namespace {
@@ -75,32 +74,31 @@ __global__ void __launch_bounds__(256) membership_softmax_kernel(
 // ---- backward
 //   t_j   = sum_k gW_kj w_kj
 //   dsim_kj = w_kj (gW_kj - t_j) [lo <= sim_kj - max <= hi] / bw^2        (sim recomputed)
-//   gC_k  = sum_j dsim_kj x_j         (cluster reduction over key slices, fixed order)
+//   gC_k  = sum_j dsim_kj x_j         (partial sums over MB_SPLIT key slices, reduced in fixed order by a second kernel)
 //   gX_j += sum_k dsim_kj c_k
+// The keys of a shape are cut into MB_SPLIT slices (a number that depends on N only, so a shape's result does not depend on
+// the batch it is launched in); with 102 KB of shared memory two CTAs share an SM and the 24 x 8 = 192 CTAs of cfg2 are one
+// wave.  (The first version used a 4-CTA cluster per shape and a DSMEM reduction: 96 CTAs, 82 us.)
+constexpr int MB_SPLIT = 8;
+
 template <int D>
-__global__ void __launch_bounds__(RG_THREADS) membership_bwd_kernel(
+__global__ void __launch_bounds__(RG_THREADS, 2) membership_bwd_kernel(
     const float* __restrict__ C, const float* __restrict__ X, const float* __restrict__ bw,
     const int32_t* __restrict__ K, const float* __restrict__ W, const float* __restrict__ smax,
-    const float* __restrict__ gW, int N, int Kcap, float* __restrict__ gC, float* __restrict__ gX) {
+    const float* __restrict__ gW, int N, int Kcap, int nsplit, float* __restrict__ part, float* __restrict__ gX) {
     constexpr int LD = D + 4;
     constexpr int NH = (D + 127) / 128;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int csize = (int)cluster.num_blocks();
-    const int rank = (int)cluster.block_rank();
-    const int b = blockIdx.z;
+    const int rank = blockIdx.x, b = blockIdx.y;
     const int Kb = min(K[b], Kcap);
     const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
-    float* gC_b = gC + (size_t)b * Kcap * D;
-    // padded rows are defined as zero
-    for (int e = rank * RG_THREADS + tid; e < (Kcap - Kb) * D; e += csize * RG_THREADS) gC_b[(size_t)Kb * D + e] = 0.f;
-    if (Kb <= 0) return;     // uniform over the cluster
+    float* part_b = part + ((size_t)b * nsplit + rank) * Kcap * D;
+    if (Kb <= 0) return;     // the reduce kernel writes zeros
 
     extern __shared__ __align__(16) float smem[];
     float* ys = smem;
     float* xs = ys + RG_ROWS * LD;
     float* ps = xs + RG_KEYS * LD;
-    float* part_o = ps + RG_ROWS * RG_LDP;
-    float* tj = part_o + RG_ROWS * D;     // [128]
+    float* tj = ps + RG_ROWS * RG_LDP;     // [128]
 
     const float* Xb = X + (size_t)b * N * D;
     float* gXb = gX + (size_t)b * N * D;
@@ -109,8 +107,9 @@ __global__ void __launch_bounds__(RG_THREADS) membership_bwd_kernel(
     const float bwv = bw[b];
     const float b2 = bwv * bwv;
     const float mxv = smax[b];
-    const int sl = (N + csize - 1) / csize;
-    const int jbeg = rank * sl, jend = min(N, jbeg + sl);
+    const int ntile = (N + RG_KEYS - 1) / RG_KEYS;
+    const int tpr = (ntile + nsplit - 1) / nsplit;                      // key tiles per slice
+    const int jbeg = min(N, rank * tpr * RG_KEYS), jend = min(N, (rank + 1) * tpr * RG_KEYS);
 
     for (int k0 = 0; k0 < Kb; k0 += RG_ROWS) {
         const int nrows = min(RG_ROWS, Kb - k0);
@@ -159,14 +158,22 @@ __global__ void __launch_bounds__(RG_THREADS) membership_bwd_kernel(
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int h = 0; h < NH; ++h)
-                if (4 * tx + 128 * h < D)
-                    *reinterpret_cast<float4*>(part_o + (ty + 8 * a) * D + 4 * tx + 128 * h) =
+                if (4 * tx + 128 * h < D && ty + 8 * a < nrows)
+                    *reinterpret_cast<float4*>(part_b + (size_t)(k0 + ty + 8 * a) * D + 4 * tx + 128 * h) =
                         make_float4(o[a][4 * h], o[a][4 * h + 1], o[a][4 * h + 2], o[a][4 * h + 3]);
-        cluster.sync();
-        rg_cluster_reduce_rows<D>(cluster, part_o, csize, [&](int row, int col, float s) {
-            if (row < nrows) gC_b[(size_t)(k0 + row) * D + col] = s;
-        });
-        cluster.sync();
+    }
+}
+
+// gC[b, k, :] = sum over the key slices in slice order (rows k >= K[b] are zero)
+__global__ void membership_gc_reduce_kernel(const float* __restrict__ part, const int32_t* __restrict__ K, int Kcap, int D, int nsplit,
+                                            float* __restrict__ gC) {
+    const int b = blockIdx.y, k = blockIdx.x;
+    const int Kb = min(K[b], Kcap);
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float v = 0.f;
+        if (k < Kb)
+            for (int q = 0; q < nsplit; ++q) v += part[(((size_t)b * nsplit + q) * Kcap + k) * D + c];
+        gC[((size_t)b * Kcap + k) * D + c] = v;
     }
 }
 
@@ -186,22 +193,15 @@ int launch_fwd(const float* C, const float* X, const float* bw, const int32_t* K
 
 template <int D>
 int launch_bwd(const float* C, const float* X, const float* bw, const int32_t* K, const float* W, const float* smax,
-               const float* gW, int B, int N, int Kcap, float* gC, float* gX, cudaStream_t st) {
-    const size_t smem = ((size_t)(RG_ROWS + RG_KEYS) * (D + 4) + (size_t)RG_ROWS * RG_LDP + (size_t)RG_ROWS * D + RG_KEYS) * sizeof(float);
+               const float* gW, int B, int N, int Kcap, float* gC, float* gX, float* part, cudaStream_t st) {
+    const size_t smem = ((size_t)(RG_ROWS + RG_KEYS) * (D + 4) + (size_t)RG_ROWS * RG_LDP + RG_KEYS) * sizeof(float);
     PF_CUDA(cudaFuncSetAttribute(membership_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int csize = 4;          // independent of the batch size (fixed summation order); 4 beats 8 on cfg2 (one wave of CTAs)
-    if (const char* e = getenv("PRIFIT_MEMB_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) csize = v; }
-    while (csize > 1 && (N + RG_KEYS - 1) / RG_KEYS < csize) csize >>= 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(csize, 1, B);
-    cfg.blockDim = dim3(RG_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    PF_CUDA(cudaLaunchKernelEx(&cfg, membership_bwd_kernel<D>, C, X, bw, K, W, smax, gW, N, Kcap, gC, gX));
+    const int ntile = (N + RG_KEYS - 1) / RG_KEYS;
+    const int nsplit = ntile < MB_SPLIT ? ntile : MB_SPLIT;          // depends on N only
+    membership_bwd_kernel<D><<<dim3(nsplit, B), RG_THREADS, smem, st>>>(C, X, bw, K, W, smax, gW, N, Kcap, nsplit, part, gX);
+    PF_LAUNCH_CHECK();
+    membership_gc_reduce_kernel<<<dim3(Kcap, B), 128, 0, st>>>(part, K, Kcap, D, nsplit, gC);
+    PF_LAUNCH_CHECK();
     return 0;
 }
 
@@ -228,16 +228,23 @@ extern "C" int prifit_membership_fwd(const float* C, const float* X, const float
     }
 }
 
+extern "C" size_t prifit_membership_bwd_workspace_bytes(int B, int Kcap, int d) {
+    return (size_t)B * MB_SPLIT * Kcap * d * sizeof(float);
+}
+
 extern "C" int prifit_membership_bwd(const float* C, const float* X, const float* bw, const int32_t* K,
                                      const float* W, const float* smax, const float* gW,
-                                     int B, int N, int d, int Kcap, float* gC_out, float* gX_inout, void* stream) {
-    PF_CHECK_ARG(C && X && bw && K && W && smax && gW && gC_out && gX_inout, PRIFIT_E_BADARG, "null pointer");
+                                     int B, int N, int d, int Kcap, float* gC_out, float* gX_inout,
+                                     void* ws, size_t ws_bytes, void* stream) {
+    PF_CHECK_ARG(C && X && bw && K && W && smax && gW && gC_out && gX_inout && ws, PRIFIT_E_BADARG, "null pointer");
     PF_CHECK_ARG(B > 0 && N > 0, PRIFIT_E_BADARG, "B, N > 0 required");
     PF_CHECK_ARG(Kcap > 0 && Kcap % 4 == 0 && Kcap <= 64, PRIFIT_E_SHAPE, "Kcap must be a multiple of 4, <= 64");
+    PF_CHECK_ARG(ws_bytes >= prifit_membership_bwd_workspace_bytes(B, Kcap, d), PRIFIT_E_WS, "workspace too small");
+    float* part = static_cast<float*>(ws);
     switch (d) {
-        case 64: return launch_bwd<64>(C, X, bw, K, W, smax, gW, B, N, Kcap, gC_out, gX_inout, pf_stream(stream));
-        case 128: return launch_bwd<128>(C, X, bw, K, W, smax, gW, B, N, Kcap, gC_out, gX_inout, pf_stream(stream));
-        case 256: return launch_bwd<256>(C, X, bw, K, W, smax, gW, B, N, Kcap, gC_out, gX_inout, pf_stream(stream));
+        case 64: return launch_bwd<64>(C, X, bw, K, W, smax, gW, B, N, Kcap, gC_out, gX_inout, part, pf_stream(stream));
+        case 128: return launch_bwd<128>(C, X, bw, K, W, smax, gW, B, N, Kcap, gC_out, gX_inout, part, pf_stream(stream));
+        case 256: return launch_bwd<256>(C, X, bw, K, W, smax, gW, B, N, Kcap, gC_out, gX_inout, part, pf_stream(stream));
         default: prifit_set_error("prifit_membership_bwd: d must be 64, 128 or 256 (got %d)", d); return PRIFIT_E_SHAPE;
     }
 }

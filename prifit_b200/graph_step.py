@@ -127,6 +127,7 @@ class GraphStep:
                 "rows": lib.prifit_meanshift_rows_workspace_bytes(Bb, N, d, rows_engine),
                 "memb": max(16, lib.prifit_membership_workspace_bytes(Bb, N, kcap)),
                 "sdf": max(16, lib.prifit_sdf_workspace_bytes(Bb, self.Mq)),
+                "membb": lib.prifit_membership_bwd_workspace_bytes(Bb, kcap, d),
             }
             self.ws.append({k: (torch.empty(v, dtype=u8, device=device), v) for k, v in sizes.items()})
         # ---- pinned staging of the host noise stream (two slots: the host may run ahead of the device)
@@ -205,7 +206,7 @@ class GraphStep:
                       _ptr(valid), _ptr(gs), _ptr(gV), _ptr(gc), Bb, N, kcap, _ptr(gW), None, st)
             gX.zero_()
             _lib.call("prifit_membership_bwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), _ptr(W), _ptr(self.smax[lo:hi]), _ptr(gW),
-                      Bb, N, d, kcap, _ptr(gC), _ptr(gX), st)
+                      Bb, N, d, kcap, _ptr(gC), _ptr(gX), _ptr(ws["membb"][0]), ws["membb"][1], st)
             _lib.call("prifit_meanshift_rows_bwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), _ptr(self.traj[lo:hi]),
                       _ptr(self.stat[lo:hi]), _ptr(gC), Bb, N, d, T, kcap, _ptr(gX), self.rows_bwd_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
             if self.cf:

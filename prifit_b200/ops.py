@@ -183,8 +183,10 @@ def membership_bwd(C, X, bw, K, W, smax, gW, gX_inout):
     B, N, d = X.shape
     kcap = C.shape[1]
     gC = torch.empty_like(C)
+    nbytes = _lib.load().prifit_membership_bwd_workspace_bytes(B, kcap, d)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=X.device)
     _lib.call("prifit_membership_bwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), _ptr(W), _ptr(smax), _ptr(gW),
-              B, N, d, kcap, _ptr(gC), _ptr(gX_inout), _stream())
+              B, N, d, kcap, _ptr(gC), _ptr(gX_inout), _ptr(ws), nbytes, _stream())
     return gC
 
 
