@@ -292,6 +292,36 @@ def pointnet_case():
                         gfeats=feats.grad.numpy(), sqd_ball=pu.square_distance(new_xyz, xyz).numpy())
 
 
+def sampler_case(ns):
+    """Deterministic parts of the surface sampler through the reference's own functions: compute_approximate_ellipsoid_area
+    (src/ellipsoid_utils.py:157-159) with the counts rule of :104-107, and SampleEllipsoid.uniform_sample_points_on_ellipsoid
+    + the transform of src/sample_ellipsoid.py:50-53.  (The sampling itself needs trimesh and is random.)"""
+    import importlib
+    se = importlib.import_module("src.sample_ellipsoid")
+    torch.manual_seed(31)
+    K = 5
+    r = 0.05 + torch.rand(K, 3)
+    r[3] = torch.tensor([1e-3, 2e-3, 1e-3])                          # share rounds to zero -> 100 points
+    areas = [ns.ellipsoid_utils.compute_approximate_ellipsoid_area(r[k, 0], r[k, 1], r[k, 2], p=1.585) for k in range(K)]
+    weights = areas / np.sum(areas)
+    num = np.round(10000 * weights).astype(int)
+    num[num <= 0] = 100
+    Q, _ = torch.linalg.qr(torch.randn(3, 3))
+    centre = torch.rand(3) - 0.5
+    U = (torch.rand(64) * 2 - 1) * 3.14159
+    Vang = torch.rand(64) * 3.14159
+    rr = r[0].clone().requires_grad_(True)
+    Qr, cr = Q.clone().requires_grad_(True), centre.clone().requires_grad_(True)
+    pts = se.SampleEllipsoid().uniform_sample_points_on_ellipsoid(U, Vang, rr[0], rr[1], rr[2]) @ Qr.T + cr
+    w = torch.randn(64, 3)
+    (pts * w).sum().backward()
+    assert np.array_equal(R.sample_counts([(r[k], None, None) for k in range(K)]), num)
+    print("[sampler] counts", num.tolist(), "| points oracle-ref %.2e" % rel(R.surface_points(U, Vang, r[0], Q, centre), pts.detach()))
+    np.savez_compressed(os.path.join(OUT, "sampler.npz"), r=r.numpy(), counts=num.astype(np.int32), V=Q.numpy(), centre=centre.numpy(),
+                        U=U.numpy(), Vang=Vang.numpy(), pts=pts.detach().numpy(), w=w.numpy(), gr=rr.grad.numpy(),
+                        gV=Qr.grad.numpy(), gc=cr.grad.numpy())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
@@ -304,9 +334,13 @@ def main():
     if "--only-pointnet" in sys.argv:
         pointnet_case()
         return
+    if "--only-sampler" in sys.argv:
+        sampler_case(ns)
+        return
     entropy_case(ns)
     chamfer_case(ns)
     pointnet_case()
+    sampler_case(ns)
     stage_case(ns)
     svd_backward_case(ns)
     fit_kat_case(ns)

@@ -84,8 +84,9 @@ class _SurfacePoints(torch.autograd.Function):
         s, V, U, Vang, offsets = ctx.saved_tensors
         B, kcap, _ = s.shape
         gs, gV, gc = torch.empty_like(s), torch.empty_like(V), torch.empty(B, kcap, 3, dtype=torch.float32, device=s.device)
+        gpts = gpts.contiguous()                         # held in a local: the library gets raw pointers
         _lib.call("prifit_surface_points_bwd", ops._ptr(s), ops._ptr(V), ops._ptr(U), ops._ptr(Vang), ops._ptr(offsets),
-                  ops._ptr(gpts.contiguous()), B, kcap, U.shape[1], ops._ptr(gs), ops._ptr(gV), ops._ptr(gc), ops._stream())
+                  ops._ptr(gpts), B, kcap, U.shape[1], ops._ptr(gs), ops._ptr(gV), ops._ptr(gc), ops._stream())
         return gs, gV, gc, None, None, None, None
 
 

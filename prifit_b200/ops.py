@@ -441,7 +441,8 @@ class EntropyLoss(torch.autograd.Function):
         idx = ctx.saved_tensors[2] if len(ctx.saved_tensors) > 2 else None
         B, N, d = X.shape
         gX = torch.zeros_like(X)
-        _lib.call("prifit_entropy_bwd", _ptr(X), _ptr(idx), _ptr(gl.contiguous()), B, N, d, ctx.n, _ptr(ws), _ptr(gX), _stream())
+        gl = gl.contiguous()                             # held in a local: the library gets raw pointers
+        _lib.call("prifit_entropy_bwd", _ptr(X), _ptr(idx), _ptr(gl), B, N, d, ctx.n, _ptr(ws), _ptr(gX), _stream())
         return gX, None
 
 
@@ -473,6 +474,7 @@ class NearestSqDist(torch.autograd.Function):
         B, Smax, _ = S.shape
         gS = torch.empty_like(S)
         gT = torch.zeros_like(T) if ctx.needs_input_grad[2] else None
-        _lib.call("prifit_nn_loss_bwd", _ptr(S), _ptr(nS), _ptr(T), _ptr(idx), _ptr(gloss.contiguous()), B, Smax, T.shape[1],
+        gloss = gloss.contiguous()                       # held in a local: the library gets raw pointers
+        _lib.call("prifit_nn_loss_bwd", _ptr(S), _ptr(nS), _ptr(T), _ptr(idx), _ptr(gloss), B, Smax, T.shape[1],
                   _ptr(gS), _ptr(gT), _stream())
         return gS, None, gT

@@ -73,7 +73,8 @@ class _Interpolate(torch.autograd.Function):
         idx, weight = ctx.saved_tensors
         B, N, S, D = ctx.shape
         g = torch.zeros(B, S, D, dtype=torch.float32, device=gout.device)
-        _lib.call("prifit_interpolate_bwd", _ptr(gout.contiguous()), _ptr(idx), _ptr(weight), B, N, S, D, _ptr(g), _stream())
+        gout = gout.contiguous()                         # held in a local: the library gets raw pointers
+        _lib.call("prifit_interpolate_bwd", _ptr(gout), _ptr(idx), _ptr(weight), B, N, S, D, _ptr(g), _stream())
         return g, None, None
 
 

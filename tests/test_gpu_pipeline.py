@@ -653,3 +653,34 @@ def test_convex_loss_full_chamfer_matches_oracle_on_the_same_samples(cuda):
     assert abs(float(l) - float(ref)) <= 1e-4 * float(ref)
     total_sdf, _, _, _ = cl.convex_loss(Pcf, Pcf, Xcf.detach(), quantile=0.05, iterations=8, max_num_clusters=25)
     assert float(l) > float(total_sdf)                       # the sampled half adds a positive term
+
+
+def test_surface_point_kernels_against_reference_fixture(cuda, golden_dir):
+    """Counts kernel and the surface-point map kernels (fwd + bwd) against values produced by the reference's own functions."""
+    from prifit_b200 import _lib, ellipsoid_utils as eu, ops
+
+    g = _g(golden_dir, "sampler")
+    K = g["r"].shape[0]
+    s = torch.zeros(1, 32, 3); s[0, :K] = torch.from_numpy(g["r"])
+    valid = torch.zeros(1, 32, dtype=torch.uint8); valid[0, :K] = 1
+    Kt = torch.tensor([K], dtype=torch.int32)
+    counts = torch.empty(1, 32, dtype=torch.int32, device=cuda)
+    offsets = torch.empty(1, 33, dtype=torch.int32, device=cuda)
+    sc, vc, kc = s.to(cuda), valid.to(cuda), Kt.to(cuda)            # (held: raw pointers go to the library)
+    _lib.call("prifit_sample_counts", ops._ptr(sc), ops._ptr(vc), ops._ptr(kc), 1, 32, 10000, 100,
+              ops._ptr(counts), ops._ptr(offsets), ops._stream())
+    assert counts[0, :K].cpu().tolist() == g["counts"].tolist() and int(counts[0, K:].sum()) == 0
+    # map: the fixture's 64 parameters as the first 64 slots of ellipsoid 0
+    n = g["U"].shape[0]
+    sp = sc.clone().requires_grad_(True)
+    V = torch.zeros(1, 32, 3, 3); V[0, 0] = torch.from_numpy(g["V"])
+    c = torch.zeros(1, 32, 3); c[0, 0] = torch.from_numpy(g["centre"])
+    Vp, cp = V.to(cuda).requires_grad_(True), c.to(cuda).requires_grad_(True)
+    owner = torch.zeros(1, n, dtype=torch.int32, device=cuda)
+    off = torch.zeros(1, 33, dtype=torch.int32); off[0, 1:] = n
+    Uc, Vc, offc = torch.from_numpy(g["U"])[None].to(cuda), torch.from_numpy(g["Vang"])[None].to(cuda), off.to(cuda)
+    pts = eu._SurfacePoints.apply(sp, Vp, cp, Uc, Vc, owner, offc)
+    (pts * torch.from_numpy(g["w"])[None].to(cuda)).sum().backward()
+    assert rel_err(pts[0], g["pts"]) < 1e-5
+    assert rel_err(sp.grad[0, 0], g["gr"]) < 1e-4 and rel_err(Vp.grad[0, 0], g["gV"]) < 1e-4 and rel_err(cp.grad[0, 0], g["gc"]) < 1e-4
+    assert float(sp.grad[0, 1:].abs().max()) == 0.0

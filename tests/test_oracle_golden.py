@@ -164,3 +164,19 @@ def test_pointnet_geometric_ops_against_reference(golden_dir):
     assert torch.equal(idx, torch.from_numpy(g["nn_idx"]))
     assert rel_err(w, g["nn_weight"]) < 1e-6 and rel_err(interp, g["interp"]) < 1e-6
     assert rel_err(feats.grad, g["gfeats"]) < 1e-6
+
+
+def test_sampler_deterministic_parts_against_reference(golden_dir):
+    """Counts rule (reference compute_approximate_ellipsoid_area + round / min-100) and the (U, V) -> points map with its
+    gradients (reference SampleEllipsoid.uniform_sample_points_on_ellipsoid + transform)."""
+    g = _load(golden_dir, "sampler")
+    r = torch.from_numpy(g["r"])
+    assert np.array_equal(R.sample_counts([(r[k], None, None) for k in range(r.shape[0])]), g["counts"])
+    assert int(g["counts"][3]) == 100
+    rr = r[0].clone().requires_grad_(True)
+    V = torch.from_numpy(g["V"]).requires_grad_(True)
+    c = torch.from_numpy(g["centre"]).requires_grad_(True)
+    pts = R.surface_points(torch.from_numpy(g["U"]), torch.from_numpy(g["Vang"]), rr, V, c)
+    (pts * torch.from_numpy(g["w"])).sum().backward()
+    assert rel_err(pts, g["pts"]) < 1e-6
+    assert rel_err(rr.grad, g["gr"]) < 1e-5 and rel_err(V.grad, g["gV"]) < 1e-5 and rel_err(c.grad, g["gc"]) < 1e-5
