@@ -49,16 +49,17 @@ def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, 
     if full_chamfer and not evaluation and not visualize:
         from .ellipsoid_utils import sample_from_pred_params
         from .utils import analytic_chamfer_distance
+        entropy_term = None
+        if include_entropy_loss:                              # reference :59-62: drawn before the clustering
+            sub = np.random.choice(X.shape[2], X.shape[2] // 4, replace=False)
+            entropy_term = entropy(ops.NormalizeTwice.apply(E.contiguous()), sub)
         out = pipeline.fit_loss(E, P, quantile=quantile, iterations=iterations, max_num_clusters=max_num_clusters,
                                 Q=Q, engine=meanshift.engine, graph=False)
         res = out["cluster"]
         params = ParamsBatch(out["s"], out["V"], out["c"], out["valid"], res.K, res.K_host)
         resampled = sample_from_pred_params(params, N, batch_id=batch_id, seed=seed)                    # reference :71
         l = analytic_chamfer_distance(params, resampled, (P if Q is None else Q).contiguous())          # reference :89
-        total = l
-        if include_entropy_loss:
-            sub = np.random.choice(X.shape[2], X.shape[2] // 4, replace=False)
-            total = l + beta * entropy(ops.NormalizeTwice.apply(E.contiguous()), sub)
+        total = l if entropy_term is None else l + beta * entropy_term
         return total.view(1, 1), l.view(1, 1), params, list(res.labels.long().unbind(0))
     if visualize:
         # reference :68 -> src/ellipsoid_utils.py:48-54: one-hot arg-max memberships instead of the soft ones; the
