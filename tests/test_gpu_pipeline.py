@@ -653,6 +653,14 @@ def test_convex_loss_full_chamfer_matches_oracle_on_the_same_samples(cuda):
     assert abs(float(l) - float(ref)) <= 1e-4 * float(ref)
     total_sdf, _, _, _ = cl.convex_loss(Pcf, Pcf, Xcf.detach(), quantile=0.05, iterations=8, max_num_clusters=25)
     assert float(l) > float(total_sdf)                       # the sampled half adds a positive term
+    # together with the entropy regulariser: total = l + beta * entropy, sub-sample drawn first (reference :59-62)
+    np.random.seed(33); torch.manual_seed(33)
+    t2, l2, _, _ = cl.convex_loss(Pcf, Pcf, Xcf.detach(), quantile=0.05, iterations=8, max_num_clusters=25, full_chamfer=True,
+                                  include_entropy_loss=True, beta=0.5)
+    np.random.seed(33)
+    idx = np.random.choice(512, 128, replace=False)
+    ent = R.entropy_term(E.double(), idx)
+    assert abs(float(t2) - float(l2) - 0.5 * float(ent)) <= 1e-5 * max(float(t2), 1e-6)
 
 
 def test_surface_point_kernels_against_reference_fixture(cuda, golden_dir):
