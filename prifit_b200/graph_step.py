@@ -366,6 +366,8 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
 
     B, N, d = E.shape
     engine = ops.DEFAULT_ENGINE if engine is None else engine
+    if engine == ops.MS_TF32_TCGEN05 and d != 128:
+        engine = ops.MS_FP32_SIMT                          # the tensor-core kernel is specialised for d = 128 (like ops.meanshift)
     rows_engine = ops._rows_engine(None, d)
     M = None if Q is None else Q.shape[1]
     # channel-first input (convex_loss hands over X[B,d,N].permute(0,2,1)): keep it channel-first, the normalisation

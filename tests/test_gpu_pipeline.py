@@ -692,3 +692,18 @@ def test_surface_point_kernels_against_reference_fixture(cuda, golden_dir):
     assert rel_err(pts[0], g["pts"]) < 1e-5
     assert rel_err(sp.grad[0, 0], g["gr"]) < 1e-4 and rel_err(Vp.grad[0, 0], g["gV"]) < 1e-4 and rel_err(cp.grad[0, 0], g["gc"]) < 1e-4
     assert float(sp.grad[0, 1:].abs().max()) == 0.0
+
+
+def test_graph_step_with_64_dimensional_embeddings(cuda):
+    """d = 64 has no tensor-core kernels: the graph-replayed step must pick the fp32 engines like the eager path does."""
+    gen = torch.Generator().manual_seed(12)
+    B, N, d, kc = 2, 384, 64, 3
+    dirs = torch.nn.functional.normalize(torch.randn(B, kc, d, generator=gen), dim=-1)
+    ids = torch.arange(N) % kc
+    E = dirs[:, ids] + 0.02 * torch.randn(B, N, d, generator=gen)
+    P = torch.rand(B, N, 3, generator=gen) * 0.2 + ids[None, :, None].float()
+    noise = torch.rand(B, 32, 3, 3, generator=gen)
+    a = _run(E, P, cuda, 0.05, 6, 25, noise=noise, graph=True)
+    b = _run(E, P, cuda, 0.05, 6, 25, noise=noise, graph=False)
+    assert a.get("graph") is True and a["cluster"].K_host == b["cluster"].K_host == [kc, kc]
+    assert torch.equal(a["loss"], b["loss"]) and torch.equal(a["grad_E"], b["grad_E"])
