@@ -37,7 +37,7 @@ extern "C" {
 #define PRIFIT_E_NODEVICE (-4)   /* no sm_100 device / driver entry point missing */
 
 /* mean-shift forward engines */
-#define PRIFIT_MS_TF32_TCGEN05 0 /* tensor cores: tcgen05.mma kind::f16 (10-bit mantissa operands like tf32), TMEM, TMA */
+#define PRIFIT_MS_F16_TCGEN05 0 /* tensor cores: tcgen05.mma kind::f16 (10-bit mantissa operands like tf32), TMEM, TMA */
 #define PRIFIT_MS_FP32_SIMT    1 /* CUDA-core fp32, used to cross-check the tensor-core kernel */
 
 int prifit_version(void);
@@ -74,9 +74,11 @@ int prifit_meanshift_fwd(const float* X, const float* bw, int B, int N, int d, i
 /* k3 -- NMS mode pruning + hard labels.  src/mean_shift.py:162-202 (nms(new_X, new_X, bw)) and the
  *   guard predicate of src/ellipsoid_utils.py:19-26.
  *   idx_out[B,Kcap]  representative point index per cluster, ascending, -1 padded
- *   K_out[B]         number of representatives (may exceed Kcap; only Kcap are stored)
- *   labels_out[B,N]  argmax_k <newX[idx[k]], newX[j]>, lowest k on ties
- *   n_labels_out[B]  number of distinct labels (== torch.unique(labels).shape[0]); K if K > Kcap */
+ *   K_out[B]         number of representatives (may exceed Kcap; only the first Kcap are stored in idx_out)
+ *   labels_out[B,N]  argmax_k <newX[rep k], newX[j]> over ALL K_out[b] representatives (also beyond Kcap), lowest k on ties
+ *   n_labels_out[B]  number of distinct labels (== torch.unique(labels).shape[0]), exact for any K: the guard criterion of
+ *                    src/ellipsoid_utils.py:23.  A shape with K_out > Kcap that passes the guard needs a larger Kcap
+ *                    for the differentiable stages (the host re-runs it with Kcap = 64). */
 size_t prifit_nms_workspace_bytes(int B, int N, int d);
 int prifit_nms_fwd(const float* newX, const float* bw, int B, int N, int d, int Kcap,
                    int32_t* idx_out, int32_t* K_out, int32_t* labels_out, int32_t* n_labels_out,

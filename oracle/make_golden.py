@@ -26,33 +26,7 @@ from prifit_b200 import synthetic  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def _seed(s):
-    torch.manual_seed(s)
-    np.random.seed(s)
-
-
-def ref_fit_loss(ns, E, P, quantile, iterations, max_num_clusters, seed):
-    """The reference's stage functions wired as convex_loss wires them (convex_loss.py:37-70,
-    src/utils.py:407-425, SDF half only), backward to the un-normalised embeddings."""
-    _seed(seed)
-    E = E.detach().clone().requires_grad_(True)
-    X = torch.nn.functional.normalize(E, dim=2, p=2)
-    X = torch.nn.functional.normalize(X, dim=2, p=2)
-    weights, labels = ns.ellipsoid_utils.clustering(
-        X, quantile=quantile, iterations=iterations, max_num_clusters=max_num_clusters, num_samples=X.shape[1])
-    n_attempt = [w.shape[1] for w in weights]
-    params = ns.ellipsoid_fitting.weighted_ellipsoid_fitting_batch(P, weights)
-    sdfs = ns.convex_loss.compute_sdf_ellipsoids_batch(P, params)
-    per_shape = []
-    for b in range(P.shape[0]):
-        if len(params[b]) == 0:
-            continue
-        s = torch.abs(torch.stack(sdfs[b], 1))
-        per_shape.append(torch.mean(torch.min(s, 1)[0] ** 2) / 2.0)
-    loss = torch.stack(per_shape).mean()
-    loss.backward()
-    return {"loss": loss.detach(), "grad_E": E.grad.detach(), "params": params, "labels": labels,
-            "weights": weights, "n_attempt": n_attempt}
+from oracle.ref_runner import ref_fit_loss, seed_all as _seed  # noqa: E402
 
 
 def drawn_noise(seed, n_attempt, kcap):
@@ -322,6 +296,100 @@ def sampler_case(ns):
                         gV=Qr.grad.numpy(), gc=cr.grad.numpy())
 
 
+def big_case(ns, name, recipes, quantile, iterations, max_num_clusters, seed=7, kcap=32, check_oracle=True):
+    """Full-size parity case.  Inputs come from prifit_b200.synthetic recipes (the fixture stores the recipes and a
+    checksum of E instead of E); outputs: the unmodified reference's labels (fp32 and fp64 runs), parameters, loss, the
+    fp64 input gradient (stored as fp32: 6e-8 relative, far below the 1e-4 acceptance) and the scalar
+    err(ref32, ref64) = max|grad32 - grad64| / max|grad64| that the acceptance rule of SURVEY 8c needs."""
+    import json
+    parts = [synthetic.from_recipe(r) for r in recipes]
+    E, P = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+    ref32 = ref_fit_loss(ns, E, P, quantile, iterations, max_num_clusters, seed)
+    ref64 = ref_fit_loss(ns, E.double(), P.double(), quantile, iterations, max_num_clusters, seed)
+    noise = drawn_noise(seed, ref32["n_attempt"], kcap)
+    err = rel(ref32["grad_E"], ref64["grad_E"])
+    print("[%s] K32=%s K64=%s loss32 %.9g loss64 %.9g  |grad32-grad64| rel %.2e  max|grad64| %.3e" % (
+        name, ref32["n_attempt"], ref64["n_attempt"], float(ref32["loss"]), float(ref64["loss"]), err,
+        float(ref64["grad_E"].abs().max())))
+    extra = {}
+    if check_oracle:
+        _seed(seed)
+        info32 = []
+        o32 = R.fit_loss(E, P, quantile, iterations, max_num_clusters, info=info32)
+        print("   oracle32-ref32: loss rel %.2e grad rel %.2e" % (rel(o32["loss"], ref32["loss"]), rel(o32["grad_E"], ref32["grad_E"])))
+        for b in range(E.shape[0]):
+            assert torch.equal(o32["labels"][b], ref32["labels"][b])
+        extra["bw32"] = np.asarray([i["bw"] for i in info32], np.float64)
+        extra["passes"] = np.asarray([i["passes"] for i in info32], np.int32)
+    s32, V32, c32, n32 = pack_params(ref32["params"], kcap, np.float32)
+    s64, V64, c64, n64 = pack_params(ref64["params"], kcap, np.float64)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), recipes=np.asarray(json.dumps(recipes)), checksum_E=np.asarray(synthetic.checksum(E)),
+        checksum_P=np.asarray(synthetic.checksum(P)), quantile=np.float64(quantile), iterations=np.int32(iterations),
+        max_num_clusters=np.int32(max_num_clusters), noise=noise.numpy(), n_attempt=np.asarray(ref32["n_attempt"], np.int32),
+        n_attempt64=np.asarray(ref64["n_attempt"], np.int32),
+        labels32=np.stack([l.numpy() for l in ref32["labels"]]).astype(np.int16),
+        labels64=np.stack([l.numpy() for l in ref64["labels"]]).astype(np.int16),
+        s32=s32, V32=V32, c32=c32, nfit32=n32, s64=s64, V64=V64, c64=c64, nfit64=n64,
+        loss32=np.float64(ref32["loss"]), loss64=np.float64(ref64["loss"]),
+        grad64=ref64["grad_E"].numpy().astype(np.float32), err32_64=np.float64(err),
+        gscale=np.float64(ref64["grad_E"].abs().max()), **extra)
+
+
+def ref_labels(ns, E, quantile, iterations, max_num_clusters, seed, P=None):
+    """clustering() of the reference on one batch -> labels, cluster counts, (and the SDF loss when P is given)."""
+    _seed(seed)
+    X = torch.nn.functional.normalize(torch.nn.functional.normalize(E, dim=2, p=2), dim=2, p=2)
+    with torch.no_grad():
+        weights, labels = ns.ellipsoid_utils.clustering(X, quantile=quantile, iterations=iterations,
+                                                        max_num_clusters=max_num_clusters, num_samples=X.shape[1])
+    return np.stack([l.numpy() for l in labels]).astype(np.int16), [w.shape[1] for w in weights]
+
+
+NOISY = [
+    # (recipe, quantile): inputs whose modes merge / do not converge in T = 10 iterations (SURVEY 8d)
+    ({"family": "unbalanced", "batch": 4, "sigma": 0.02, "seed": 900}, 0.05),
+    ({"family": "unbalanced", "batch": 4, "sigma": 0.03, "seed": 910}, 0.05),
+    ({"family": "unbalanced", "batch": 4, "sigma": 0.03, "seed": 920}, 0.02),
+    ({"family": "unbalanced", "batch": 4, "sigma": 0.04, "seed": 930}, 0.02),
+    ({"family": "planted", "batch": 2, "sigma": 0.03, "seed": 940}, 0.05),
+    ({"family": "smooth", "batch": 3, "freq": 0.5, "sigma": 0.0, "seed": 950}, 0.02),
+    ({"family": "smooth", "batch": 3, "freq": 1.0, "sigma": 0.0, "seed": 960}, 0.02),
+]
+
+
+def noisy_case(ns):
+    """Labels of the reference's fp32 and fp64 runs on the "noisy" family, with the reference's own fp32-vs-fp64 partition
+    disagreement -- the floor the engines' label agreement is judged against (tests/helpers.partition_disagreement)."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import partition_disagreement
+    out = {"groups": np.asarray(json.dumps(NOISY))}
+    for i, (recipe, q) in enumerate(NOISY):
+        E, P = synthetic.from_recipe(recipe)
+        l32, k32 = ref_labels(ns, E, q, 10, 25, seed=3)
+        l64, k64 = ref_labels(ns, E.double(), q, 10, 25, seed=3)
+        d = [partition_disagreement(l32[b], l64[b]) for b in range(E.shape[0])]
+        print("[noisy %d] %s q=%g  K32 %s K64 %s  disagreement %s" % (i, recipe, q, k32, k64, ["%.4f" % v for v in d]))
+        out["labels32_%d" % i], out["labels64_%d" % i] = l32, l64
+        out["K32_%d" % i], out["K64_%d" % i] = np.asarray(k32, np.int32), np.asarray(k64, np.int32)
+        out["dis_%d" % i] = np.asarray(d, np.float64)
+        out["checksum_%d" % i] = np.asarray(synthetic.checksum(E))
+    np.savez_compressed(os.path.join(OUT, "noisy_labels.npz"), **out)
+
+
+def round2_cases(ns):
+    # guard redo that ends with K > 1 (3 passes -> 4 clusters) next to a shape that needs no redo (sub-batch compaction)
+    E0, P0, _ = synthetic.hier_shapes(1, seed=1)
+    E1, P1, _ = synthetic.planted_shapes(1, n_points=1024, n_clusters=8, sigma=0.02, seed=210)
+    E2, P2, _ = synthetic.hier_shapes(1, n_groups=5, per_group=6, seed=2)
+    pipeline_case(ns, "guard_multi", torch.cat([E0, E1, E2]), torch.cat([P0, P1, P2]), 0.01, 10, 25)
+    big_case(ns, "planted_cfg2", [{"family": "planted", "batch": 2, "n_points": 2048, "n_clusters": 16, "seed": 5}], 0.05, 10, 25)
+    noisy_case(ns)
+    big_case(ns, "planted_cfg4", [{"family": "planted", "batch": 1, "n_points": 10000, "n_clusters": 16, "seed": 3}], 0.05, 10, 50,
+             kcap=64, check_oracle=False)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
@@ -337,6 +405,9 @@ def main():
     if "--only-sampler" in sys.argv:
         sampler_case(ns)
         return
+    if "--round2" in sys.argv:                # round 2: full-size, guard-redo and noisy cases; earlier fixtures untouched
+        round2_cases(ns)
+        return
     entropy_case(ns)
     chamfer_case(ns)
     pointnet_case()
@@ -350,6 +421,7 @@ def main():
     pipeline_case(ns, "guard_small", E, P, 0.01, 10, 8)
     E, P = synthetic.random_shapes(1, n_points=256, seed=300)
     pipeline_case(ns, "random_small", E, P, 0.05, 5, 25)
+    round2_cases(ns)
 
 
 if __name__ == "__main__":

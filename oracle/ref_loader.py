@@ -16,7 +16,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("PRIFIT_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    """/root/reference in the build container; on the benchmark box the git-ignored copy __graft_entry__.build() left in
+    baseline/_ref (it travels with the tree like the built .so files do)."""
+    for cand in (os.environ.get("PRIFIT_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "src")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 _STUB_NAMES = [
     "open3d", "trimesh", "ipdb", "matplotlib", "matplotlib.pyplot", "matplotlib.cm",
@@ -49,8 +61,9 @@ def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "src"))
 
 
-def load():
-    """Import the reference hot-path modules; returns a namespace of them."""
+def load(force_cpu=False):
+    """Import the reference hot-path modules; returns a namespace of them.  force_cpu: make the reference's hard-coded
+    `.cuda()` calls the identity even on a machine that has a GPU (the CPU arm of the benchmark)."""
     import torch
 
     if not available():
@@ -61,7 +74,7 @@ def load():
                 importlib.import_module(name)
             except Exception:
                 sys.modules[name] = _Stub(name)
-    if not torch.cuda.is_available():
+    if force_cpu or not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)

@@ -24,15 +24,29 @@ _MIRRORS = {
 def install():
     """Make the reference's import paths (`from src.mean_shift import MeanShift`, `import convex_loss`,
     ...) resolve to this package, so the reference's training scripts run on the new path unmodified.
-    Call before the reference modules are imported."""
+    Call before the reference's hot-path modules are imported.  The reference's own `src` package stays
+    importable: every module that is not mirrored here (src.utils, src.VisUtils, src.sample_ellipsoid,
+    src.augment_utils, ...) still comes from the reference tree on sys.path."""
     import types
 
     if "src" not in sys.modules:
-        pkg = types.ModuleType("src")
-        pkg.__path__ = []
-        sys.modules["src"] = pkg
+        try:
+            importlib.import_module("src")                 # the reference's package (namespace or regular), if reachable
+        except ImportError:
+            pkg = types.ModuleType("src")                  # no reference tree on sys.path: mirrored modules only
+            pkg.__path__ = []
+            sys.modules["src"] = pkg
     for ref_name, ours in _MIRRORS.items():
         mod = importlib.import_module(ours)
         sys.modules[ref_name] = mod
         if ref_name.startswith("src."):
             setattr(sys.modules["src"], ref_name.split(".", 1)[1], mod)
+
+
+def bind_pointnet_ops(pointnet_util_module):
+    """Replace the geometric operators of the reference's models/pointnet_util.py (farthest_point_sample,
+    query_ball_point and the 3-NN interpolation inside PointNetFeaturePropagation) with the device kernels of
+    csrc/pointnet.cu, in place, on the module object the reference's models import."""
+    from . import pointnet_util as ours
+
+    ours.bind(pointnet_util_module)

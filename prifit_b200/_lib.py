@@ -64,7 +64,7 @@ SIGNATURES = {
 }
 
 FIT_CTX = 48
-MS_TF32_TCGEN05 = 0
+MS_F16_TCGEN05 = 0
 MS_FP32_SIMT = 1
 ROWS_SPLIT_TCGEN05 = 0
 ROWS_FP32_SIMT = 1

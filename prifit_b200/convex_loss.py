@@ -3,11 +3,13 @@
     convex_loss                     reference :27-103   normalise -> cluster -> fit -> loss
     compute_sdf_ellipsoid[s][_batch] reference :313-343
 
-Scope: by default the fitting loss computed here is the analytic SDF half of
-`analytic_chamfer_distance` (src/utils.py:407-411,418,425) evaluated on `chamfer_points`; `full_chamfer=True` adds the
-sampled-surface half (device sampler + nearest-neighbour kernel in place of trimesh + an sklearn KD-tree on the CPU,
-src/utils.py:413-416, src/sample_ellipsoid.py); the entropy regulariser (include_entropy_loss, :59-62,
-:209-225) is built (csrc/entropy.cu); the intersection / pruning / cuboid terms are out of scope and raise.
+The fitting loss is the reference's: `analytic_chamfer_distance` (src/utils.py:384-426) = 1/2 [SDF half on
+`chamfer_points`] + 1/2 [sampled-surface -> nearest chamfer point], the second half with a device sampler + a
+nearest-neighbour kernel in place of trimesh + an sklearn KD-tree on the CPU (src/utils.py:413-416,
+src/sample_ellipsoid.py).  `full_chamfer=False` (or PRIFIT_FULL_CHAMFER=0) is an explicit opt-in to the SDF half alone --
+the deterministic term the hot-path benchmark is defined on, replayed as CUDA graphs.  The entropy
+regulariser (include_entropy_loss, :59-62, :209-225) and the intersection term (include_intersect_loss, v4, :346-441)
+are built; pruning / cuboids are out of scope and raise.
 """
 import os
 
@@ -19,48 +21,48 @@ from .ellipsoid_fitting import ParamsBatch
 from .ellipsoid_utils import meanshift
 
 
+def _world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, quantile=0.01, iterations=5,
                 visualize=False, max_num_clusters=25, class_list=[], include_intersect_loss=False, alpha=1, beta=1,
                 if_cuboid=False, include_pruning=False, include_entropy_loss=False, evaluation=False, dist_reduce=False,
                 full_chamfer=None):
     """points[B,3,N], chamfer_points[B,3,M], X[B,128,N] -> (total[1,1], l[1,1], params, labels).
 
-    Same signature, defaults and return structure as the reference.  `params` is a lazy sequence of
-    per-shape lists of (s, V, center); `labels` a list of int64 [N] tensors.
+    Same signature, defaults, return structure and -- by default -- the same objective as the reference.  `params` is a
+    lazy sequence of per-shape lists of (s, V, center); `labels` a list of int64 [N] tensors.
+
+    full_chamfer (extension; None = PRIFIT_FULL_CHAMFER, default ON): True = the reference's complete
+    analytic_chamfer_distance (:68-89): surface points sampled on the predicted ellipsoids on the device
+    (ellipsoid_utils.sample_from_pred_params) and their nearest chamfer points, plus the SDF half (the sampler's random
+    stream differs from trimesh's).  False = the SDF half alone, i.e. l = 1/2 mean_j min_k |sdf|^2 WITHOUT
+    the sampled term: a different objective, for callers that ask for it explicitly (the hot-path benchmark; fastest,
+    CUDA-graph replayed).
 
     dist_reduce (extension, one process per GPU): the batch mean runs over the shapes of every rank (one 8-byte
-    all-reduce, train_partseg_shapenet.py:445 takes the mean of the replica losses); `total` is then this rank's share
-    sum_local / n_global -- calling backward() on it on every rank gives the gradient of the global mean -- and `l` the
-    global mean itself.
-
-    full_chamfer (extension; default from PRIFIT_FULL_CHAMFER, off): the fitting loss becomes the reference's complete
-    analytic_chamfer_distance (:68-89) -- surface points sampled on the predicted ellipsoids on the device
-    (ellipsoid_utils.sample_from_pred_params) and their nearest chamfer points, plus the SDF half -- instead of the SDF half
-    alone.  Eager path; the sampler's random stream differs from trimesh's."""
-    if include_intersect_loss or include_pruning or if_cuboid:
-        raise NotImplementedError("intersection / pruning / cuboid terms are outside the accelerated path")
+    all-reduce; train_partseg_shapenet.py:445 takes the mean of the replica losses); `total` is then this rank's share
+    of the global objective -- fitting term sum_local / n_global, regularisers / world_size -- so that backward() on every
+    rank followed by a SUM of the gradients gives the gradient of the mean of the replica losses; `l` is the global mean
+    of the fitting term."""
+    if include_pruning or if_cuboid:
+        raise NotImplementedError("pruning / cuboid terms are outside the accelerated path")
+    if full_chamfer is None:
+        full_chamfer = os.environ.get("PRIFIT_FULL_CHAMFER", "1") != "0"
+    if visualize and dist_reduce:
+        raise NotImplementedError("visualize=True (one-hot memberships, evaluation only) does not take dist_reduce")
     # channel-last views (reference :37,38,84); the pipeline copies them into its own row-major buffers, so the
     # transposition costs no separate pass
     E = X.permute(0, 2, 1)
     P = points.permute(0, 2, 1)
     Q = None if evaluation or chamfer_points is points else chamfer_points.permute(0, 2, 1)
-    if full_chamfer is None:
-        full_chamfer = os.environ.get("PRIFIT_FULL_CHAMFER", "0") == "1"
-    if full_chamfer and not evaluation and not visualize:
-        from .ellipsoid_utils import sample_from_pred_params
-        from .utils import analytic_chamfer_distance
-        entropy_term = None
-        if include_entropy_loss:                              # reference :59-62: drawn before the clustering
-            sub = np.random.choice(X.shape[2], X.shape[2] // 4, replace=False)
-            entropy_term = entropy(ops.NormalizeTwice.apply(E.contiguous()), sub)
-        out = pipeline.fit_loss(E, P, quantile=quantile, iterations=iterations, max_num_clusters=max_num_clusters,
-                                Q=Q, engine=meanshift.engine, graph=False)
-        res = out["cluster"]
-        params = ParamsBatch(out["s"], out["V"], out["c"], out["valid"], res.K, res.K_host)
-        resampled = sample_from_pred_params(params, N, batch_id=batch_id, seed=seed)                    # reference :71
-        l = analytic_chamfer_distance(params, resampled, (P if Q is None else Q).contiguous())          # reference :89
-        total = l if entropy_term is None else l + beta * entropy_term
-        return total.view(1, 1), l.view(1, 1), params, list(res.labels.long().unbind(0))
+    share = 1.0 / _world() if dist_reduce else 1.0        # a regulariser's weight in this rank's share of the objective
+    entropy_loss = None
+    if include_entropy_loss:                              # reference :59-62: drawn BEFORE the clustering (host RNG order)
+        sub_sample_indices = np.random.choice(X.shape[2], X.shape[2] // 4, replace=False)
+        entropy_loss = entropy(ops.NormalizeTwice.apply(E.contiguous()), sub_sample_indices)      # reference :41,57
     if visualize:
         # reference :68 -> src/ellipsoid_utils.py:48-54: one-hot arg-max memberships instead of the soft ones; the
         # stage-by-stage route (clustering -> fit -> SDF loss) handles it, no gradient reaches X through one-hot weights
@@ -72,25 +74,46 @@ def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, 
         params = weighted_ellipsoid_fitting_batch(P.contiguous(), weights)
         l = sdf_fitting_loss((P if Q is None else Q).contiguous(), params) if not evaluation else \
             torch.zeros(1, device=E.device, requires_grad=True)
-        return l.view(1, 1), l.view(1, 1), params, labels
-    entropy_loss = None
-    if include_entropy_loss:                                  # reference :59-62 (same host RNG call), entropy() :209-225
-        sub_sample_indices = np.random.choice(X.shape[2], X.shape[2] // 4, replace=False)
-        entropy_loss = entropy(ops.NormalizeTwice.apply(E.contiguous()), sub_sample_indices)      # reference :41,57
-    # the regulariser reaches X beside the fitting loss, so this case takes the eager autograd path
+        total = l
+        if entropy_loss is not None:
+            total = total + beta * entropy_loss
+        if include_intersect_loss:
+            total = total + alpha * intersection_loss(params)
+        return total.view(1, 1), l.view(1, 1), params, labels
+    # the regularisers reach X / the parameters beside the fitting loss, so those cases take the eager autograd path
+    eager = full_chamfer or include_entropy_loss or include_intersect_loss
     out = pipeline.fit_loss(E, P, quantile=quantile, iterations=iterations, max_num_clusters=max_num_clusters,
-                            Q=Q, engine=meanshift.engine, graph=False if include_entropy_loss else None,
-                            dist_reduce=dist_reduce)
+                            Q=Q, engine=meanshift.engine, graph=False if eager else None,
+                            dist_reduce=dist_reduce and not full_chamfer)
     res = out["cluster"]
     params = ParamsBatch(out["s"], out["V"], out["c"], out["valid"], res.K, res.K_host)
     labels = list(res.labels.long().unbind(0))
-    l = out["loss"] if not evaluation else torch.zeros(1, device=E.device, requires_grad=True)   # reference :92-94
-    total = l
-    if dist_reduce and not evaluation:
-        total, l = out["loss_backward"], out["loss_global"]
-    if entropy_loss is not None:
-        total = total + beta * entropy_loss                            # reference :100 (intersection term not built)
+    if evaluation:                                                                                  # reference :92-94
+        l = total = torch.zeros(1, device=E.device, requires_grad=True)
+    elif full_chamfer:
+        from .ellipsoid_utils import sample_from_pred_params
+        from .utils import analytic_chamfer_distance
+        resampled = sample_from_pred_params(params, N, batch_id=batch_id, seed=seed)                    # reference :71
+        l = total = analytic_chamfer_distance(params, resampled, (P if Q is None else Q).contiguous())  # reference :89
+        if dist_reduce:
+            # mean over the shapes of every rank that have a fitted ellipsoid (src/utils.py:425 over the global batch)
+            from . import dist as pdist
+            l, total = pdist.global_mean_from_local(l, out["n_valid"].detach())
+    else:
+        l = total = out["loss"]
+        if dist_reduce:
+            total, l = out["loss_backward"], out["loss_global"]
+    if entropy_loss is not None and not evaluation:
+        total = total + (beta * share) * entropy_loss                                               # reference :96-100
+    if include_intersect_loss and not evaluation:
+        total = total + (alpha * share) * intersection_loss(params)                                 # reference :95-100
     return total.view(1, 1), l.view(1, 1), params, labels
+
+
+def intersection_loss(params):
+    """Ellipsoid-ellipsoid intersection penalty of the reference (v4, :346-441); see ops.IntersectionLoss."""
+    from .intersect import intersection_loss_v4
+    return intersection_loss_v4(params)
 
 
 def entropy(X, sub_sample_indices=None):

@@ -74,9 +74,6 @@ __global__ void to_half_kernel(const float4* __restrict__ in, uint2* __restrict_
     }
 }
 
-// DBG (timing experiments only, results are meaningless for DBG != 0): 1 = no ex2, 2 = no tcgen05.ld of S,
-// 3 = no tcgen05.ld / ex2 / tcgen05.st at all (the softmax warps only relay the barriers).
-template <int DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
     const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ Xh, const float* __restrict__ bw,
     int N, int T, float* __restrict__ newX) {
@@ -190,24 +187,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
                 tc_fence_after();
                 const uint32_t sbase = tmem + lane_base + COL_S0 + buf * 128 + 64 * half;
                 const int key0 = j * TC_BN + 64 * half;
-                if (DBG < 2) {
-                    tmem_ld32(sbase, v[0]);
-                    tmem_ld32(sbase + 32, v[1]);
-                    tmem_wait_ld();
-                }
+                tmem_ld32(sbase, v[0]);
+                tmem_ld32(sbase + 32, v[1]);
+                tmem_wait_ld();
                 // P = 2^10 exp(clamp((s-1)/bw^2, -13, .)) packed as f16 pairs over the first 32 of this
                 // thread's own 64 S columns (already in registers); padded keys weigh nothing
-                if (DBG == 3) {
-                } else if (key0 + 64 <= N) {
+                if (key0 + 64 <= N) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
                             const float x0 = fmaxf(fmaf(__uint_as_float(v[c][2 * e]), c1, c0), lo2);
                             const float x1 = fmaxf(fmaf(__uint_as_float(v[c][2 * e + 1]), c1, c0), lo2);
-                            const float p0 = DBG == 1 ? x0 : ex2_approx(x0);
-                            const float p1 = DBG == 1 ? x1 : ex2_approx(x1);
-                            h[e] = pack_f16x2(p0, p1);
+                            h[e] = pack_f16x2(ex2_approx(x0), ex2_approx(x1));
                         }
                         tmem_st16(sbase + 16 * c, h);
                     }
@@ -267,347 +259,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
                 mbar_arrive(&bars->q_full);
             }
         }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
-}
-
-// --------------------------------------------------------------------------------------------------
-// Work-unit variant.  One CTA per 128-row tile for all T iterations leaves a partial last wave: 24 shapes x 16 tiles =
-// 384 CTAs are 2.59 waves of 148 SMs, and since every CTA takes the same time the kernel lasts 3 CTA times (14 % of the
-// SM time idle).  Here the unit of work is (row tile, ONE iteration), 10x finer: persistent CTAs (one per SM) draw units
-// from a global counter in iteration-major order, the normalised rows leave each unit as an fp16 tile in global memory
-// (32 KB, L2 resident) and a per-tile flag says which iteration is complete.  Unit (tile, t) is drawn 384 units after
-// (tile, t - 1), i.e. 2.6 unit times later, so the flag wait never spins in practice; it cannot deadlock either, because a
-// unit's predecessor was drawn earlier, by a CTA that is already running.  Same arithmetic, same results.
-// Extra warp role: lane 0 of warp 2 draws the units and hands them to the TMA / MMA / softmax threads through a
-// two-slot ring of mbarriers, so every role can run ahead into the next unit (the TMA producer prefetches its key tiles).
-// Pipelining across the unit boundary: two Q tiles in shared memory and two O accumulators in tensor memory
-// (S0 | S1 | O0 | O1 = 512 columns), so the first S tiles of unit s + 1 are computed and soft-maxed while the epilogue of unit
-// s (norm of O, write-back) runs; the next unit's rows are fetched two key tiles before the boundary.
-constexpr int TU_STAGES = 4;
-struct TuBarriers {
-    uint64_t x_full[TU_STAGES];
-    uint64_t x_empty[TU_STAGES];
-    uint64_t s_full[2];
-    uint64_t p_full[2];
-    uint64_t o_full[2];
-    uint64_t q_full[2];
-    uint64_t u_full[2];
-    uint64_t u_empty[2];
-    uint32_t tmem_base;
-    int32_t unit[2];
-    float ssum[2][2][TC_BM];
-};
-constexpr uint32_t TU_CONSUMERS = TC_SOFTMAX + 2;            // softmax threads + the TMA thread + the MMA thread
-constexpr size_t TU_SMEM_BYTES = 1024 + (size_t)TU_STAGES * TC_TILE_BYTES + 2 * TC_Q_BYTES + sizeof(TuBarriers);
-constexpr uint32_t TU_COL_O = 256;                           // O[ob] at TU_COL_O + 128 * ob
-
-__device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// AND-reduction of a predicate over the 256 softmax threads (named barrier 1)
-__device__ __forceinline__ bool softmax_all(bool pred) {
-    uint32_t r;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.and.pred q, 1, 256, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
-                 : "=r"(r) : "r"((uint32_t)pred) : "memory");
-    return r != 0;
-}
-__device__ __forceinline__ void st_release_gpu(int32_t* p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_units_kernel(
-    const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ Xh, const float* __restrict__ bw,
-    int N, int T, int B, __half* __restrict__ Qbuf, int32_t* __restrict__ flags, int32_t* __restrict__ counter,
-    float* __restrict__ newX) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* tiles = smem;
-    uint8_t* qtiles = smem + (size_t)TU_STAGES * TC_TILE_BYTES;          // two Q tiles
-    TuBarriers* bars = reinterpret_cast<TuBarriers*>(qtiles + 2 * TC_Q_BYTES);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nt = (N + TC_BN - 1) / TC_BN;
-    const int ntot = B * nt, total = ntot * T;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < TU_STAGES; ++s) { mbar_init(&bars->x_full[s], 1); mbar_init(&bars->x_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], TC_SOFTMAX);
-            mbar_init(&bars->o_full[s], 1); mbar_init(&bars->q_full[s], TC_SOFTMAX);
-            mbar_init(&bars->u_full[s], 1); mbar_init(&bars->u_empty[s], TU_CONSUMERS);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 0 && lane == 0) prefetch_tensormap(&tmap);
-    if (warp == 2) { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-
-    // step s of every role reads the unit published in slot s & 1
-    auto next_unit = [&](uint32_t s) -> int {
-        const uint32_t slot = s & 1;
-        mbar_wait(&bars->u_full[slot], (s >> 1) & 1);
-        const int u = *reinterpret_cast<volatile int32_t*>(&bars->unit[slot]);
-        mbar_arrive(&bars->u_empty[slot]);
-        return u;
-    };
-
-    if (warp == 2) {
-        // ================================ unit scheduler ===============================
-        if (lane == 0) {
-            for (uint32_t s = 0;; ++s) {
-                const uint32_t slot = s & 1;
-                mbar_wait(&bars->u_empty[slot], ((s >> 1) & 1) ^ 1);
-                int u = atomicAdd(counter, 1);
-                if (u >= total) u = -1;
-                *reinterpret_cast<volatile int32_t*>(&bars->unit[slot]) = u;
-                mbar_arrive(&bars->u_full[slot]);
-                if (u < 0) break;
-            }
-        }
-    } else if (warp == 0) {
-        // ================================ TMA producer ================================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (uint32_t s = 0;; ++s) {
-                const int u = next_unit(s);
-                if (u < 0) break;
-                const int b = (u % ntot) / nt;
-                for (int j = 0; j < nt; ++j, ++it) {
-                    const uint32_t st = it % TU_STAGES, ph = (it / TU_STAGES) & 1;
-                    mbar_wait(&bars->x_empty[st], ph ^ 1);
-                    mbar_arrive_expect_tx(&bars->x_full[st], TC_TILE_BYTES);
-                    const uint32_t dst = smem_u32(tiles + (size_t)st * TC_TILE_BYTES);
-                    tma_load_3d(dst, &tmap, &bars->x_full[st], 0, j * TC_BN, b);
-                    tma_load_3d(dst + TC_KBLOCK_BYTES, &tmap, &bars->x_full[st], 64, j * TC_BN, b);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ================================= MMA issuer =================================
-        // One flat stream of key tiles over all units of this CTA: G1(tile i + 1) is issued before G2(tile i), also across
-        // a unit boundary, where G1 reads the other Q tile and G2 accumulates into the other O.
-        if (lane == 0) {
-            constexpr uint32_t idesc1 = idesc_f16(TC_BM, TC_BN, false);   // S = Q . X^T   (B K-major)
-            constexpr uint32_t idesc2 = idesc_f16(TC_BM, TC_D, true);     // O += P . X    (B MN-major)
-            bool have_prev = false, prev_first = false, prev_last = false;
-            uint32_t prev_it = 0, prev_ob = 0;
-            auto gemm2_prev = [&]() {
-                const uint32_t st = prev_it % TU_STAGES, buf = prev_it & 1, ph = (prev_it >> 1) & 1;
-                mbar_wait(&bars->p_full[buf], ph);
-                tc_fence_after();
-                const uint32_t base = smem_u32(tiles + (size_t)st * TC_TILE_BYTES);
-#pragma unroll
-                for (int kk = 0; kk < TC_BN / 16; ++kk) {
-                    const uint64_t bd = smem_desc_sw128(base + kk * 2048, TC_KBLOCK_BYTES, 1024);
-                    mma_f16_ts(tmem + TU_COL_O + 128 * prev_ob, tmem + COL_S0 + buf * 128 + (kk >> 2) * 64 + (kk & 3) * 8, bd, idesc2,
-                               !(prev_first && kk == 0));
-                }
-                mma_commit(&bars->x_empty[st]);
-                if (prev_last) mma_commit(&bars->o_full[prev_ob]);
-                have_prev = false;
-            };
-            uint32_t it = 0;
-            int u = next_unit(0);
-            for (uint32_t s = 0; u >= 0; ++s) {
-                const uint32_t qb = s & 1;
-                // the next unit's Q normally arrives two key tiles before the boundary; if it does not (it may depend on
-                // the unit in flight), G2 of the last tile must not wait behind it
-                if (have_prev && !mbar_try_wait(&bars->q_full[qb], (s >> 1) & 1)) gemm2_prev();
-                mbar_wait(&bars->q_full[qb], (s >> 1) & 1);
-                tc_fence_after();
-                const uint32_t qbase = smem_u32(qtiles + (size_t)qb * TC_Q_BYTES);
-                for (int j = 0; j < nt; ++j, ++it) {
-                    const uint32_t st = it % TU_STAGES, xph = (it / TU_STAGES) & 1, buf = it & 1;
-                    mbar_wait(&bars->x_full[st], xph);
-                    tc_fence_after();
-                    const uint32_t base = smem_u32(tiles + (size_t)st * TC_TILE_BYTES);
-#pragma unroll
-                    for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t ad = smem_desc_sw128(qbase + kb * TC_KBLOCK_BYTES + ks * 32, 16, 1024);
-                            const uint64_t bd = smem_desc_sw128(base + kb * TC_KBLOCK_BYTES + ks * 32, 16, 1024);
-                            mma_f16_ss(tmem + COL_S0 + buf * 128, ad, bd, idesc1, (kb | ks) != 0);
-                        }
-                    mma_commit(&bars->s_full[buf]);
-                    if (have_prev) gemm2_prev();
-                    have_prev = true; prev_it = it; prev_ob = s & 1; prev_first = j == 0; prev_last = j == nt - 1;
-                }
-                u = next_unit(s + 1);
-            }
-            if (have_prev) gemm2_prev();
-        }
-    } else if (warp >= 4) {
-        // ============================= softmax / epilogue ==============================
-        const int ew = warp - 4, half = ew >> 2;
-        const int row = 32 * (ew & 3) + lane;
-        const uint32_t lane_base = (uint32_t)(32 * (ew & 3)) << 16;
-        const float lo2 = PRIFIT_LO * LOG2E + P_SCALE_LOG2;
-        uint32_t v[2][32], h[16];
-        // Q rows of a unit -> registers: the tile's own rows of X (t = 0) or the rows unit (tile, t - 1) left in Qbuf.
-        // blocking = false: give up (return false) when the predecessor unit is not complete yet.
-        uint4 qreg[8];
-        auto fetch_q = [&](int u, bool blocking) -> bool {
-            const int t = u / ntot, g = u - t * ntot, b = g / nt, r0 = (g - b * nt) * TC_BM;
-            const uint4* src;
-            bool take = true;
-            if (t == 0) {
-                take = r0 + row < N;
-                src = reinterpret_cast<const uint4*>(Xh + ((size_t)b * N + (take ? r0 + row : 0)) * TC_D) + 8 * half;
-            } else {
-                // one acquire load per warp (lane 0), handed to the other lanes by the shuffle's warp synchronisation
-                int ready = lane == 0 ? (ld_acquire_gpu(flags + g) >= t) : 0;
-                ready = __shfl_sync(0xffffffffu, ready, 0);
-                if (!ready) {
-                    if (!blocking) return false;
-                    const long long t0 = clock64();
-                    while (!ready) {
-                        ready = lane == 0 ? (ld_acquire_gpu(flags + g) >= t) : 0;
-                        ready = __shfl_sync(0xffffffffu, ready, 0);
-                        if (clock64() - t0 > 4000000000LL) { printf("prifit_b200: unit dependency wait timed out\n"); __trap(); }
-                    }
-                }
-                src = reinterpret_cast<const uint4*>(Qbuf + ((size_t)g * TC_BM + row) * TC_D) + 8 * half;
-            }
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                qreg[c] = make_uint4(0u, 0u, 0u, 0u);
-                if (take) qreg[c] = t == 0 ? __ldg(src + c) : __ldcg(src + c);     // Qbuf is written during this launch: L2 only
-            }
-            return true;
-        };
-        auto hand_over_q = [&](uint32_t qb) {     // registers -> swizzled Q tile qb in shared memory -> MMA warp
-            uint8_t* qrow = qtiles + (size_t)qb * TC_Q_BYTES + (size_t)half * TC_KBLOCK_BYTES + (size_t)row * 128;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(qrow + ((c ^ (row & 7)) << 4)) = qreg[c];
-            fence_proxy_async();
-            mbar_arrive(&bars->q_full[qb]);
-        };
-        int pub_g = -1, pub_t = 0;           // rows written to Qbuf whose flag is still to be published
-        auto publish = [&]() {               // every thread's stores happen-before thread 128's gpu-scope release
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (threadIdx.x == 128) st_release_gpu(flags + pub_g, pub_t);
-            pub_g = -1;
-        };
-        // epilogue of unit number es = (t, g): y' = O / ||O|| -> newX (last iteration) or Qbuf (+ flag, published later)
-        auto epilogue = [&](uint32_t es, int eu) {
-            const int t = eu / ntot, g = eu - t * ntot, b = g / nt, r0 = (g - b * nt) * TC_BM;
-            const uint32_t ob = es & 1;
-            mbar_wait(&bars->o_full[ob], (es >> 1) & 1);
-            tc_fence_after();
-            tmem_ld32(tmem + lane_base + TU_COL_O + 128 * ob + 64 * half, v[0]);
-            tmem_ld32(tmem + lane_base + TU_COL_O + 128 * ob + 64 * half + 32, v[1]);
-            tmem_wait_ld();
-            tc_fence_before();
-            float ss = 0.f;
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-                for (int e = 0; e < 32; ++e) ss = fmaf(__uint_as_float(v[c][e]), __uint_as_float(v[c][e]), ss);
-            bars->ssum[ob][half][row] = ss;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float inv = 1.0f / sqrtf(bars->ssum[ob][0][row] + bars->ssum[ob][1][row]);
-            if (t == T - 1) {
-                if (r0 + row < N) {
-                    float4* orow = reinterpret_cast<float4*>(newX + ((size_t)b * N + r0 + row) * TC_D) + 16 * half;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            orow[c * 8 + e] = make_float4(__uint_as_float(v[c][4 * e]) * inv, __uint_as_float(v[c][4 * e + 1]) * inv,
-                                                          __uint_as_float(v[c][4 * e + 2]) * inv, __uint_as_float(v[c][4 * e + 3]) * inv);
-                }
-            } else {
-                uint4* dst = reinterpret_cast<uint4*>(Qbuf + ((size_t)g * TC_BM + row) * TC_D) + 8 * half;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        h[e] = pack_f16x2(__uint_as_float(v[c][2 * e]) * inv, __uint_as_float(v[c][2 * e + 1]) * inv);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) __stcg(dst + 4 * c + q, make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]));
-                }
-                pub_g = g; pub_t = t + 1;
-            }
-        };
-
-        uint32_t it = 0;
-        int u = next_unit(0);
-        if (u >= 0) { fetch_q(u, true); hand_over_q(0); }
-        bool pe_valid = false;               // epilogue of the previous unit still to run (after this unit's first key tile)
-        uint32_t pe_s = 0;
-        int pe_u = 0;
-        for (uint32_t s = 0; u >= 0; ++s) {
-            const int t = u / ntot, g = u - t * ntot, b = g / nt;
-            const float bwv = bw[b];
-            const float c1 = LOG2E / (bwv * bwv), c0 = P_SCALE_LOG2 - c1;
-            int un = -1;
-            bool handed = false;
-            for (int j = 0; j < nt; ++j, ++it) {
-                // publish the previous unit's rows a few tiles after they were stored (the stores have landed by then)
-                if (pub_g >= 0 && (j == 2 || j == nt - 1)) publish();
-                if (j == max(nt - 2, 0)) {
-                    // the next unit's rows: fetched and handed to the MMA warp two key tiles before the boundary.  With many
-                    // row tiles the predecessor unit finished 2.6 unit times ago; with few it may be THIS unit: never block.
-                    un = next_unit(s + 1);
-                    if (un >= 0 && softmax_all(fetch_q(un, false))) { hand_over_q((s + 1) & 1); handed = true; }
-                }
-                const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-                mbar_wait(&bars->s_full[buf], ph);
-                tc_fence_after();
-                const uint32_t sbase = tmem + lane_base + COL_S0 + buf * 128 + 64 * half;
-                const int key0 = j * TC_BN + 64 * half;
-                tmem_ld32(sbase, v[0]);
-                tmem_ld32(sbase + 32, v[1]);
-                tmem_wait_ld();
-                if (key0 + 64 <= N) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const float x0 = fmaxf(fmaf(__uint_as_float(v[c][2 * e]), c1, c0), lo2);
-                            const float x1 = fmaxf(fmaf(__uint_as_float(v[c][2 * e + 1]), c1, c0), lo2);
-                            h[e] = pack_f16x2(ex2_approx(x0), ex2_approx(x1));
-                        }
-                        tmem_st16(sbase + 16 * c, h);
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            float p0 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[c][2 * e]), c1, c0), lo2));
-                            float p1 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[c][2 * e + 1]), c1, c0), lo2));
-                            if (key0 + 32 * c + 2 * e >= N) p0 = 0.f;
-                            if (key0 + 32 * c + 2 * e + 1 >= N) p1 = 0.f;
-                            h[e] = pack_f16x2(p0, p1);
-                        }
-                        tmem_st16(sbase + 16 * c, h);
-                    }
-                }
-                tmem_wait_st();
-                tc_fence_before();
-                mbar_arrive(&bars->p_full[buf]);
-                if (j == 0 && pe_valid) { epilogue(pe_s, pe_u); pe_valid = false; }
-            }
-            if (un >= 0 && handed) {
-                pe_valid = true; pe_s = s; pe_u = u;          // overlapped with the next unit's first key tile
-            } else {
-                epilogue(s, u);
-                if (pub_g >= 0) publish();                   // last unit of this CTA, or the next unit may depend on this one
-                if (un >= 0) { fetch_q(un, true); hand_over_q((s + 1) & 1); }
-            }
-            u = un;
-        }
-        if (pub_g >= 0) publish();
     }
     tc_fence_before();
     __syncthreads();
@@ -713,11 +364,8 @@ int convert_to_half(const float* X, __half* Xh, size_t n, cudaStream_t st) {
 int prifit_tc_convert_to_half(const float* X, __half* Xh, size_t n, cudaStream_t st) { return convert_to_half(X, Xh, n, st); }
 int prifit_tc_make_tile_map(CUtensorMap* map, const __half* X, int B, int N) { return make_tile_map(map, X, B, N); }
 
-// Xh | Qbuf (one fp16 tile per row tile) | flags (one per row tile) | unit counter
 size_t prifit_meanshift_tc_workspace_bytes(int B, int N) {
-    const size_t nt = (size_t)(N + TC_BM - 1) / TC_BM;
-    return (size_t)B * N * TC_D * sizeof(__half) + 256 + (size_t)B * nt * TC_BM * TC_D * sizeof(__half) + 256 +
-           ((size_t)B * nt + 1) * sizeof(int32_t) + 256;
+    return (size_t)B * N * TC_D * sizeof(__half) + 256;
 }
 
 int prifit_meanshift_fwd_tc(const float* X, const float* bw, int B, int N, int T, float* newX,
@@ -734,37 +382,8 @@ int prifit_meanshift_fwd_tc(const float* X, const float* bw, int B, int N, int T
     rc = make_tile_map(&map, Xh, B, N);
     if (rc) return rc;
     dim3 grid((N + TC_BM - 1) / TC_BM, B);
-    const char* e = getenv("PRIFIT_MS_DEBUG");
-    const int dbg = e ? atoi(e) : 0;
-    // PRIFIT_MS_UNITS=1 selects the work-unit kernel (no partial last wave, boundary pipelined).  Measured slower so far:
-    // cfg2 568-591 us against 551 us, cfg4 7.8-8.0 ms against 7.7 ms -- ncu: the same tensor-pipe cycles (425 k per SM) but
-    // 3.7 us of extra SM time per unit (profiles/r01_ncu_v12_meanshift_units.txt), so it stays an experiment.
-    const char* eu = getenv("PRIFIT_MS_UNITS");
-    const bool units = dbg == 0 && eu && atoi(eu) == 1;
-    if (units) {
-        const size_t nt = grid.x;
-        uint8_t* p = reinterpret_cast<uint8_t*>(Xh) + (size_t)B * N * TC_D * sizeof(__half);
-        __half* Qbuf = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(p) + 255) & ~(uintptr_t)255);
-        int32_t* flags = reinterpret_cast<int32_t*>((reinterpret_cast<uintptr_t>(Qbuf + (size_t)B * nt * TC_BM * TC_D) + 255) & ~(uintptr_t)255);
-        int32_t* counter = flags + (size_t)B * nt;
-        PF_CUDA(cudaMemsetAsync(flags, 0, ((size_t)B * nt + 1) * sizeof(int32_t), st));
-        static int n_sm = 0;
-        if (!n_sm) {
-            int dev = 0;
-            PF_CUDA(cudaGetDevice(&dev));
-            PF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        }
-        const int ctas = (int)min((size_t)n_sm, (size_t)B * nt);      // at most one unit per row tile can run at a time
-        PF_CUDA(cudaFuncSetAttribute(meanshift_tc_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TU_SMEM_BYTES));
-        meanshift_tc_units_kernel<<<ctas, TC_THREADS, TU_SMEM_BYTES, st>>>(map, Xh, bw, N, T, B, Qbuf, flags, counter, newX);
-        PF_LAUNCH_CHECK();
-        return 0;
-    }
-#define MS_LAUNCH(D)                                                                                                          \
-    do { PF_CUDA(cudaFuncSetAttribute(meanshift_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES)); \
-         meanshift_tc_kernel<D><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map, Xh, bw, N, T, newX); } while (0)
-    if (dbg == 1) MS_LAUNCH(1); else if (dbg == 2) MS_LAUNCH(2); else if (dbg == 3) MS_LAUNCH(3); else MS_LAUNCH(0);
-#undef MS_LAUNCH
+    PF_CUDA(cudaFuncSetAttribute(meanshift_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    meanshift_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map, Xh, bw, N, T, newX);
     PF_LAUNCH_CHECK();
     return 0;
 }

@@ -133,10 +133,13 @@ __global__ void __launch_bounds__(1024) nms_compact_kernel(const int32_t* __rest
     if (tid == 0) K_out[b] = base_s;
 }
 
-// labels[j] = argmax_k <newX[idx[k]], newX[j]>, lowest k on ties; used[b][k] = 1 if some point took label k
+// labels[j] = argmax_k <newX[idx[k]], newX[j]>, lowest k on ties; used[b][k] = 1 if some point took label k.
+// idx is the FULL ascending list of centres (stride N): a shape may have more centres than the padded capacity of the
+// differentiable stages and still pass the guard, which counts distinct labels (src/ellipsoid_utils.py:23); the label pass
+// therefore runs over every centre, like the reference's (src/mean_shift.py:200-201).
 template <int D>
 __global__ void __launch_bounds__(RG_THREADS) nms_label_kernel(
-    const float* __restrict__ Xn, int N, int Kcap, const int32_t* __restrict__ idx, const int32_t* __restrict__ Kfound,
+    const float* __restrict__ Xn, int N, const int32_t* __restrict__ idx, const int32_t* __restrict__ Kfound,
     int32_t* __restrict__ labels, int32_t* __restrict__ used) {
     constexpr int LD = D + 4;
     extern __shared__ __align__(16) float smem[];
@@ -147,8 +150,8 @@ __global__ void __launch_bounds__(RG_THREADS) nms_label_kernel(
     const int b = blockIdx.y, j0 = blockIdx.x * RG_KEYS;
     const float* Xb = Xn + (size_t)b * N * D;
     const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
-    const int Kb = min(Kfound[b], Kcap);
-    const int32_t* idx_b = idx + (size_t)b * Kcap;
+    const int Kb = Kfound[b];
+    const int32_t* idx_b = idx + (size_t)b * N;
 
     rg_load_rows<D>(xs, RG_KEYS, Xb, [&](int r) -> long long { return j0 + r < N ? (long long)(j0 + r) : -1; });
     float bestv[4];
@@ -183,25 +186,34 @@ __global__ void __launch_bounds__(RG_THREADS) nms_label_kernel(
             if (gt_max(v, i, bv, bi)) { bv = v; bi = i; }
         }
         labels[(size_t)b * N + j0 + tid] = bi;
-        used[(size_t)b * 64 + bi] = 1;
+        used[(size_t)b * N + bi] = 1;
     }
 }
 
-__global__ void nms_nlabels_kernel(const int32_t* __restrict__ used, const int32_t* __restrict__ Kfound, int Kcap,
-                                   int32_t* __restrict__ n_labels) {
+// n_labels[b] = number of distinct labels (exact, also when there are more centres than Kcap); idx_out[b][:Kcap] = the
+// first Kcap centres of the full list, -1 padded
+__global__ void __launch_bounds__(256) nms_nlabels_kernel(const int32_t* __restrict__ used, const int32_t* __restrict__ Kfound,
+                                                          const int32_t* __restrict__ idx_full, int N, int Kcap,
+                                                          int32_t* __restrict__ idx_out, int32_t* __restrict__ n_labels) {
     const int b = blockIdx.x;
     const int Kf = Kfound[b];
     int v = 0;
-    if ((int)threadIdx.x < min(Kf, Kcap)) v = used[(size_t)b * 64 + threadIdx.x] ? 1 : 0;
-    const unsigned b0 = __ballot_sync(0xffffffffu, v);
-    __shared__ int s[2];
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = __popc(b0);
+    for (int k = threadIdx.x; k < Kf; k += blockDim.x) v += used[(size_t)b * N + k] ? 1 : 0;
+    for (int k = threadIdx.x; k < Kcap; k += blockDim.x) idx_out[(size_t)b * Kcap + k] = k < Kf ? idx_full[(size_t)b * N + k] : -1;
+    __shared__ int s[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
     __syncthreads();
-    if (threadIdx.x == 0) n_labels[b] = Kf > Kcap ? Kf : s[0] + s[1];
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += s[w];
+        n_labels[b] = t;
+    }
 }
 
 struct NmsWs {
-    int32_t *nearest, *votes, *best, *flags, *used, *rowsel, *nrows;
+    int32_t *nearest, *votes, *best, *flags, *used, *rowsel, *nrows, *idx_full;
 };
 
 NmsWs carve(void* ws, int B, int N) {
@@ -211,10 +223,11 @@ NmsWs carve(void* ws, int B, int N) {
     w.votes = p;                 // votes, flags, used are contiguous: one memset
     w.flags = p + bn;
     w.used = p + 2 * bn;
-    w.nearest = p + 2 * bn + (size_t)B * 64;
+    w.nearest = p + 3 * bn;
     w.best = w.nearest + bn;
     w.rowsel = w.best + bn;
-    w.nrows = w.rowsel + bn;
+    w.idx_full = w.rowsel + bn;
+    w.nrows = w.idx_full + bn;
     return w;
 }
 
@@ -226,7 +239,7 @@ int launch_nms(const float* newX, const float* bw, int B, int N, int Kcap, int32
     PF_CUDA(cudaFuncSetAttribute(nms_gram_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PF_CUDA(cudaFuncSetAttribute(nms_gram_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PF_CUDA(cudaFuncSetAttribute(nms_label_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PF_CUDA(cudaMemsetAsync(w.votes, 0, (2 * (size_t)B * N + (size_t)B * 64) * sizeof(int32_t), st));
+    PF_CUDA(cudaMemsetAsync(w.votes, 0, 3 * (size_t)B * N * sizeof(int32_t), st));
     dim3 gt((N + RG_KEYS - 1) / RG_KEYS, B), ge((N + 255) / 256, B);
     const bool tc = D == 128 && prifit_gram_engine() == 0;      // Gram passes on the tensor cores (gram_tc.cu)
     __half* Xh = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(w.nrows + B) + 255) & ~(uintptr_t)255);
@@ -253,11 +266,11 @@ int launch_nms(const float* newX, const float* bw, int B, int N, int Kcap, int32
     }
     nms_flag_kernel<<<ge, 256, 0, st>>>(w.votes, w.best, N, w.flags);
     PF_LAUNCH_CHECK();
-    nms_compact_kernel<<<B, 1024, 0, st>>>(w.flags, N, Kcap, idx_out, K_out);
+    nms_compact_kernel<<<B, 1024, 0, st>>>(w.flags, N, N, w.idx_full, K_out);
     PF_LAUNCH_CHECK();
-    nms_label_kernel<D><<<gt, RG_THREADS, smem, st>>>(newX, N, Kcap, idx_out, K_out, labels_out, w.used);
+    nms_label_kernel<D><<<gt, RG_THREADS, smem, st>>>(newX, N, w.idx_full, K_out, labels_out, w.used);
     PF_LAUNCH_CHECK();
-    nms_nlabels_kernel<<<B, 64, 0, st>>>(w.used, K_out, Kcap, n_labels_out);
+    nms_nlabels_kernel<<<B, 256, 0, st>>>(w.used, K_out, w.idx_full, N, Kcap, idx_out, n_labels_out);
     PF_LAUNCH_CHECK();
     return 0;
 }
@@ -265,8 +278,8 @@ int launch_nms(const float* newX, const float* bw, int B, int N, int Kcap, int32
 }  // namespace
 
 extern "C" size_t prifit_nms_workspace_bytes(int B, int N, int d) {
-    // votes, flags, used, nearest, best, rowsel, nrows | split fp16 rows (hi + lo) for the tensor-core Gram
-    return (5 * (size_t)B * N + (size_t)B * 64 + B) * sizeof(int32_t) + 256 + (d == 128 ? prifit_tc_gram_split_bytes(B, N) : 0);
+    // votes, flags, used, nearest, best, rowsel, idx_full, nrows | split fp16 rows (hi + lo) for the tensor-core Gram
+    return (7 * (size_t)B * N + B) * sizeof(int32_t) + 256 + (d == 128 ? prifit_tc_gram_split_bytes(B, N) : 0);
 }
 
 extern "C" int prifit_nms_fwd(const float* newX, const float* bw, int B, int N, int d, int Kcap,

@@ -1,6 +1,6 @@
 // Thin inline-PTX layer for the Blackwell (sm_100a) features the tensor-core kernels use:
 // mbarrier, TMA (cp.async.bulk.tensor), TMEM allocation / tcgen05.ld / tcgen05.st, tcgen05.mma
-// (kind::tf32) and its shared-memory / instruction descriptors.
+// (kind::f16) and its shared-memory / instruction descriptors.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -123,15 +123,6 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
     d |= (uint64_t)2 << 61;          // SWIZZLE_128B
     return d;
 }
-// Instruction descriptor for kind::tf32, fp32 accumulate, A K-major (from TMEM or smem).
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool b_mn_major) {
-    return (1u << 4)                  // D format f32
-         | (2u << 7)                  // A format tf32
-         | (2u << 10)                 // B format tf32
-         | ((b_mn_major ? 1u : 0u) << 16)
-         | ((uint32_t)(N >> 3) << 17)
-         | ((uint32_t)(M >> 4) << 24);
-}
 // Instruction descriptor for kind::f16 with fp16 operands, fp32 accumulate, A K-major.
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool b_mn_major) {
     return (1u << 4)                  // D format f32;  A/B format fields 0 = f16
@@ -157,34 +148,11 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem desc]
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
-        : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]
-__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
-        : "memory");
-}
 // mbarrier arrives once all tcgen05.mma issued so far by this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ uint32_t to_tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
 __device__ __forceinline__ float ex2_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

@@ -22,6 +22,7 @@ small ones (losses, cluster lists, labels, ellipsoid parameters) are snapshotted
 """
 import os
 
+import numpy as np
 import torch
 
 from . import _lib, ops
@@ -292,10 +293,10 @@ class GraphStep:
         state = self._state
         if state is not None:
             torch.set_rng_state(state)
-        if max(nlab_host) > self.kmax:                     # src/ellipsoid_utils.py:23-24 -> redo on the eager path
+        if max(nlab_host) > self.kmax or max(K_host) > self.kcap:
+            # src/ellipsoid_utils.py:23-24 (quantile doubling), or a shape accepted with more centres than the padding
+            # holds (re-run in the 64-wide layout): both redo the step on the eager path
             return False
-        if max(K_host) > self.kcap:
-            raise _lib.PrifitError("%d cluster centres exceed the padded capacity %d" % (max(K_host), self.kcap))
         if state is not None:
             torch.rand(int(sum(K_host)), 3, 3)             # one rand(3, 3) per attempted cluster, like the reference
         out["K_host"], out["n_labels_host"] = K_host, nlab_host
@@ -366,7 +367,7 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
 
     B, N, d = E.shape
     engine = ops.DEFAULT_ENGINE if engine is None else engine
-    if engine == ops.MS_TF32_TCGEN05 and d != 128:
+    if engine == ops.MS_F16_TCGEN05 and d != 128:
         engine = ops.MS_FP32_SIMT                          # the tensor-core kernel is specialised for d = 128 (like ops.meanshift)
     rows_engine = ops._rows_engine(None, d)
     M = None if Q is None else Q.shape[1]
@@ -376,11 +377,14 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
     src = E.transpose(1, 2) if cf else E
     step = get_step(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, E.device,
                     default_branches() if branches is None else int(branches), cf)
+    np_state = np.random.get_state()
     res = step.run_forward(src.detach(), P.detach(), None if Q is None else Q.detach(), noise)
     loss_sum, loss = res["loss_sum"], res["loss"]
     if E.requires_grad and torch.is_grad_enabled():
         loss_sum, loss = _Attach.apply(src, step, res["serial"], loss_sum, loss)
+    pipeline.replay_shuffles(B, N)                         # host RNG parity (src/mean_shift.py:150) while graph 1 runs
     if not step.finish_forward(res):
+        np.random.set_state(np_state)                      # the eager redo replays the shuffles of every pass itself
         return None
     extra = {}
     if dist_reduce:

@@ -49,7 +49,7 @@ class _AllSeeds(torch.autograd.Function):
 class MeanShift:
     def __init__(self):
         """Differentiable mean-shift clustering on the unit hypersphere (https://arxiv.org/abs/1712.08273)."""
-        self.engine = None      # None = ops.DEFAULT_ENGINE (tcgen05 TF32); ops.MS_FP32_SIMT for the fp32 engine
+        self.engine = None      # None = ops.DEFAULT_ENGINE (tcgen05, f16 operands); ops.MS_FP32_SIMT for the fp32 engine
 
     # ---------------------------------------------------------------------------------------- API
     def mean_shift(self, X, num_samples, quantile, iterations, kernel_type="gaussian", bw=None, eff=False):

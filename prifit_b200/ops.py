@@ -18,11 +18,11 @@ import torch
 
 from . import _lib
 
-MS_TF32_TCGEN05 = _lib.MS_TF32_TCGEN05
+MS_F16_TCGEN05 = _lib.MS_F16_TCGEN05
 MS_FP32_SIMT = _lib.MS_FP32_SIMT
 
 # default mean-shift engine for the full N-seed pass (the K differentiable seeds are always fp32)
-DEFAULT_ENGINE = MS_TF32_TCGEN05
+DEFAULT_ENGINE = MS_F16_TCGEN05
 
 # engine of the K differentiable seeds' trajectories (forward and backward): split-fp16 tensor cores
 # (fp32-class) or fp32 CUDA cores.  PRIFIT_ROWS_ENGINE=1 in the environment selects the latter.
@@ -51,10 +51,14 @@ def _chk(t, dtype=torch.float32):
     return t.contiguous()
 
 
+KCAP_MAX = 64          # widest padded cluster list the K-seed / membership / fit / SDF kernels are built for
+
+
 def kcap_for(max_num_clusters):
-    if max_num_clusters > 64:
-        raise _lib.PrifitError("max_num_clusters > 64 is not supported by the padded layouts")
-    return 32 if max_num_clusters <= 32 else 64
+    """Padded width of the per-shape cluster lists: 32 up to 32 clusters, else 64.  max_num_clusters above 64 is accepted
+    (the guard then simply allows more labels) as long as every shape ends with at most 64 cluster CENTRES; a shape with
+    more raises pipeline.KcapOverflow -- the documented limit of the padded layouts."""
+    return 32 if max_num_clusters <= 32 else KCAP_MAX
 
 
 # ------------------------------------------------------------------------------------------ raw ops
@@ -106,7 +110,7 @@ def meanshift(X, bw, iterations, engine=None):
     X, bw = _chk(X), _chk(bw)
     B, N, d = X.shape
     engine = DEFAULT_ENGINE if engine is None else engine
-    if engine == MS_TF32_TCGEN05 and d != 128:
+    if engine == MS_F16_TCGEN05 and d != 128:
         engine = MS_FP32_SIMT          # the tensor-core kernel is specialised for d = 128
     nbytes = _lib.load().prifit_meanshift_workspace_bytes(B, N, d, engine)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=X.device)

@@ -12,6 +12,8 @@ per guard pass (the reference syncs ~30 times per shape).
 from dataclasses import dataclass, field
 from typing import List
 
+import os
+
 import numpy as np
 import torch
 
@@ -40,10 +42,37 @@ def _kth_tensor(quantiles, n_s, device):
     return torch.tensor([min(k, n_s) for k in ks], dtype=torch.int32).to(device, non_blocking=True)
 
 
+class KcapOverflow(_lib.PrifitError):
+    """A shape passed the guard (distinct labels <= max_num_clusters) with more cluster centres than the padded
+    capacity of the differentiable stages; carries the capacity that would hold it."""
+
+    def __init__(self, needed, kcap):
+        super().__init__("%d cluster centres exceed the padded capacity %d" % (needed, kcap))
+        self.needed = needed
+
+
+def replay_shuffles(count, N):
+    """compute_bandwidth shuffles arange(N) on the host once per call (src/mean_shift.py:148-151), i.e. once per
+    shape per guard pass.  With num_samples == N the bandwidth is permutation invariant and needs no permutation, but
+    every later consumer of NumPy's global generator (the entropy sub-sample, the sampler seed, the data augmentation)
+    sees the state those shuffles leave behind -- so they are replayed on a scratch array (the generator's consumption
+    does not depend on the array's content).  PRIFIT_REPLAY_SHUFFLE=0 skips them."""
+    if count <= 0 or os.environ.get("PRIFIT_REPLAY_SHUFFLE", "1") == "0":
+        return
+    L = _scratch.get(N)
+    if L is None:
+        L = _scratch[N] = np.arange(N)
+    for _ in range(count):
+        np.random.shuffle(L)
+
+
+_scratch = {}
+
+
 def _sample_rows(B, N, num_samples, device):
-    """Replays compute_bandwidth's host shuffle (src/mean_shift.py:148-151) when it matters, i.e. when
-    only a subset of the rows is used.  With num_samples == N the result is permutation invariant
-    and the shuffle is skipped (the host RNG stream is then not advanced; documented deviation)."""
+    """Replays compute_bandwidth's host shuffle (src/mean_shift.py:148-151) where its outcome matters, i.e. when only
+    a subset of the rows is used.  With num_samples == N the result is permutation invariant; the generator is then
+    advanced by replay_shuffles() off the critical path."""
     if num_samples >= N:
         return None
     rows = np.empty((B, num_samples), np.int32)
@@ -88,14 +117,14 @@ class _Counts:
 
 
 @torch.no_grad()
-def cluster_batch_begin(X, num_samples, quantile, iterations, max_num_clusters, engine=None):
+def cluster_batch_begin(X, num_samples, quantile, iterations, max_num_clusters, engine=None, kcap=None):
     """First guard pass of guard_mean_shift (src/ellipsoid_utils.py:9-27) for all shapes, enqueued without
     waiting for it: returns (ClusterResult with the device tensors of pass 1, pending counts).  The stages
     that only need device-side cluster lists can be enqueued behind it speculatively; cluster_batch_end()
     then reads the counts (the one host synchronisation of the pass) and runs the redo passes, if any."""
     X = ops._chk(X)
     B, N, d = X.shape
-    kcap = ops.kcap_for(max_num_clusters)
+    kcap = ops.kcap_for(max_num_clusters) if kcap is None else int(kcap)
     n_s = min(int(num_samples), N)
     bw, idx, K, labels, nlab = _cluster_pass(X, [float(quantile)] * B, n_s, iterations, kcap, engine)
     out = ClusterResult(bw=bw, idx=idx, K=K, labels=labels, K_host=[0] * B, n_labels_host=[0] * B, passes=[0] * B,
@@ -116,6 +145,8 @@ def cluster_batch_end(out: ClusterResult, pending) -> bool:
     active = list(range(B))
     redone = False
     while True:
+        if n_s >= N:
+            replay_shuffles(len(active), N)                     # host RNG parity, while the device works on the pass
         K_l, nlab_l = counts.wait()
         again = []
         for i, b in enumerate(active):
@@ -124,9 +155,9 @@ def cluster_batch_end(out: ClusterResult, pending) -> bool:
             if out.n_labels_host[b] > max_num_clusters:         # src/ellipsoid_utils.py:23-24
                 out.quantiles[b] *= 2
                 again.append(b)
-            elif out.K_host[b] > kcap:
-                raise _lib.PrifitError("shape %d: %d cluster centres exceed the padded capacity %d" % (b, out.K_host[b], kcap))
         if not again:
+            if max(out.K_host) > kcap:                          # accepted by the guard with more centres than the padding
+                raise KcapOverflow(max(out.K_host), kcap)
             return redone
         if not redone:                                          # pass-1 tensors may be shared with speculative work
             out.bw, out.idx, out.K, out.labels = out.bw.clone(), out.idx.clone(), out.K.clone(), out.labels.clone()
@@ -146,9 +177,19 @@ def cluster_batch_end(out: ClusterResult, pending) -> bool:
 def cluster_batch(X, num_samples, quantile, iterations, max_num_clusters, engine=None) -> ClusterResult:
     """guard_mean_shift (src/ellipsoid_utils.py:9-27) for all shapes at once: bandwidth -> T mean-shift
     iterations of all N seeds -> NMS; shapes whose label count exceeds max_num_clusters are re-run
-    with a doubled quantile."""
+    with a doubled quantile.  The guard counts distinct labels, so a shape may be accepted with more cluster centres than
+    labels (centres no point is closest to still get memberships and an ellipsoid, src/ellipsoid_utils.py:45); if they
+    exceed the 32-wide padding the batch is re-clustered into the 64-wide one (same result, host RNG rewound)."""
+    state = np.random.get_state()
     out, pending = cluster_batch_begin(X, num_samples, quantile, iterations, max_num_clusters, engine)
-    cluster_batch_end(out, pending)
+    try:
+        cluster_batch_end(out, pending)
+    except KcapOverflow as e:
+        if e.needed > ops.KCAP_MAX or out.kcap >= ops.KCAP_MAX:
+            raise
+        np.random.set_state(state)
+        out, pending = cluster_batch_begin(X, num_samples, quantile, iterations, max_num_clusters, engine, kcap=ops.KCAP_MAX)
+        cluster_batch_end(out, pending)
     return out
 
 
@@ -230,7 +271,7 @@ def _graph_ok(E, P, Q, noise, num_samples, kcap):
 
 
 def fit_loss(E, P, quantile=0.05, iterations=10, max_num_clusters=25, noise=None, Q=None, engine=None,
-             num_samples=None, graph=None, dist_reduce=False):
+             num_samples=None, graph=None, dist_reduce=False, kcap=None):
     """Whole hot path on a batch.  Returns dict(loss, loss_sum, n_valid, loss_b, has, s, V, c, valid, cluster, W, C, X).
 
     `loss` is differentiable w.r.t. E (and P/Q if they require grad).  graph=None/True replays the step as CUDA
@@ -243,15 +284,29 @@ def fit_loss(E, P, quantile=0.05, iterations=10, max_num_clusters=25, noise=None
 
     if graph is None:
         graph = graph_step.default_enabled()
-    if graph and _graph_ok(E, P, Q, noise, num_samples, ops.kcap_for(max_num_clusters)):
+    if graph and kcap is None and _graph_ok(E, P, Q, noise, num_samples, ops.kcap_for(max_num_clusters)):
         out = graph_step.fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, dist_reduce=dist_reduce)
         if out is not None:
             return out
+    if kcap is None:
+        # Rare: a shape accepted by the guard has more cluster centres than the 32-wide padding -> the step is redone in
+        # the 64-wide one (host generators rewound, so the outcome equals a first run at that width).
+        states = (np.random.get_state(), torch.get_rng_state())
+        try:
+            return fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, num_samples, False, dist_reduce,
+                            kcap=ops.kcap_for(max_num_clusters))
+        except KcapOverflow as e:
+            if e.needed > ops.KCAP_MAX or ops.kcap_for(max_num_clusters) >= ops.KCAP_MAX or noise is not None:
+                raise
+            np.random.set_state(states[0])
+            torch.set_rng_state(states[1])
+            return fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, num_samples, False, dist_reduce,
+                            kcap=ops.KCAP_MAX)
     X = ops.NormalizeTwice.apply(E)
     # the differentiable stages that only need the device-side cluster lists are enqueued behind pass 1 before
     # the host learns the counts; in the rare guard-redo case they are recomputed on the final clustering
     res, pending = cluster_batch_begin(X.detach(), X.shape[1] if num_samples is None else num_samples, quantile,
-                                       iterations, max_num_clusters, engine)
+                                       iterations, max_num_clusters, engine, kcap=kcap)
     W, C = soft_memberships(X, res)
     Qp = P if Q is None else Q
     spec = None

@@ -1,10 +1,11 @@
-"""Mirror of the geometric operators of the reference's models/pointnet_util.py (the stage in front of the fitting path).
+"""Device kernels for the geometric operators of the reference's models/pointnet_util.py (the stage in front of the
+fitting path) and the hook that binds them into the reference's module.
 
-    square_distance, index_points   reference :18-60     torch expressions (kept for API compatibility)
     farthest_point_sample           reference :63-84     csrc/pointnet.cu fps_kernel (one CTA per cloud)
     query_ball_point                reference :87-107    ball_query_kernel (no N-long sort per query)
     three_interpolate               reference :287-294   three_nn_kernel + interpolate kernels (no S-long sort per point)
-    sample_and_group                reference :110-136
+    bind(module)                    patches those three into the reference's module object (its grouping / gather helpers
+                                    and its nn.Modules stay the reference's own code)
 
 Index semantics are the reference's (first index on ties; ball query pads with the first hit).  CUDA fp32 tensors only.
 """
@@ -12,25 +13,6 @@ import torch
 
 from . import _lib, ops
 from .ops import _ptr, _stream
-
-
-def square_distance(src, dst):
-    """reference :18-41."""
-    B, N, _ = src.shape
-    _, M, _ = dst.shape
-    dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))
-    dist += torch.sum(src ** 2, -1).view(B, N, 1)
-    dist += torch.sum(dst ** 2, -1).view(B, 1, M)
-    return dist
-
-
-def index_points(points, idx):
-    """reference :44-60: points[B,N,C], idx[B,S...] -> [B,S...,C]."""
-    B = points.shape[0]
-    view_shape = [B] + [1] * (idx.dim() - 1)
-    repeat_shape = [1] + list(idx.shape[1:])
-    batch_indices = torch.arange(B, dtype=torch.long, device=points.device).view(view_shape).repeat(repeat_shape)
-    return points[batch_indices, idx, :]
 
 
 def farthest_point_sample(xyz, npoint, start=None):
@@ -98,19 +80,23 @@ def three_interpolate(xyz1, xyz2, points2):
     return _Interpolate.apply(points2, idx, weight)
 
 
-def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):
-    """reference :110-136."""
-    B, N, C = xyz.shape
-    S = npoint
-    fps_idx = farthest_point_sample(xyz, npoint)
-    new_xyz = index_points(xyz, fps_idx)
-    idx = query_ball_point(radius, nsample, xyz, new_xyz)
-    grouped_xyz = index_points(xyz, idx)
-    grouped_xyz_norm = grouped_xyz - new_xyz.view(B, S, 1, C)
-    if points is not None:
-        new_points = torch.cat([grouped_xyz_norm, index_points(points, idx)], dim=-1)
-    else:
-        new_points = grouped_xyz_norm
-    if returnfps:
-        return new_xyz, new_points, grouped_xyz, fps_idx
-    return new_xyz, new_points
+def _feature_propagation_forward(self, xyz1, xyz2, points1, points2):
+    """Drop-in for PointNetFeaturePropagation.forward (reference :275-302): channel-first in and out, the 3-NN
+    inverse-distance interpolation on the device kernels, the module's own 1x1 conv / batch-norm stack unchanged."""
+    feats = three_interpolate(xyz1.transpose(1, 2), xyz2.transpose(1, 2), points2.transpose(1, 2).contiguous())
+    x = feats.transpose(1, 2)
+    if points1 is not None:
+        x = torch.cat([points1, x], dim=1)
+    for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+        x = torch.relu(bn(conv(x)))
+    return x
+
+
+def bind(module):
+    """Patch the reference's models.pointnet_util module object in place: its farthest_point_sample / query_ball_point
+    and the interpolation inside PointNetFeaturePropagation run on the kernels above.  Returns the module."""
+    module.farthest_point_sample = farthest_point_sample
+    module.query_ball_point = query_ball_point
+    module.PointNetFeaturePropagation.forward = _feature_propagation_forward
+    module._prifit_b200_bound = True
+    return module

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Time the all-seed mean-shift kernel (tcgen05) on cfg2 / cfg4 shapes, with and without the FMA-pipe exp2."""
+"""Time the all-seed mean-shift kernel (tcgen05) on cfg2 / cfg4 shapes."""
 import os
 import sys
 
@@ -29,10 +29,8 @@ def main():
         X = ops.normalize_fwd(E.to(dev))
         bw = torch.full((B,), 0.15, device=dev)
         flops = 4.0 * N * N * 128 * 10 * B
-        for dbg in os.environ.get("DBG_LIST", "0").split(","):
-            os.environ["PRIFIT_MS_DEBUG"] = dbg
-            t = timeit(lambda: ops.meanshift(X, bw, 10, ops.MS_TF32_TCGEN05))
-            print("B=%d N=%d debug-variant=%s  %8.1f us  %.0f TFLOP/s" % (B, N, dbg, t, flops / t / 1e6), flush=True)
+        t = timeit(lambda: ops.meanshift(X, bw, 10, ops.MS_F16_TCGEN05))
+        print("B=%d N=%d  %8.1f us  %.0f TFLOP/s" % (B, N, t, flops / t / 1e6), flush=True)
 
 
 if __name__ == "__main__":

@@ -42,7 +42,7 @@ def pointnet():
     xyz = torch.rand(24, 2048, 3, device=dev) * 2 - 1
     start = torch.zeros(24, dtype=torch.long)
     print("fps 2048 -> 512   %7.1f us" % timeit(lambda: pu.farthest_point_sample(xyz, 512, start=start)))
-    new_xyz = pu.index_points(xyz, pu.farthest_point_sample(xyz, 512, start=start))
+    new_xyz = torch.gather(xyz, 1, pu.farthest_point_sample(xyz, 512, start=start).unsqueeze(-1).expand(-1, -1, 3))
     print("ball query r=0.2  %7.1f us" % timeit(lambda: pu.query_ball_point(0.2, 32, xyz, new_xyz)))
     feats = torch.randn(24, 512, 128, device=dev, requires_grad=True)
     print("3-NN interp fwd   %7.1f us" % timeit(lambda: pu.three_interpolate(xyz, new_xyz, feats)))

@@ -30,3 +30,17 @@ def axes_close(V_ours, V_ref, tol):
         if d > tol:
             return False, d
     return True, 0.0
+
+
+def partition_disagreement(a, b):
+    """Fraction of points on which two labelings disagree after the best one-to-one matching of their clusters
+    (0 = same partition up to relabelling; unmatched clusters count fully)."""
+    from scipy.optimize import linear_sum_assignment
+
+    a, b = np.asarray(a).astype(np.int64).ravel(), np.asarray(b).astype(np.int64).ravel()
+    ua, ia = np.unique(a, return_inverse=True)
+    ub, ib = np.unique(b, return_inverse=True)
+    C = np.zeros((len(ua), len(ub)), np.int64)
+    np.add.at(C, (ia, ib), 1)
+    r, c = linear_sum_assignment(-C)
+    return 1.0 - float(C[r, c].sum()) / len(a)

@@ -107,13 +107,10 @@ def _tc_or_skip(fn):
         raise
 
 
-@pytest.mark.parametrize("units", ["0", "1"])
 @pytest.mark.parametrize("n", [320, 2048, 1000])
-def test_meanshift_tcgen05_vs_fp32(cuda, golden_dir, n, units, monkeypatch):
-    """TF32 tensor-core engine against the fp32 engine: TF32 rounding of the 128-term dot products,
-    amplified by 1/bw^2 in the exponent, bounds the seed error by ~1e-4 absolute.
-    units = 1: the experimental work-unit kernel (dynamic (row tile, iteration) units, pipelined boundary)."""
-    monkeypatch.setenv("PRIFIT_MS_UNITS", units)
+def test_meanshift_tcgen05_vs_fp32(cuda, golden_dir, n):
+    """f16-operand tensor-core engine against the fp32 engine: the 10-bit-mantissa rounding of the 128-term dot products,
+    amplified by 1/bw^2 in the exponent, bounds the seed error by ~1e-4 absolute."""
     from prifit_b200 import ops, synthetic
 
     if n == 320:
@@ -125,7 +122,7 @@ def test_meanshift_tcgen05_vs_fp32(cuda, golden_dir, n, units, monkeypatch):
         X = R.normalize_twice(E)
         bw = torch.tensor([0.31, 0.45])
     a = ops.meanshift(X.to(cuda), bw.to(cuda), 10, ops.MS_FP32_SIMT)
-    b = _tc_or_skip(lambda: ops.meanshift(X.to(cuda), bw.to(cuda), 10, ops.MS_TF32_TCGEN05))
+    b = _tc_or_skip(lambda: ops.meanshift(X.to(cuda), bw.to(cuda), 10, ops.MS_F16_TCGEN05))
     assert float((a - b).abs().max()) < 2e-4
     assert float((b.norm(dim=-1) - 1).abs().max()) < 1e-5
 
@@ -598,7 +595,7 @@ def test_pointnet_ops_against_reference_fixture(cuda, golden_dir):
     xyz = torch.from_numpy(g["xyz"]).to(cuda)
     fps = pu.farthest_point_sample(xyz, g["fps"].shape[1], start=torch.from_numpy(g["start"]))
     assert torch.equal(fps.cpu(), torch.from_numpy(g["fps"]))
-    new_xyz = pu.index_points(xyz, fps)
+    new_xyz = torch.gather(xyz, 1, fps.unsqueeze(-1).expand(-1, -1, 3))
     ball = pu.query_ball_point(float(g["radius"]), int(g["nsample"]), xyz, new_xyz).cpu()
     ref_ball = torch.from_numpy(g["ball"])
     r2 = float(g["radius"]) ** 2

@@ -64,8 +64,8 @@ def test_kcap_and_kth():
     from prifit_b200 import _lib, ops, pipeline
 
     assert ops.kcap_for(25) == 32 and ops.kcap_for(32) == 32 and ops.kcap_for(50) == 64
-    with pytest.raises(_lib.PrifitError):
-        ops.kcap_for(65)
+    assert ops.kcap_for(65) == 64          # accepted: the limit is 64 cluster CENTRES per shape (pipeline.KcapOverflow)
+    assert issubclass(pipeline.KcapOverflow, _lib.PrifitError) and pipeline.KcapOverflow(70, 64).needed == 70
     assert pipeline._kth_tensor([0.05, 0.1], 2048, torch.device("cpu")).tolist() == [102, 204]
     with pytest.raises(_lib.PrifitError):
         pipeline._kth_tensor([1e-5], 2048, torch.device("cpu"))
@@ -136,6 +136,69 @@ def test_install_redirects_reference_imports():
                 sys.modules[k] = v
 
 
+def test_install_keeps_non_mirrored_reference_modules_importable(tmp_path):
+    """install() before anything of the reference is imported (the documented order): modules of the reference's `src`
+    package that are NOT mirrored (src.utils, src.VisUtils, src.sample_ellipsoid ...) must still import from the reference
+    tree on sys.path, next to the mirrored ones.  A miniature reference tree stands in for /root/reference."""
+    import importlib
+
+    import prifit_b200
+
+    tree = tmp_path / "reftree"
+    (tree / "src").mkdir(parents=True)
+    (tree / "src" / "__init__.py").write_text("")
+    (tree / "src" / "augment_extra.py").write_text("VALUE = 41\nfrom src.guard import guard_exp\n")
+    (tree / "src" / "mean_shift.py").write_text("raise ImportError('the reference module must not be imported after install()')\n")
+    saved = {k: sys.modules.get(k) for k in list(prifit_b200._MIRRORS) + ["src", "src.augment_extra"]}
+    for k in saved:
+        sys.modules.pop(k, None)
+    sys.path.insert(0, str(tree))
+    try:
+        importlib.invalidate_caches()
+        prifit_b200.install()
+        import src.augment_extra as extra                      # non-mirrored: from the tree
+        from src.mean_shift import MeanShift                   # mirrored: ours
+
+        assert extra.VALUE == 41 and extra.guard_exp.__module__ == "prifit_b200.guard"
+        assert MeanShift.__module__ == "prifit_b200.mean_shift"
+        assert sys.modules["src"].__file__ == str(tree / "src" / "__init__.py")
+    finally:
+        sys.path.remove(str(tree))
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_bandwidth_shuffle_replay_leaves_numpy_generator_like_the_reference():
+    """src/mean_shift.py:150 shuffles arange(N) once per compute_bandwidth call.  pipeline.replay_shuffles(count, N)
+    must leave NumPy's global generator exactly where `count` such calls leave it (it reuses a scratch array: the
+    generator's consumption does not depend on the array's content)."""
+    import numpy as np
+
+    from prifit_b200 import pipeline
+
+    for count, N in ((24, 2048), (3, 10000), (5, 7)):
+        np.random.seed(123)
+        for _ in range(count):
+            L = np.arange(N)
+            np.random.shuffle(L)
+        want = np.random.randint(0, 2 ** 31 - 1, size=4)
+        np.random.seed(123)
+        pipeline.replay_shuffles(count, N)
+        assert np.array_equal(np.random.randint(0, 2 ** 31 - 1, size=4), want)
+    np.random.seed(5)
+    os.environ["PRIFIT_REPLAY_SHUFFLE"] = "0"
+    try:
+        pipeline.replay_shuffles(3, 64)
+        got = np.random.randint(0, 1000)
+    finally:
+        del os.environ["PRIFIT_REPLAY_SHUFFLE"]
+    np.random.seed(5)
+    assert got == np.random.randint(0, 1000)
+
+
 _GLOO_WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, {root!r})
@@ -161,6 +224,21 @@ assert abs(float(L2) - float(ref)) < 1e-12
 assert torch.allclose(lb2.grad, has_all[lo:hi] / has_all.sum()), lb2.grad
 out["loss_global"], out["loss_backward"] = L2, Lb2
 assert pdist.global_loss(out)[0] is L2
+# reference semantics of the total objective (train_partseg_shapenet.py:445): mean over replicas of (l_r + beta * ent_r).
+# Every rank back-propagates its share  sum_local / n_global + (beta / world) * ent_r ; summing the gradients over the
+# ranks (what DDP / the all-reduce does) must give the gradient of that mean -- for equal shards with every shape valid.
+import prifit_b200.convex_loss as cl
+assert cl._world() == 2
+beta = 0.7
+x = torch.tensor([0.3, 1.1, 0.9], dtype=torch.float64) + rank
+xr = x.clone().requires_grad_(True)
+l_local = xr ** 2                                            # per-shape fitting losses of this rank (3 shapes each)
+ent = xr.sum() ** 2                                          # this replica's regulariser
+Lg, Lb3 = pdist.global_masked_mean(l_local, torch.ones(3, dtype=torch.float64))
+total = Lb3 + (beta * (1.0 / cl._world())) * ent
+total.backward()
+want = (2 * x / 3 + beta * 2 * x.sum()) / 2                 # d/dx of mean_r (mean(l_r) + beta ent_r)
+assert torch.allclose(xr.grad, want), (xr.grad, want)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """

@@ -72,7 +72,7 @@ def test_fit_known_answer(golden_dir):
         assert np.allclose(s.numpy(), g["planted"][k], rtol=0.02)
 
 
-@pytest.mark.parametrize("name", ["planted_small", "guard_small", "random_small"])
+@pytest.mark.parametrize("name", ["planted_small", "guard_small", "random_small", "guard_multi"])
 def test_pipeline_against_reference(golden_dir, name):
     g = _load(golden_dir, name)
     E, P = torch.from_numpy(g["E"]), torch.from_numpy(g["P"])
@@ -96,6 +96,81 @@ def test_pipeline_against_reference(golden_dir, name):
         assert np.abs(out["grad_E"].numpy() - g["grad32"]).max() <= 1e-3 * scale
     else:
         assert np.abs(out["grad_E"].numpy()).max() < 1e-6   # rounding residue of e / sum(e) with one cluster
+
+
+def test_guard_multi_fixture_ends_with_several_clusters(golden_dir):
+    """The round-2 guard fixture: two shapes need three passes of guard_mean_shift and end with 4 / 5 clusters (a real
+    gradient after a redo), the shape between them needs one pass."""
+    g = _load(golden_dir, "guard_multi")
+    assert g["passes"].tolist() == [3, 1, 3] and g["n_attempt"].tolist() == [4, 8, 5]
+    assert float(np.abs(g["grad64"]).max()) > 1e-8
+
+
+def _recipe_inputs(g):
+    import json
+
+    from prifit_b200 import synthetic
+
+    parts = [synthetic.from_recipe(r) for r in json.loads(str(g["recipes"]))]
+    E, P = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+    assert synthetic.checksum(E) == str(g["checksum_E"]) and synthetic.checksum(P) == str(g["checksum_P"]), \
+        "the seeded generator no longer reproduces the inputs the fixture was made from"
+    return E, P
+
+
+def test_full_size_fixture_cfg2_against_oracle(golden_dir):
+    """planted_cfg2 (2 x 2048 x 128, 16 clusters, the README configuration): inputs regenerated from the stored recipe
+    (checksummed), oracle fp64 vs the reference's fp64 loss / gradient, and the stored err(ref32, ref64)."""
+    g = _load(golden_dir, "planted_cfg2")
+    E, P = _recipe_inputs(g)
+    q, T, kmax = float(g["quantile"]), int(g["iterations"]), int(g["max_num_clusters"])
+    gn = torch.from_numpy(g["noise"]).double()
+    np.random.seed(7)
+    first = R.fit_loss(E.double(), P.double(), q, T, kmax, noise=gn)
+    noise = torch.zeros_like(gn)
+    for b in range(2):
+        for r, o in label_map(first["labels"][b].numpy(), g["labels64"][b]).items():
+            noise[b, o] = gn[b, r]
+    np.random.seed(7)
+    out = R.fit_loss(E.double(), P.double(), q, T, kmax, noise=noise)
+    assert rel_err(out["loss"], g["loss64"]) < 1e-9
+    assert rel_err(out["grad_E"], g["grad64"]) < 1e-6          # the fixture stores the fp64 gradient rounded to fp32
+    assert 1e-5 < float(g["err32_64"]) < 1e-2 and float(g["gscale"]) > 0
+
+
+def test_recipes_of_the_large_fixtures_reproduce(golden_dir):
+    """planted_cfg4 and the noisy family store recipes + checksums only: the generator must reproduce them here."""
+    import json
+
+    from prifit_b200 import synthetic
+
+    _recipe_inputs(_load(golden_dir, "planted_cfg4"))
+    g = _load(golden_dir, "noisy_labels")
+    for i, (recipe, q) in enumerate(json.loads(str(g["groups"]))):
+        E, _ = synthetic.from_recipe(recipe)
+        assert synthetic.checksum(E) == str(g["checksum_%d" % i])
+
+
+def test_noisy_family_oracle_labels_equal_reference_fp32(golden_dir):
+    """On inputs whose modes merge / do not converge, the oracle (fp32) still reproduces the reference's fp32 labels bit
+    for bit, and the reference's own fp32-vs-fp64 partition disagreement is what the fixture says (up to 65 %)."""
+    import json
+
+    from helpers import partition_disagreement
+    from prifit_b200 import synthetic
+
+    g = _load(golden_dir, "noisy_labels")
+    worst = 0.0
+    for i, (recipe, q) in enumerate(json.loads(str(g["groups"]))):
+        E, _ = synthetic.from_recipe(recipe)
+        np.random.seed(3)
+        _, labels = R.clustering(R.normalize_twice(E), E.shape[1], q, 10, 25)
+        for b in range(E.shape[0]):
+            assert np.array_equal(labels[b].numpy(), g["labels32_%d" % i][b])
+            d = partition_disagreement(g["labels32_%d" % i][b], g["labels64_%d" % i][b])
+            assert abs(d - float(g["dis_%d" % i][b])) < 1e-12
+            worst = max(worst, d)
+    assert worst > 0.3
 
 
 def test_oracle_fp64_matches_reference_fp64(golden_dir):
