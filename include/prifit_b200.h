@@ -56,6 +56,14 @@ int prifit_normalize_bwd(const float* E, const float* gX, int64_t rows, int d, f
  *   (Ecf[B,d,N], gX[B,N,d]) -> gEcf[B,d,N]; d = 128; same arithmetic as the row-major pair (bit-identical X). */
 int prifit_normalize_fwd_cf(const float* Ecf, int B, int N, int d, float* X, void* stream);
 int prifit_normalize_bwd_cf(const float* Ecf, const float* gX, int B, int N, int d, float* gEcf, void* stream);
+/* Backward of the two normalisations with an upstream scale read from device memory:
+ *   gE = normalize_bwd(E, gX * (g_sum[0] + g_mean[0] / max(stats[1], 1)))        (g_sum / g_mean may be NULL = 0)
+ * The gradient of the whole path is linear in dL/d(loss): the graph-replayed step computes d(sum_b has_b loss_b)/dX ahead
+ * of time and this kernel applies dL/d(loss_sum), dL/d(loss_mean) (stats = [loss_sum, n_valid, loss_mean] of
+ * prifit_masked_mean_fwd) when autograd delivers them -- the autograd edge of src/utils.py:425 + convex_loss.py:41,57.
+ * E, gE: [B,N,d] (channel_first = 0) or [B,d,N] (channel_first = 1, d == 128); gX: [B,N,d]. */
+int prifit_normalize_bwd_scaled(const float* E, const float* gX, int B, int N, int d, int channel_first,
+                                const float* g_sum, const float* g_mean, const float* stats, float* gE, void* stream);
 
 /* k1 -- bandwidth.  src/mean_shift.py:138-160 (compute_bandwidth)
  *   rows: optional [B, n_s] int32 subset (the first num_samples entries of the host shuffle,

@@ -297,8 +297,9 @@ def sampler_case(ns):
 
 
 def big_case(ns, name, recipes, quantile, iterations, max_num_clusters, seed=7, kcap=32, check_oracle=True):
-    """Full-size parity case.  Inputs come from prifit_b200.synthetic recipes (the fixture stores the recipes and a
-    checksum of E instead of E); outputs: the unmodified reference's labels (fp32 and fp64 runs), parameters, loss, the
+    """Full-size parity case.  The embeddings come from prifit_b200.synthetic recipes (the fixture stores the recipes and a
+    checksum of E instead of E; torch's CPU generator is bit-reproducible across machines), the points are stored (their
+    recipe goes through LAPACK's QR, which is not); outputs: the unmodified reference's labels (fp32 and fp64 runs), parameters, loss, the
     fp64 input gradient (stored as fp32: 6e-8 relative, far below the 1e-4 acceptance) and the scalar
     err(ref32, ref64) = max|grad32 - grad64| / max|grad64| that the acceptance rule of SURVEY 8c needs."""
     import json
@@ -325,7 +326,7 @@ def big_case(ns, name, recipes, quantile, iterations, max_num_clusters, seed=7, 
     s64, V64, c64, n64 = pack_params(ref64["params"], kcap, np.float64)
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"), recipes=np.asarray(json.dumps(recipes)), checksum_E=np.asarray(synthetic.checksum(E)),
-        checksum_P=np.asarray(synthetic.checksum(P)), quantile=np.float64(quantile), iterations=np.int32(iterations),
+        P=P.numpy(), quantile=np.float64(quantile), iterations=np.int32(iterations),
         max_num_clusters=np.int32(max_num_clusters), noise=noise.numpy(), n_attempt=np.asarray(ref32["n_attempt"], np.int32),
         n_attempt64=np.asarray(ref64["n_attempt"], np.int32),
         labels32=np.stack([l.numpy() for l in ref32["labels"]]).astype(np.int16),
@@ -404,6 +405,11 @@ def main():
         return
     if "--only-sampler" in sys.argv:
         sampler_case(ns)
+        return
+    if "--only-big" in sys.argv:
+        big_case(ns, "planted_cfg2", [{"family": "planted", "batch": 2, "n_points": 2048, "n_clusters": 16, "seed": 5}], 0.05, 10, 25)
+        big_case(ns, "planted_cfg4", [{"family": "planted", "batch": 1, "n_points": 10000, "n_clusters": 16, "seed": 3}], 0.05, 10, 50,
+                 kcap=64, check_oracle=False)
         return
     if "--round2" in sys.argv:                # round 2: full-size, guard-redo and noisy cases; earlier fixtures untouched
         round2_cases(ns)

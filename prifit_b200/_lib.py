@@ -23,6 +23,7 @@ SIGNATURES = {
     "prifit_normalize_bwd": (_i, [_p, _p, _i64, _i, _p, _p]),
     "prifit_normalize_fwd_cf": (_i, [_p, _i, _i, _i, _p, _p]),
     "prifit_normalize_bwd_cf": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "prifit_normalize_bwd_scaled": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "prifit_bandwidth_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "prifit_bandwidth_fwd": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "prifit_meanshift_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -103,7 +104,7 @@ def check(rc, what):
 
 # kernels (and memset nodes) each entry point enqueues; bench.py reports the sum as `gpu_launches`
 LAUNCHES = {
-    "prifit_normalize_fwd": 1, "prifit_normalize_bwd": 1, "prifit_normalize_fwd_cf": 1, "prifit_normalize_bwd_cf": 1, "prifit_bandwidth_fwd": 6, "prifit_meanshift_fwd": 3,
+    "prifit_normalize_fwd": 1, "prifit_normalize_bwd": 1, "prifit_normalize_fwd_cf": 1, "prifit_normalize_bwd_cf": 1, "prifit_normalize_bwd_scaled": 1, "prifit_bandwidth_fwd": 6, "prifit_meanshift_fwd": 3,
     "prifit_nms_fwd": 10, "prifit_meanshift_rows_fwd": 2, "prifit_meanshift_rows_bwd": 2,
     "prifit_membership_fwd": 2, "prifit_membership_bwd": 2, "prifit_fit_fwd": 1, "prifit_fit_bwd": 1,
     "prifit_sdf_loss_fwd": 2, "prifit_sdf_loss_bwd": 1,

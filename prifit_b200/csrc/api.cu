@@ -70,12 +70,23 @@ __global__ void __launch_bounds__(256) normalize_fwd_kernel(const float* __restr
 
 // backward of y = v / max(||v||, eps) applied twice: g1 = (g - x (x.g)) / n1 ; gE = (g1 - x1 (x1.g1)) / n0
 // (when the clamp is active, i.e. ||v|| < eps, the node is a plain division by eps.)
+// Upstream scale of the scaled variants: the backward of the whole path is linear in dL/d(loss), so the graph-replayed step
+// computes the gradient of sum_b has_b loss_b ahead of time and this last kernel multiplies it by
+//   g = dL/d(loss_sum) + dL/d(loss_mean) / max(n_valid, 1)          (device scalars; n_valid = stats[1])
+__device__ __forceinline__ float upstream_scale(const float* g_sum, const float* g_mean, const float* stats) {
+    if (!stats) return 1.0f;
+    return (g_sum ? g_sum[0] : 0.f) + (g_mean ? g_mean[0] / fmaxf(stats[1], 1.0f) : 0.f);
+}
+
 template <int NVF>
 __global__ void __launch_bounds__(256) normalize_bwd_kernel(const float* __restrict__ E, const float* __restrict__ gX,
-                                                            int64_t rows, int d, float* __restrict__ gE) {
+                                                            int64_t rows, int d, float* __restrict__ gE,
+                                                            const float* __restrict__ g_sum, const float* __restrict__ g_mean,
+                                                            const float* __restrict__ stats) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
+    const float up = upstream_scale(g_sum, g_mean, stats);
     const float4* e4 = reinterpret_cast<const float4*>(E + row * d);
     const float4* g4 = reinterpret_cast<const float4*>(gX + row * d);
     float4* o4 = reinterpret_cast<float4*>(gE + row * d);
@@ -99,6 +110,7 @@ __global__ void __launch_bounds__(256) normalize_bwd_kernel(const float* __restr
     float xg = 0.f;
     for (int c = lane; c < nv; c += 32) {
         float4 v = e4[c], g = g4[c];
+        g.x *= up; g.y *= up; g.z *= up; g.w *= up;
         xg += ((v.x / n0) / n1) * g.x + ((v.y / n0) / n1) * g.y + ((v.z / n0) / n1) * g.z + ((v.w / n0) / n1) * g.w;
     }
     xg = warp_sum(xg);
@@ -107,6 +119,7 @@ __global__ void __launch_bounds__(256) normalize_bwd_kernel(const float* __restr
     float x1g1 = 0.f;
     for (int c = lane; c < nv; c += 32) {
         float4 v = e4[c], g = g4[c];
+        g.x *= up; g.y *= up; g.z *= up; g.w *= up;
         float x1[4] = {v.x / n0, v.y / n0, v.z / n0, v.w / n0};
         float gg[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
@@ -118,6 +131,7 @@ __global__ void __launch_bounds__(256) normalize_bwd_kernel(const float* __restr
     x1g1 = warp_sum(x1g1);
     for (int c = lane; c < nv; c += 32) {
         float4 v = e4[c], g = g4[c];
+        g.x *= up; g.y *= up; g.z *= up; g.w *= up;
         float x1[4] = {v.x / n0, v.y / n0, v.z / n0, v.w / n0};
         float gg[4] = {g.x, g.y, g.z, g.w};
         float o[4];
@@ -141,7 +155,9 @@ constexpr int CF_D = 128, CF_PTS = 32;
 
 template <bool BWD>
 __global__ void __launch_bounds__(256) normalize_cf_kernel(const float* __restrict__ Ecf, const float* __restrict__ gX, int N,
-                                                           float* __restrict__ out) {
+                                                           float* __restrict__ out, const float* __restrict__ g_sum = nullptr,
+                                                           const float* __restrict__ g_mean = nullptr,
+                                                           const float* __restrict__ stats = nullptr) {
     __shared__ float tile[CF_D][CF_PTS + 1];
     const int b = blockIdx.y, n0 = blockIdx.x * CF_PTS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -163,7 +179,9 @@ __global__ void __launch_bounds__(256) normalize_cf_kernel(const float* __restri
             reinterpret_cast<float4*>(out + ((size_t)b * N + n) * CF_D)[lane] =
                 make_float4(x1.x / nrm1, x1.y / nrm1, x1.z / nrm1, x1.w / nrm1);
         } else {
-            const float4 g = reinterpret_cast<const float4*>(gX + ((size_t)b * N + n) * CF_D)[lane];
+            float4 g = reinterpret_cast<const float4*>(gX + ((size_t)b * N + n) * CF_D)[lane];
+            const float up = upstream_scale(g_sum, g_mean, stats);
+            g.x *= up; g.y *= up; g.z *= up; g.w *= up;
             float xg = (x1.x / nrm1) * g.x + (x1.y / nrm1) * g.y + (x1.z / nrm1) * g.z + (x1.w / nrm1) * g.w;
             xg = warp_sum(xg);
             const bool proj1 = r1 >= 1e-12f, proj0 = r0 >= 1e-12f;
@@ -205,6 +223,24 @@ extern "C" int prifit_normalize_bwd_cf(const float* Ecf, const float* gX, int B,
     return 0;
 }
 
+extern "C" int prifit_normalize_bwd_scaled(const float* E, const float* gX, int B, int N, int d, int channel_first,
+                                           const float* g_sum, const float* g_mean, const float* stats, float* gE, void* stream) {
+    PF_CHECK_ARG(E && gX && gE && stats, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(B > 0 && N > 0 && d > 0 && d % 4 == 0, PRIFIT_E_SHAPE, "B, N > 0 and d % 4 == 0 required");
+    if (channel_first) {
+        PF_CHECK_ARG(d == CF_D, PRIFIT_E_SHAPE, "the channel-first kernels are specialised for d = 128");
+        normalize_cf_kernel<true><<<dim3((N + CF_PTS - 1) / CF_PTS, B), 256, 0, pf_stream(stream)>>>(E, gX, N, gE, g_sum, g_mean, stats);
+    } else {
+        const int wpb = 8;
+        const int64_t rows = (int64_t)B * N;
+        const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+        if (d == 128) normalize_bwd_kernel<32><<<grid, wpb * 32, 0, pf_stream(stream)>>>(E, gX, rows, d, gE, g_sum, g_mean, stats);
+        else normalize_bwd_kernel<0><<<grid, wpb * 32, 0, pf_stream(stream)>>>(E, gX, rows, d, gE, g_sum, g_mean, stats);
+    }
+    PF_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int prifit_normalize_fwd(const float* E, int64_t rows, int d, float* X, void* stream) {
     PF_CHECK_ARG(E && X, PRIFIT_E_BADARG, "null pointer");
     PF_CHECK_ARG(rows > 0 && d > 0 && d % 4 == 0, PRIFIT_E_SHAPE, "rows > 0 and d % 4 == 0 required");
@@ -221,8 +257,8 @@ extern "C" int prifit_normalize_bwd(const float* E, const float* gX, int64_t row
     PF_CHECK_ARG(rows > 0 && d > 0 && d % 4 == 0, PRIFIT_E_SHAPE, "rows > 0 and d % 4 == 0 required");
     const int wpb = 8;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    if (d == 128) normalize_bwd_kernel<32><<<grid, wpb * 32, 0, pf_stream(stream)>>>(E, gX, rows, d, gE);
-    else normalize_bwd_kernel<0><<<grid, wpb * 32, 0, pf_stream(stream)>>>(E, gX, rows, d, gE);
+    if (d == 128) normalize_bwd_kernel<32><<<grid, wpb * 32, 0, pf_stream(stream)>>>(E, gX, rows, d, gE, nullptr, nullptr, nullptr);
+    else normalize_bwd_kernel<0><<<grid, wpb * 32, 0, pf_stream(stream)>>>(E, gX, rows, d, gE, nullptr, nullptr, nullptr);
     PF_LAUNCH_CHECK();
     return 0;
 }

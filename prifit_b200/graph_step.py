@@ -1,8 +1,17 @@
-"""The whole hot path of one batch as three CUDA graphs over static buffers.
+"""The whole hot path of one batch as three CUDA graphs over static buffers, launched back to back.
 
     graph 1  (per branch)  normalise x2 -> bandwidth -> T mean-shift iterations -> NMS     | counts -> pinned host
     graph 2  noise scatter | (per branch) K-seed trajectories -> membership -> fit -> SDF  | batch mean
-    graph 3  batch-mean backward | (per branch) SDF -> fit -> membership -> K-seed trajectories -> normalise backward
+    graph 3  (per branch) SDF -> fit -> membership -> K-seed trajectories backward of  sum_b has_b loss_b   (speculative)
+    + one kernel at autograd-backward time: normalise backward with the upstream scale dL/d(loss) applied
+
+The backward of the path is linear in dL/d(loss), so when the embeddings require a gradient graph 3 is enqueued right
+behind graph 2 -- before the host has made the guard decision and before autograd asks for it -- computing the gradient
+of sum_b has_b loss_b w.r.t. the unit embeddings.  When autograd does call backward, ONE kernel
+(prifit_normalize_bwd_scaled) multiplies by g = dL/d(loss_sum) + dL/d(loss_mean) / n_valid (device scalars) and maps the
+result through the two normalisations.  The device therefore never waits for the host between the forward and the
+backward chain, and the multi-GPU all-reduce of [loss_sum, n_valid] (which only g depends on) runs on a side stream
+beside graph 3 instead of between the two.
 
 Why.  The eager pipeline (pipeline.fit_loss with graph=False) enqueues ~40 launches per step from Python and runs
 them back to back on one stream, so (1) every kernel's partial last wave leaves SMs idle -- 24 shapes x 16 row
@@ -99,6 +108,9 @@ class GraphStep:
         self.kth = torch.full((B,), min(kth, N), dtype=i32, device=device)
         self.g_sum, self.g_mean = torch.zeros(1, device=device), torch.zeros(1, device=device)
         self.g_zero = [True, True]
+        self.g_one, self.g_nil = torch.ones(1, device=device), torch.zeros(1, device=device)   # upstream of the speculative backward
+        self.side = torch.cuda.Stream(device=device)                  # multi-GPU all-reduce beside graph 3
+        self.backward_serial = -1
         # ---- small outputs (snapshotted per step)
         ar = self.arena = _Arena(device)
         for name, shape, dt in (("stats", (3,), f32), ("has", (B,), f32), ("loss_b", (B,), f32), ("bw", (B,), f32),
@@ -192,7 +204,8 @@ class GraphStep:
 
     def _seq_backward(self):
         B, N, d, T, kcap, M, sm = self.B, self.N, self.d, self.T, self.kcap, self.Mq, self.small
-        _lib.call("prifit_masked_mean_bwd", _ptr(self.g_sum), _ptr(self.g_mean), _ptr(sm["has"]), _ptr(sm["stats"]), B,
+        # gloss_b = has_b: the gradient of sum_b has_b loss_b; the true upstream scale is applied by the last kernel
+        _lib.call("prifit_masked_mean_bwd", _ptr(self.g_one), _ptr(self.g_nil), _ptr(sm["has"]), _ptr(sm["stats"]), B,
                   _ptr(self.gloss), _stream())
 
         def branch(i, lo, hi):
@@ -210,12 +223,12 @@ class GraphStep:
                       Bb, N, d, kcap, _ptr(gC), _ptr(gX), _ptr(ws["membb"][0]), ws["membb"][1], st)
             _lib.call("prifit_meanshift_rows_bwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), _ptr(self.traj[lo:hi]),
                       _ptr(self.stat[lo:hi]), _ptr(gC), Bb, N, d, T, kcap, _ptr(gX), self.rows_bwd_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
-            if self.cf:
-                _lib.call("prifit_normalize_bwd_cf", _ptr(self.E[lo:hi]), _ptr(gX), Bb, N, d, _ptr(self.gE[lo:hi]), st)
-            else:
-                _lib.call("prifit_normalize_bwd", _ptr(self.E[lo:hi]), _ptr(gX), Bb * N, d, _ptr(self.gE[lo:hi]), st)
 
         self._fork_join(branch)
+
+    def _scaled_normalize_bwd(self):
+        _lib.call("prifit_normalize_bwd_scaled", _ptr(self.E), _ptr(self.gX), self.B, self.N, self.d, 1 if self.cf else 0,
+                  _ptr(self.g_sum), _ptr(self.g_mean), _ptr(self.small["stats"]), _ptr(self.gE), _stream())
 
     def _capture(self):
         seqs = (self._seq_cluster, self._seq_rest, self._seq_backward)
@@ -230,6 +243,7 @@ class GraphStep:
         with torch.cuda.stream(side):
             for seq in seqs:
                 seq()
+            self._scaled_normalize_bwd()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.graphs = []
@@ -244,9 +258,10 @@ class GraphStep:
         _lib._launches -= sum(self.launches)          # capture enqueues nothing; replays are counted in run_*
 
     # ------------------------------------------------------------------------------------------ per step
-    def run_forward(self, E, P, Q, noise):
-        """Enqueues the step (input copies, noise staging, graphs 1 and 2, snapshot of the small outputs) without
-        waiting for anything and returns the result dict; finish_forward() then makes the guard decision."""
+    def run_forward(self, E, P, Q, noise, want_grad=False):
+        """Enqueues the step (input copies, noise staging, graphs 1 and 2, snapshot of the small outputs, and -- when a
+        gradient will be asked for -- the speculative backward graph 3) without waiting for anything and returns the
+        result dict; finish_forward() then makes the guard decision."""
         self.serial += 1
         self.E.copy_(E)
         self.P.copy_(P)
@@ -279,6 +294,12 @@ class GraphStep:
         # snapshot of the small outputs: enqueued (and its views built) before the host waits, so that after the
         # read-back the host only has the guard decision between itself and the backward launch
         snap = self.arena.views(self.arena.buf.clone())
+        self._ev_fwd = torch.cuda.Event()
+        self._ev_fwd.record()                              # forward results complete: what the multi-GPU all-reduce waits for
+        if want_grad:
+            self.graphs[2].replay()                        # speculative: d(sum_b has_b loss_b)/dX into self.gX
+            _lib._launches += self.launches[2]
+            self.backward_serial = self.serial
         loss_sum, n_valid, loss = snap["stats"].unbind(0)
         out = dict(snap)
         out.update({"loss": loss, "loss_sum": loss_sum, "n_valid": n_valid, "W": self.W, "C": self.C, "X": self.X,
@@ -314,8 +335,11 @@ class GraphStep:
             else:
                 dst.copy_(g.reshape(1))
                 self.g_zero[i] = False
-        self.graphs[2].replay()
-        _lib._launches += self.launches[2]
+        if self.backward_serial != serial:                 # the forward ran without grad mode's speculation (not expected)
+            self.graphs[2].replay()
+            _lib._launches += self.launches[2]
+            self.backward_serial = serial
+        self._scaled_normalize_bwd()                       # gE = normalize_bwd(E, g * gX)
         return self.gE
 
 
@@ -378,9 +402,10 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
     step = get_step(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, E.device,
                     default_branches() if branches is None else int(branches), cf)
     np_state = np.random.get_state()
-    res = step.run_forward(src.detach(), P.detach(), None if Q is None else Q.detach(), noise)
+    want_grad = E.requires_grad and torch.is_grad_enabled()
+    res = step.run_forward(src.detach(), P.detach(), None if Q is None else Q.detach(), noise, want_grad)
     loss_sum, loss = res["loss_sum"], res["loss"]
-    if E.requires_grad and torch.is_grad_enabled():
+    if want_grad:
         loss_sum, loss = _Attach.apply(src, step, res["serial"], loss_sum, loss)
     pipeline.replay_shuffles(B, N)                         # host RNG parity (src/mean_shift.py:150) while graph 1 runs
     if not step.finish_forward(res):
@@ -389,9 +414,18 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
     extra = {}
     if dist_reduce:
         # The multi-GPU mean.  After the guard decision on purpose: a rank that has to redo its step on the eager path
-        # reduces there, and every rank must issue exactly one collective per step.
+        # reduces there, and every rank must issue exactly one collective per step.  On a side stream that only waits for
+        # the forward results: the all-reduce runs beside the speculative backward graph, and the main stream picks the
+        # result up behind it (only the upstream scale of the last backward kernel depends on it).
         from . import dist as pdist
-        extra["loss_global"], extra["loss_backward"] = pdist.global_loss({"loss": loss, "loss_sum": loss_sum, "n_valid": res["n_valid"]})
+        main = torch.cuda.current_stream()
+        step.side.wait_event(step._ev_fwd)
+        with torch.cuda.stream(step.side):
+            lg, lb = pdist.global_loss({"loss": loss, "loss_sum": loss_sum, "n_valid": res["n_valid"]})
+        main.wait_stream(step.side)
+        for t in (lg, lb):
+            t.record_stream(main)
+        extra["loss_global"], extra["loss_backward"] = lg, lb
     cluster = pipeline.ClusterResult(bw=res["bw"], idx=res["idx"], K=res["K"], labels=res["labels"], K_host=res["K_host"],
                                      n_labels_host=res["n_labels_host"], passes=[1] * B, quantiles=[float(quantile)] * B,
                                      kcap=step.kcap, iterations=int(iterations))

@@ -74,7 +74,7 @@ def main():
         E, P = sets[i % 4]
         Ei = E.detach().requires_grad_(True)
         if cf:
-            total, l, params, labels = cl.convex_loss(P, P, Ei, quantile=0.05, iterations=10, max_num_clusters=25)
+            total, l, params, labels = cl.convex_loss(P, P, Ei, quantile=0.05, iterations=10, max_num_clusters=25, full_chamfer=False)
             total.backward()
             return
         out = pipeline.fit_loss(Ei, P, quantile=0.05, iterations=10, max_num_clusters=25, graph="--eager" not in sys.argv)

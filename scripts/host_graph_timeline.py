@@ -41,7 +41,7 @@ def main():
         t0 = time.perf_counter()
         Ei = E.detach().requires_grad_(True)
         if cf:
-            total, l, params, labels = cl.convex_loss(P, P, Ei, quantile=0.05, iterations=10, max_num_clusters=25)
+            total, l, params, labels = cl.convex_loss(P, P, Ei, quantile=0.05, iterations=10, max_num_clusters=25, full_chamfer=False)
         else:
             total = pipeline.fit_loss(Ei, P, quantile=0.05, iterations=10, max_num_clusters=25)["loss"]
         marks.append(("forward returned", time.perf_counter()))

@@ -198,10 +198,9 @@ def _recipe_inputs(g):
 
     from prifit_b200 import synthetic
 
-    parts = [synthetic.from_recipe(r) for r in json.loads(str(g["recipes"]))]
-    E, P = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
-    assert synthetic.checksum(E) == str(g["checksum_E"]) and synthetic.checksum(P) == str(g["checksum_P"])
-    return E, P
+    E = torch.cat([synthetic.from_recipe(r)[0] for r in json.loads(str(g["recipes"]))])
+    assert synthetic.checksum(E) == str(g["checksum_E"]), "the seeded generator no longer reproduces the fixture's embeddings"
+    return E, torch.from_numpy(g["P"])         # points are stored: their recipe uses LAPACK's QR (machine dependent)
 
 
 @pytest.mark.parametrize("engine_name", ["fp32", "tcgen05"])
@@ -448,7 +447,9 @@ def test_noise_staged_before_counts_equals_reference_stream(cuda):
 @pytest.mark.parametrize("branches", [1, 2, 3])
 def test_graph_replayed_step_equals_eager_step(cuda, branches, monkeypatch):
     """graph_step.py replays the same C-ABI calls as CUDA graphs over static buffers, the batch cut into parallel
-    branches: every output and the input gradient must be bit-identical to the eager path (batch invariance)."""
+    branches: every forward output must be bit-identical to the eager path (batch invariance).  The input gradient is
+    computed ahead of time for a unit upstream gradient and scaled by dL/d(loss) in its last kernel (the path is linear in
+    it), so it agrees with the eager chain -- which carries the scale through every stage -- to rounding (2e-6)."""
     from prifit_b200 import graph_step, pipeline, synthetic
 
     monkeypatch.setenv("PRIFIT_GRAPH_BRANCHES", str(branches))
@@ -470,7 +471,7 @@ def test_graph_replayed_step_equals_eager_step(cuda, branches, monkeypatch):
             for k in ("bw", "idx", "K", "labels"):
                 assert torch.equal(getattr(g["cluster"], k), getattr(eager["cluster"], k)), k
             assert g["cluster"].K_host == eager["cluster"].K_host
-            assert torch.equal(g["grad_E"], eager["grad_E"])
+            assert rel_err(g["grad_E"], eager["grad_E"]) < 2e-6
     # gradient through loss_sum with an upstream scale (the multi-GPU form)
     Ec = E.to(cuda).requires_grad_(True)
     torch.manual_seed(8)
@@ -480,7 +481,17 @@ def test_graph_replayed_step_equals_eager_step(cuda, branches, monkeypatch):
     torch.manual_seed(8)
     oute = pipeline.fit_loss(Ee, P.to(cuda), quantile=0.05, iterations=8, max_num_clusters=25, graph=False)
     (oute["loss_sum"] * 0.25).backward()
-    assert torch.equal(Ec.grad, Ee.grad)
+    assert rel_err(Ec.grad, Ee.grad) < 2e-6
+    # a second backward through the same step (retain_graph) re-applies the scale to the stored unit gradient
+    Ec2 = E.to(cuda).requires_grad_(True)
+    torch.manual_seed(8)
+    out2 = pipeline.fit_loss(Ec2, P.to(cuda), quantile=0.05, iterations=8, max_num_clusters=25, graph=True)
+    (out2["loss"] * 3.0).backward(retain_graph=True)
+    first = Ec2.grad.clone()
+    Ec2.grad = None
+    (out2["loss"] * 3.0).backward()
+    assert torch.equal(Ec2.grad, first)
+    assert rel_err(first, Ee.grad * (3.0 / 0.25) / float(oute["n_valid"])) < 2e-6
 
 
 def test_graph_step_guard_redo_and_stale_backward(cuda, golden_dir):
@@ -530,7 +541,7 @@ def test_channel_first_public_api_graph_vs_eager(cuda, monkeypatch):
         total.backward()
         outs.append((total.detach().clone(), X.grad, [t.clone() for t in params.padded], [t.clone() for t in labels]))
     g, e, g2 = outs
-    assert torch.equal(g[0], e[0]) and torch.equal(g[1], e[1])
+    assert torch.equal(g[0], e[0]) and rel_err(g[1], e[1]) < 2e-6
     for a, b in zip(g[2], e[2]):
         assert torch.equal(a, b)
     for a, b in zip(g[3], e[3]):
