@@ -165,6 +165,21 @@ int prifit_sdf_loss_bwd(const float* Q, const float* s, const float* V, const fl
                         const int32_t* K, const int32_t* argmin, const float* gloss, int B, int M, int Kcap,
                         float* gs_out, float* gV_out, float* gc_out, float* gQ_out, void* stream);
 
+/* Intersection penalty between the ellipsoids of a shape.  convex_loss.py:346-441: version 3 =
+ * compute_intersection_loss_volume_3 (called at :97; as written with torch_scatter.scatter_mean), version 4 =
+ * compute_intersection_loss_volume_4.  With g_kj = min(sdf_k(q_j), -1e-3) over the valid ellipsoids of shape b:
+ *   version 3: loss_b = mean_j (mean_{k != argmin_k g_kj} g_kj)^2        version 4: loss_b = mean_j (sum_k g_kj^2 - (min_k g_kj)^2)
+ *   Q[B,M,3] probe points; loss_out[B] (0 for shapes with fewer than two ellipsoids); counted_out[B] = 1 where the shape has
+ *   at least two; kstar_out[B,M] / aux_out[B,M] = arg-min ellipsoid and mean (v3) / min (v4), saved for the backward.
+ *   Backward: gloss[B] -> gs, gV, gc (the probe points carry no gradient in the reference's use). */
+size_t prifit_intersect_workspace_bytes(int B, int M);
+int prifit_intersect_fwd(const float* Q, const float* s, const float* V, const float* c, const uint8_t* valid,
+                         const int32_t* K, int B, int M, int Kcap, int version, float* loss_out, float* counted_out,
+                         int32_t* kstar_out, float* aux_out, void* ws, size_t ws_bytes, void* stream);
+int prifit_intersect_bwd(const float* Q, const float* s, const float* V, const float* c, const uint8_t* valid,
+                         const int32_t* K, const int32_t* kstar, const float* aux, const float* gloss, int B, int M,
+                         int Kcap, int version, float* gs_out, float* gV_out, float* gc_out, void* stream);
+
 /* batch mean of the per-shape losses.  src/utils.py:418,425 (mean over the shapes that kept at least one
  *   ellipsoid) and train_partseg_shapenet.py:445 (mean over the replicas).
  *   has_out[B] = 1 if any valid[b,:] else 0;  stats_out[3] = { sum_b loss_b has_b, sum_b has_b, sum / max(n, 1) }.

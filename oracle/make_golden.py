@@ -379,6 +379,50 @@ def noisy_case(ns):
     np.savez_compressed(os.path.join(OUT, "noisy_labels.npz"), **out)
 
 
+def intersect_case(ns):
+    """Intersection penalty through the reference's own functions: compute_intersection_loss_volume_4 unmodified; and
+    compute_intersection_loss_volume_3 with the one name its file fails to import (torch_scatter.scatter_mean, commented out
+    at convex_loss.py:17) supplied as a three-line torch function -- the reference's code is otherwise run as is.
+    Overlapping ellipsoids, probe points inside several of them; one shape with a single ellipsoid (skipped)."""
+    torch.manual_seed(37)
+    B, M = 3, 240
+    params = []
+    for b in range(B):
+        per = []
+        for k in range([4, 1, 3][b]):
+            Q, _ = torch.linalg.qr(torch.randn(3, 3))
+            per.append((0.35 + 0.4 * torch.rand(3), Q.contiguous(), 0.5 * (torch.rand(3) - 0.5)))
+        params.append(per)
+    pts = (torch.rand(B, M, 3) - 0.5) * 1.2
+
+    def scatter_mean(src, index, dim=1):
+        n = int(index.max()) + 1
+        out = torch.zeros(src.shape[0], n, dtype=src.dtype).scatter_add(1, index, src)
+        cnt = torch.zeros(src.shape[0], n, dtype=src.dtype).scatter_add(1, index, torch.ones_like(src))
+        return out / cnt.clamp(min=1)
+
+    ns.convex_loss.scatter_mean = scatter_mean
+    out = {"points": pts.numpy(), "n_ell": np.asarray([len(p) for p in params], np.int32)}
+    for b in range(B):
+        out["s_%d" % b] = np.stack([r.numpy() for (r, V, c) in params[b]])
+        out["V_%d" % b] = np.stack([V.numpy() for (r, V, c) in params[b]])
+        out["c_%d" % b] = np.stack([c.numpy() for (r, V, c) in params[b]])
+    for version, fn in ((3, ns.convex_loss.compute_intersection_loss_volume_3), (4, ns.convex_loss.compute_intersection_loss_volume_4)):
+        for dt, name in ((torch.float32, "32"), (torch.float64, "64")):
+            P = [[(r.to(dt).clone().requires_grad_(True), V.to(dt).clone().requires_grad_(True), c.to(dt).clone().requires_grad_(True))
+                  for (r, V, c) in per] for per in params]
+            loss = fn(P, pts.to(dt))
+            loss.backward()
+            o = R.intersection_loss([[(r.detach(), V.detach(), c.detach()) for (r, V, c) in per] for per in P], pts.to(dt), version)
+            print("[intersect v%d fp%s] reference %.9g oracle %.9g" % (version, name, float(loss), float(o)))
+            out["loss%d_%s" % (version, name)] = np.float64(loss.detach())
+            for b in (0, 2):
+                out["gs%d_%s_%d" % (version, name, b)] = np.stack([r.grad.numpy() for (r, V, c) in P[b]])
+                out["gV%d_%s_%d" % (version, name, b)] = np.stack([V.grad.numpy() for (r, V, c) in P[b]])
+                out["gc%d_%s_%d" % (version, name, b)] = np.stack([c.grad.numpy() for (r, V, c) in P[b]])
+    np.savez_compressed(os.path.join(OUT, "intersect.npz"), **out)
+
+
 def round2_cases(ns):
     # guard redo that ends with K > 1 (3 passes -> 4 clusters) next to a shape that needs no redo (sub-batch compaction)
     E0, P0, _ = synthetic.hier_shapes(1, seed=1)
@@ -387,6 +431,7 @@ def round2_cases(ns):
     pipeline_case(ns, "guard_multi", torch.cat([E0, E1, E2]), torch.cat([P0, P1, P2]), 0.01, 10, 25)
     big_case(ns, "planted_cfg2", [{"family": "planted", "batch": 2, "n_points": 2048, "n_clusters": 16, "seed": 5}], 0.05, 10, 25)
     noisy_case(ns)
+    intersect_case(ns)
     big_case(ns, "planted_cfg4", [{"family": "planted", "batch": 1, "n_points": 10000, "n_clusters": 16, "seed": 3}], 0.05, 10, 50,
              kcap=64, check_oracle=False)
 
@@ -405,6 +450,9 @@ def main():
         return
     if "--only-sampler" in sys.argv:
         sampler_case(ns)
+        return
+    if "--only-intersect" in sys.argv:
+        intersect_case(ns)
         return
     if "--only-big" in sys.argv:
         big_case(ns, "planted_cfg2", [{"family": "planted", "batch": 2, "n_points": 2048, "n_clusters": 16, "seed": 5}], 0.05, 10, 25)

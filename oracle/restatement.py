@@ -390,3 +390,27 @@ def surface_points(U, Vang, r, V, centre):
     y = r[1] * torch.sin(U) * torch.sin(Vang)
     z = r[2] * torch.cos(Vang)
     return torch.stack([x, y, z], 1) @ V.T + centre
+
+
+# ------------------------------------------------------------------------------------------ intersection penalty
+def intersection_loss(params_batch, points, version=4):
+    """convex_loss.py:377-410 (version 3, with torch_scatter.scatter_mean written out) and :413-441 (version 4):
+    penalty on probe points that lie inside more than one ellipsoid.  params_batch: list (B) of lists of (s, V, c);
+    points [B,M,3]."""
+    losses = []
+    for b, per in enumerate(params_batch):
+        if len(per) <= 1:
+            continue
+        sdf = torch.stack([compute_sdf_ellipsoid(points[b], c, r, V) for (r, V, c) in per], 1)       # [M, K]
+        sdf = torch.clamp_max(sdf, -1e-3)
+        if version == 4:
+            losses.append((torch.sum(sdf ** 2, 1) - torch.min(sdf, 1, keepdim=True)[0][:, 0] ** 2).mean())
+        else:
+            closest = torch.min(sdf, 1)[1]
+            others = torch.ones_like(sdf)
+            others[torch.arange(sdf.shape[0]), closest] = 0.0             # scatter_mean(sdf, index, dim=1)[:, 0]: mean over index == 0
+            mean_others = (sdf * others).sum(1) / others.sum(1)
+            losses.append((mean_others ** 2).mean())
+    if not losses:
+        return torch.zeros(1, dtype=points.dtype)
+    return torch.stack(losses).mean()

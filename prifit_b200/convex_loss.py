@@ -77,8 +77,8 @@ def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, 
         total = l
         if entropy_loss is not None:
             total = total + beta * entropy_loss
-        if include_intersect_loss:
-            total = total + alpha * intersection_loss(params)
+        if include_intersect_loss and not evaluation:
+            total = total + alpha * intersection_loss(params, (P if Q is None else Q).contiguous())
         return total.view(1, 1), l.view(1, 1), params, labels
     # the regularisers reach X / the parameters beside the fitting loss, so those cases take the eager autograd path
     eager = full_chamfer or include_entropy_loss or include_intersect_loss
@@ -106,14 +106,30 @@ def convex_loss(points, chamfer_points, X, batch_id=0, epoch=-1, seed=0, N=500, 
     if entropy_loss is not None and not evaluation:
         total = total + (beta * share) * entropy_loss                                               # reference :96-100
     if include_intersect_loss and not evaluation:
-        total = total + (alpha * share) * intersection_loss(params)                                 # reference :95-100
+        total = total + (alpha * share) * intersection_loss(params, (P if Q is None else Q).contiguous())   # reference :95-100
     return total.view(1, 1), l.view(1, 1), params, labels
 
 
-def intersection_loss(params):
-    """Ellipsoid-ellipsoid intersection penalty of the reference (v4, :346-441); see ops.IntersectionLoss."""
-    from .intersect import intersection_loss_v4
-    return intersection_loss_v4(params)
+def intersection_loss(params, chamfer_points):
+    """reference :95-97: the intersection penalty on the chamfer cloud minus a U[0, 0.2) jitter (host generator draw).
+    The reference calls compute_intersection_loss_volume_3 there, which as shipped dies on its commented-out torch_scatter
+    import; version 3 here computes what that code says (PRIFIT_INTERSECT_VERSION=4 selects volume_4)."""
+    from . import intersect
+    return intersect.intersection_loss(params, intersect.probe_points(chamfer_points))
+
+
+def compute_intersection_loss_volume_3(ellipsoid_params_batch, points, cuboid=False):
+    """reference :377-410 (scatter_mean semantics), on the device kernels."""
+    if cuboid:
+        raise NotImplementedError("cuboids are outside the accelerated path")
+    from . import intersect
+    return intersect.intersection_loss(ellipsoid_params_batch, points, version=3)
+
+
+def compute_intersection_loss_volume_4(ellipsoid_params_batch, points):
+    """reference :413-441, on the device kernels."""
+    from . import intersect
+    return intersect.intersection_loss(ellipsoid_params_batch, points, version=4)
 
 
 def entropy(X, sub_sample_indices=None):

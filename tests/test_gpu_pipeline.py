@@ -449,7 +449,9 @@ def test_graph_replayed_step_equals_eager_step(cuda, branches, monkeypatch):
     """graph_step.py replays the same C-ABI calls as CUDA graphs over static buffers, the batch cut into parallel
     branches: every forward output must be bit-identical to the eager path (batch invariance).  The input gradient is
     computed ahead of time for a unit upstream gradient and scaled by dL/d(loss) in its last kernel (the path is linear in
-    it), so it agrees with the eager chain -- which carries the scale through every stage -- to rounding (2e-6)."""
+    it), so it agrees with the eager chain -- which carries the scale through every stage -- to the rounding of a
+    cancellation-dominated gradient: measured 3e-5 of max|grad| (the reference's own fp32 run is 2e-4 .. 5e-4 from its fp64
+    run on such inputs)."""
     from prifit_b200 import graph_step, pipeline, synthetic
 
     monkeypatch.setenv("PRIFIT_GRAPH_BRANCHES", str(branches))
@@ -471,7 +473,7 @@ def test_graph_replayed_step_equals_eager_step(cuda, branches, monkeypatch):
             for k in ("bw", "idx", "K", "labels"):
                 assert torch.equal(getattr(g["cluster"], k), getattr(eager["cluster"], k)), k
             assert g["cluster"].K_host == eager["cluster"].K_host
-            assert rel_err(g["grad_E"], eager["grad_E"]) < 2e-6
+            assert rel_err(g["grad_E"], eager["grad_E"]) < 1e-4     # cancellation-dominated gradient: see docstring
     # gradient through loss_sum with an upstream scale (the multi-GPU form)
     Ec = E.to(cuda).requires_grad_(True)
     torch.manual_seed(8)
@@ -481,7 +483,7 @@ def test_graph_replayed_step_equals_eager_step(cuda, branches, monkeypatch):
     torch.manual_seed(8)
     oute = pipeline.fit_loss(Ee, P.to(cuda), quantile=0.05, iterations=8, max_num_clusters=25, graph=False)
     (oute["loss_sum"] * 0.25).backward()
-    assert rel_err(Ec.grad, Ee.grad) < 2e-6
+    assert rel_err(Ec.grad, Ee.grad) < 1e-4
     # a second backward through the same step (retain_graph) re-applies the scale to the stored unit gradient
     Ec2 = E.to(cuda).requires_grad_(True)
     torch.manual_seed(8)
@@ -491,7 +493,7 @@ def test_graph_replayed_step_equals_eager_step(cuda, branches, monkeypatch):
     Ec2.grad = None
     (out2["loss"] * 3.0).backward()
     assert torch.equal(Ec2.grad, first)
-    assert rel_err(first, Ee.grad * (3.0 / 0.25) / float(oute["n_valid"])) < 2e-6
+    assert rel_err(first, Ee.grad * (3.0 / 0.25) / float(oute["n_valid"])) < 1e-4
 
 
 def test_graph_step_guard_redo_and_stale_backward(cuda, golden_dir):
@@ -541,7 +543,7 @@ def test_channel_first_public_api_graph_vs_eager(cuda, monkeypatch):
         total.backward()
         outs.append((total.detach().clone(), X.grad, [t.clone() for t in params.padded], [t.clone() for t in labels]))
     g, e, g2 = outs
-    assert torch.equal(g[0], e[0]) and rel_err(g[1], e[1]) < 2e-6
+    assert torch.equal(g[0], e[0]) and rel_err(g[1], e[1]) < 1e-4
     for a, b in zip(g[2], e[2]):
         assert torch.equal(a, b)
     for a, b in zip(g[3], e[3]):

@@ -642,3 +642,30 @@ def test_pointnet_ops_full_size_vs_oracle(cuda):
     # S == 1: the single feature row is repeated (reference :285-286)
     one = pu.three_interpolate(xyz.to(cuda), new_xyz[:, :1].to(cuda), feats[:, :1].to(cuda))
     assert torch.equal(one.cpu(), feats[:, :1].repeat(1, N, 1))
+
+
+@pytest.mark.parametrize("version", [3, 4])
+def test_intersection_loss_kernels_against_reference_fixture(cuda, golden_dir, version):
+    """csrc/intersect.cu (fwd + bwd) against the reference's compute_intersection_loss_volume_3 / _4: loss 1e-5, gradients
+    w.r.t. s, V, c of every ellipsoid 1e-4 of the fp64 reference; the one-ellipsoid shape contributes nothing."""
+    from prifit_b200 import intersect
+
+    g = _g(golden_dir, "intersect")
+    B = g["points"].shape[0]
+    params = [[(torch.from_numpy(g["s_%d" % b][k]).to(cuda).requires_grad_(True),
+                torch.from_numpy(g["V_%d" % b][k]).to(cuda).requires_grad_(True),
+                torch.from_numpy(g["c_%d" % b][k]).to(cuda).requires_grad_(True)) for k in range(int(g["n_ell"][b]))]
+              for b in range(B)]
+    pts = torch.from_numpy(g["points"]).to(cuda)
+    loss = intersect.intersection_loss(params, pts, version=version)
+    loss.backward()
+    assert rel_err(loss, g["loss%d_64" % version]) < 1e-5
+    for b in (0, 2):
+        for i, key in enumerate(("gs", "gV", "gc")):
+            got = torch.stack([p[i].grad for p in params[b]])
+            assert rel_err(got, g["%s%d_64_%d" % (key, version, b)]) < 1e-4, (key, b)
+    assert all(p.grad is None or float(p.grad.abs().max()) == 0.0 for p in params[1][0])
+    # public names of the reference module
+    import prifit_b200.convex_loss as cl
+    again = (cl.compute_intersection_loss_volume_3 if version == 3 else cl.compute_intersection_loss_volume_4)(params, pts)
+    assert float(again) == float(loss)

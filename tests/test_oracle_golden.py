@@ -253,3 +253,29 @@ def test_sampler_deterministic_parts_against_reference(golden_dir):
     (pts * torch.from_numpy(g["w"])).sum().backward()
     assert rel_err(pts, g["pts"]) < 1e-6
     assert rel_err(rr.grad, g["gr"]) < 1e-5 and rel_err(V.grad, g["gV"]) < 1e-5 and rel_err(c.grad, g["gc"]) < 1e-5
+
+
+def _intersect_inputs(g, dtype):
+    B = g["points"].shape[0]
+    return [[(torch.from_numpy(g["s_%d" % b][k]).to(dtype).requires_grad_(True),
+              torch.from_numpy(g["V_%d" % b][k]).to(dtype).requires_grad_(True),
+              torch.from_numpy(g["c_%d" % b][k]).to(dtype).requires_grad_(True)) for k in range(int(g["n_ell"][b]))]
+            for b in range(B)], torch.from_numpy(g["points"]).to(dtype)
+
+
+@pytest.mark.parametrize("version", [3, 4])
+def test_intersection_loss_against_reference(golden_dir, version):
+    """oracle.intersection_loss vs the reference's compute_intersection_loss_volume_3 / _4 (fixture intersect.npz: loss and
+    the gradients w.r.t. every ellipsoid parameter, fp32 and fp64; the middle shape has one ellipsoid and is skipped)."""
+    g = _load(golden_dir, "intersect")
+    for dt, name, tol in ((torch.float32, "32", 2e-5), (torch.float64, "64", 1e-10)):
+        params, pts = _intersect_inputs(g, dt)
+        loss = R.intersection_loss(params, pts, version)
+        loss.backward()
+        assert rel_err(loss, g["loss%d_%s" % (version, name)]) < tol
+        for b in (0, 2):
+            assert rel_err(torch.stack([p[0].grad for p in params[b]]), g["gs%d_%s_%d" % (version, name, b)]) < 50 * tol
+            assert rel_err(torch.stack([p[1].grad for p in params[b]]), g["gV%d_%s_%d" % (version, name, b)]) < 50 * tol
+            assert rel_err(torch.stack([p[2].grad for p in params[b]]), g["gc%d_%s_%d" % (version, name, b)]) < 50 * tol
+        assert all(p.grad is None for p in params[1][0])
+    assert float(g["loss3_64"]) > 1e-4 and float(g["loss4_64"]) > 1e-4
