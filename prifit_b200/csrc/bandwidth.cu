@@ -201,7 +201,7 @@ extern "C" int prifit_bandwidth_fwd(const float* X, int B, int N, int d, const i
         int32_t* overflow = reinterpret_cast<int32_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
         int2* rowinfo = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(overflow) + 16 + 255) & ~(uintptr_t)255);
         __half* Xh = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(rowinfo + (size_t)B * N) + 255) & ~(uintptr_t)255);
-        PF_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int32_t), st));
+        PF_CUDA(cudaMemsetAsync(overflow, 0, 4 * sizeof(int32_t), st));      // [0] overflow, [1] level-1 request
         rc = prifit_tc_bandwidth_rows(X, B, N, kth, Xh, rowinfo, rowval, overflow, st);
         if (rc) return rc;
         only_if = overflow;      // the exact CUDA-core kernel below re-does the batch only if a candidate list overflowed

@@ -3,10 +3,14 @@
 //   NEAREST  nearest[i] = argmin_j (2 - 2 <x_i, x_j>)                       NMS step 1, src/mean_shift.py:169-172
 //   BEST     best[i]    = argmax_j ([2 - 2 <x_i, x_j> < bw] * votes[j])     NMS step 3, src/mean_shift.py:187-194
 //            (only for the rows i that received votes -- the reference indexes nbrs[uniques] too)
-//   HIST     per-row 256-bin histogram of the distances inside the row's current window      } bandwidth,
-//            -> narrower window holding the k-th smallest (two levels: 1/64, then 1/16384)     } src/mean_shift.py:153-158
-//   COLLECT  candidates inside the final window (+- margin), EXACT fp32 recompute of just    }
-//            those, exact k-th order statistic, sqrt(max(., 1e-6))
+//   HIST     per-row 256-bin histogram of the distances                                       } bandwidth,
+//            level 0: LOGARITHMIC bins (16 per binade over 16 binades: 6 % wide) -> the bin    } src/mean_shift.py:153-158
+//            holding the k-th smallest; level 1 (only launched to work when some row's bin     }
+//            holds more candidates than COLLECT's row list takes): 256 uniform sub-bins        }
+//   COLLECT  candidates inside the final window (+- margin) with their tensor-core values;    }
+//            the k-th of those is located on the tensor-core values, and only the candidates  }
+//            within the rounding margin of it are recomputed EXACTLY in fp32 and ranked:      }
+//            exact k-th order statistic, sqrt(max(., 1e-6))                                   }
 //   DUMP     the distance matrix itself (tests only)
 //
 // (the Gram matrix is symmetric and the products commute bit-for-bit, so the reference's column-wise
@@ -26,13 +30,19 @@
 // warps (four per SM sub-partition: thread = (row, 32-column quarter)) consume S straight from tensor
 // memory.  The n x n matrix never exists outside TMEM.
 //
-// Exactness of the bandwidth.  The histogram levels partition the tensor-core distances exactly (the
-// MMA sequence is deterministic, bin edges are exact in fp32), so after two levels the k-th smallest
-// tensor-core distance is known to lie in a window of width 2^-14.  Its fp32 counterpart lies within
-// BW_MARGIN/2 of it; COLLECT keeps every element within BW_MARGIN of the window, counts the elements
-// below, recomputes the kept ones with fp32 FMAs and ranks them -- the result is the exact fp32 order
-// statistic, independent of the tensor-core rounding.  Rows with too many candidates (massive
-// duplicates) raise the overflow flag and the exact CUDA-core kernel (bandwidth.cu) redoes the batch.
+// Exactness of the bandwidth.  The histogram bins partition the tensor-core distances exactly (the MMA
+// sequence is deterministic and every pass evaluates the same expression; log bins are bit fields of
+// the value, uniform sub-bins have power-of-two widths), so after HIST the k-th smallest tensor-core
+// distance t_k is known to lie in one bin.  COLLECT keeps every element within BW_MARGIN of that bin
+// with its tensor-core value and counts the elements below; t_k is then the (k - below)-th kept value.
+// An element's fp32 distance lies within BW_MARGIN/2 of its tensor-core distance, so the order of two
+// elements whose tensor-core values differ by more than BW_MARGIN is already the fp32 order: only the
+// kept elements within BW_MARGIN of t_k are recomputed with fp32 FMAs and ranked -- the result is the
+// exact fp32 order statistic, independent of the tensor-core rounding, at a tail cost that does not
+// grow with the bin population.  Round 1 used two uniform levels (1/64, then 2^-14) = three full Gram
+// passes per bandwidth; the logarithmic level makes it two (98 + 114 + 107 us -> see DESIGN.md).
+// Rows with too many candidates (massive duplicates) raise the overflow flag and the exact CUDA-core
+// kernel (bandwidth.cu) redoes the batch.
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -60,17 +70,23 @@ enum { GM_NEAREST = 0, GM_BEST = 1, GM_HIST = 2, GM_COLLECT = 3, GM_DUMP = 4 };
 
 constexpr int HIST_BINS = 256;
 constexpr int HIST_WORDS = HIST_BINS / 2 + 1;            // packed uint16 pairs; odd word stride: conflict-free rows
-constexpr float HIST_SCALE0 = 64.0f;                     // level 0: bins of 1/64 over [0, 4)
-constexpr float HIST_SCALE1 = 64.0f * 256.0f;            // level 1: bins of 2^-14 inside the level-0 bin
+// bandwidth passes work on u = dist / 4 + 2^-15 in [~2^-15, 1 + 2^-15]: one FFMA, always positive and normal, so the bit
+// pattern orders like the value and its top bits are a logarithmic bin index
+constexpr float BW_UOFF = 1.0f / 32768.0f;
+constexpr uint32_t LOG_SHIFT = 19;                       // 4 mantissa bits: 16 bins per binade, 6.25 % wide
+constexpr uint32_t LOG_BASE = 111u << 4;                 // first bin starts at u = 2^-16 (biased exponent 111): 16 binades up to u = 1
 constexpr float BW_MARGIN = 2.0e-5f;                     // >= 2 x the bound on |tensor-core - fp32| distance
-constexpr int CAND_Q = 32;                               // candidates per (row, column quarter)
+constexpr float BW_MARGIN_U = 0.25f * BW_MARGIN;         // the same in u units
+constexpr int CAND_ROW = 64;                             // candidates per row (COLLECT)
+constexpr int REFINE_ABOVE = 48;                         // level-0 bin population above which level 1 refines the row
 
 template <int MODE> struct GCfg {
     static constexpr size_t scratch =
         MODE == GM_NEAREST ? (size_t)3 * G_BM * 8
       : MODE == GM_BEST ? (size_t)3 * G_BM * 8 + 2 * G_BN * sizeof(float)
       : MODE == GM_HIST ? (size_t)G_BM * HIST_WORDS * 4
-      : MODE == GM_COLLECT ? (size_t)G_EPI * CAND_Q * 2 + 16 * 16 * CAND_Q * sizeof(float) + 2 * G_EPI * sizeof(int)
+      : MODE == GM_COLLECT ? (size_t)G_BM * CAND_ROW * (4 + 2) + (size_t)G_BM * sizeof(int) + (size_t)G_EPI * sizeof(int)
+                             + (size_t)16 * 4 * CAND_ROW * sizeof(float)
       : 16;
     static constexpr size_t smem = 1024 + (size_t)G_STAGES * G_STAGE_BYTES + 256 + scratch;
 };
@@ -89,9 +105,11 @@ struct GramArgs {
     const int32_t* nrows;    // [B]       (BEST) length of that list
     const int32_t* kth;      // [B]       (HIST / COLLECT), 1-based rank
     int32_t* out_idx;        // [B,N]     (NEAREST / BEST)
-    int2* rowinfo;           // [B,N]     (HIST in/out, COLLECT in): (window start as float bits, remaining rank)
+    int2* rowinfo;           // [B,N]     (HIST in/out, COLLECT in): x = window start (bits of u), y = remaining rank (24 bits)
+                             //           | width code c << 24 (window width 2^-c in u units) | bit 31: level 1 must refine the row
     float* rowval;           // [B,N]     (COLLECT out)
-    int32_t* overflow;       // [1]       (COLLECT out): candidate list overflow / window miss
+    int32_t* overflow;       // [2]       [0] (COLLECT out): candidate list overflow / window miss; [1] (HIST level 0 out): some
+                             //           row needs level 1
     float* dump;             // [B,N,N]   (DUMP out)
     int N, B, level;
     int dbg;                 // timing experiments only (PRIFIT_GRAM_DEBUG): 1 = hi.hi product only
@@ -107,6 +125,10 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 512;" 
 __device__ __forceinline__ float tc_q(uint32_t sbits) {
     return __saturatef(fmaf(__uint_as_float(sbits), 0.25f * G_DIST_MUL, 0.5f));
 }
+// bandwidth passes: u = dist / 4 + 2^-15, NOT saturated (a dot product that rounds to 1 + 1e-6 still gives u > 2^-16)
+__device__ __forceinline__ float tc_u(uint32_t sbits) {
+    return fmaf(__uint_as_float(sbits), 0.25f * G_DIST_MUL, 0.5f + BW_UOFF);
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
@@ -114,6 +136,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
     int nsel = N;                                              // rows this shape contributes (BEST: voted rows only)
     if (MODE == GM_BEST) nsel = a.nrows[b];
     if (r0 >= nsel) return;                                    // uniform over the CTA, before any barrier / allocation
+    if (MODE == GM_HIST && a.level > 0 && a.overflow[1] == 0) return;   // no row of the batch asked for the refinement level
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -224,9 +247,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
         float* vt = reinterpret_cast<float*>(scratch + (size_t)3 * G_BM * 8);              // BEST: [2][128]
         uint32_t* hist = reinterpret_cast<uint32_t*>(scratch) + (size_t)row * HIST_WORDS;  // HIST: own row
         const uint32_t hist_s = smem_u32(hist);
-        uint16_t* cand = reinterpret_cast<uint16_t*>(scratch) + (size_t)(row * 4 + qt) * CAND_Q;   // COLLECT
-        float win_lo = 0.f, win_hi = 0.f, hscale = HIST_SCALE0;
-        int below = 0, ncand = 0, krem = 1;
+        // COLLECT scratch: values [128][64] u32 | columns [128][64] u16 | per-row counters [128] | per-thread below [512] | tail values
+        uint32_t* cval = reinterpret_cast<uint32_t*>(scratch) + (size_t)row * CAND_ROW;
+        uint16_t* ccol = reinterpret_cast<uint16_t*>(scratch + (size_t)G_BM * CAND_ROW * 4) + (size_t)row * CAND_ROW;
+        int* ccnt_all = reinterpret_cast<int*>(scratch + (size_t)G_BM * CAND_ROW * 6);
+        int* below_s = ccnt_all + G_BM;
+        float win_lo = 0.f, win_hi = 0.f, hscale4 = 0.f;
+        int below = 0, krem = 1, wcode = 0;
+        bool refine_row = false;
         float vnext = 0.f;
         if (MODE == GM_BEST) {
             bwv = 0.25f * a.bw[b];                                 // threshold in q units
@@ -237,21 +265,31 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
             krem = max(1, min(a.kth[b], N));
             if (a.level > 0 && row_ok) {
                 const int2 ri = a.rowinfo[grow];
-                win_lo = 0.25f * __int_as_float(ri.x);                // window start in q units (rowinfo keeps distance units)
-                krem = ri.y;
-                hscale = HIST_SCALE1;
+                refine_row = ri.y < 0;                                // bit 31
+                if (refine_row) {
+                    win_lo = __int_as_float(ri.x);                    // window start (u units), width 2^-wcode
+                    wcode = (ri.y >> 24) & 0x7f;
+                    krem = ri.y & 0xffffff;
+                    hscale4 = ldexpf(256.0f, wcode);                  // 256 uniform sub-bins
+                }
             }
             epi_barrier();
         }
-        if (MODE == GM_COLLECT && row_ok) {
-            const float lo2 = __int_as_float(a.rowinfo[grow].x);
-            win_lo = 0.25f * (lo2 - BW_MARGIN);
-            win_hi = 0.25f * (lo2 + 1.0f / HIST_SCALE1 + BW_MARGIN);
+        if (MODE == GM_COLLECT) {
+            if (qt == 0) ccnt_all[row] = 0;
+            if (row_ok) {
+                const int2 ri = a.rowinfo[grow];
+                const float lo_u = __int_as_float(ri.x);
+                win_lo = lo_u - BW_MARGIN_U;
+                win_hi = lo_u + ldexpf(1.0f, -((ri.y >> 24) & 0x7f)) + BW_MARGIN_U;
+            }
+            epi_barrier();
         }
 
-        const float hscale4 = 4.0f * hscale;                       // bins per unit of q
-        const uint32_t lo_bits = __float_as_uint(fmaxf(win_lo, 0.f));                 // COLLECT: window as bit patterns of q
+        const uint32_t lo_bits = __float_as_uint(fmaxf(win_lo, 0.f));                 // COLLECT: window as bit patterns of u
         const uint32_t win_bits = __float_as_uint(fmaxf(win_hi, 0.f)) - lo_bits;
+        const bool level0 = a.level == 0;
+        int* ccnt = ccnt_all + row;
         for (int j = 0; j < nt; ++j) {
             const uint32_t buf = j & 1, ph = (j >> 1) & 1;
             const int key0 = j * G_BN;
@@ -270,12 +308,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
             mbar_arrive(&bars->s_free[buf]);                         // S is in registers: the MMA warp may refill it
             const int ncols = min(G_BN, N - key0) - 32 * qt;         // valid columns among this thread's 32
             // per-element epilogue; CHK = false on full tiles (every tile but possibly the last) drops the column test
-            auto consume = [&](auto chk) {
+            auto consume = [&](auto chk, auto lv0) {
                 constexpr bool CHK = decltype(chk)::value;
+                constexpr bool LEVEL0 = decltype(lv0)::value;            // HIST only: logarithmic (true) / uniform sub-bins (false)
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                     if (CHK && e >= ncols) break;
-                    const float dist = tc_q(v[e]);                       // distance / 4
+                    const float dist = (MODE == GM_HIST || MODE == GM_COLLECT) ? tc_u(v[e]) : tc_q(v[e]);   // distance / 4 (+ 2^-15)
                     const int col = key0 + 32 * qt + e;
                     if (MODE == GM_NEAREST) {
                         if (dist < best) { best = dist; besti = col; }
@@ -283,16 +322,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                         const float val = dist < bwv ? vt[buf * G_BN + 32 * qt + e] : 0.f;
                         if (val > best) { best = val; besti = col; }
                     } else if (MODE == GM_HIST) {
-                        // bin = floor((dist - lo) * scale); one unsigned compare covers 0 <= bin < 256; the
-                        // update is a single predicated shared-memory atomic (no divergent region)
-                        // Every element updates the histogram: the ones outside the window go to bin 256, the spare word
-                        // at the end of the row's histogram.  (A conditional update compiles to a BSSY / BRA / BSYNC region per
-                        // element, and the C++ atomicAdd on a generic pointer to a generic ATOM: 19.5 instructions per element.)
-                        // bin = floor((dist - lo) * scale) through a round-down FMA onto 2^23 (FMA pipe; F2I is an 8-cycle XU
-                        // instruction): the low mantissa bits of floor(y) + 2^23 are floor(y) for 0 <= y < 2^22, and anything
-                        // below the window wraps to a huge unsigned value, i.e. to the spare bin as well
-                        const float biased = __fmaf_rd(dist - win_lo, hscale4, 8388608.0f);
-                        const uint32_t ub = __float_as_uint(biased) - 0x4b000000u;
+                        // One predicated shared-memory atomic per element, no divergent region (a conditional update compiles to a
+                        // BSSY / BRA / BSYNC region per element and the C++ atomicAdd on a generic pointer to a generic ATOM: 19.5
+                        // instructions per element).  Elements outside [0, 256) -- u >= 1 at level 0, anything outside the
+                        // row's window at level 1 (negative values wrap to huge unsigned ones) -- update nothing.
+                        //   level 0: bin = top bits of u (logarithmic, 16 bins per binade)
+                        //   level 1: bin = floor((u - lo) * 256 / width) through a round-down FMA onto 2^23 (FMA pipe; F2I is an
+                        //            8-cycle XU instruction): the low mantissa bits of floor(y) + 2^23 are floor(y) for 0 <= y < 2^22
+                        uint32_t ub;
+                        if (LEVEL0) {
+                            ub = (__float_as_uint(dist) >> LOG_SHIFT) - LOG_BASE;
+                        } else {
+                            const float biased = __fmaf_rd(dist - win_lo, hscale4, 8388608.0f);
+                            ub = refine_row ? __float_as_uint(biased) - 0x4b000000u : 0xffffffffu;
+                        }
                         const uint32_t sh = (ub & 1u) << 4;
                         asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, 256;\n\t@p red.shared.add.u32 [%1], %2;\n\t}"
                                      :: "r"(ub), "r"(hist_s + ((ub >> 1) << 2)), "r"(1u << sh) : "memory");
@@ -301,16 +344,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                         // float compares on the (half-rate) ALU pipe
                         const uint32_t qb = __float_as_uint(dist);
                         below += qb < lo_bits ? 1 : 0;
-                        if (qb - lo_bits <= win_bits) {
-                            if (ncand < CAND_Q) cand[ncand] = (uint16_t)col;
-                            ++ncand;
+                        if (qb - lo_bits <= win_bits) {                  // rare: one list per row, slots handed out atomically
+                            const int slot = atomicAdd(ccnt, 1);
+                            if (slot < CAND_ROW) { cval[slot] = qb; ccol[slot] = (uint16_t)col; }
                         }
                     } else if (row_ok) {
                         a.dump[grow * N + col] = 4.0f * dist;
                     }
                 }
             };
-            if (ncols >= 32) consume(std::false_type{}); else consume(std::true_type{});
+            if (MODE == GM_HIST && level0) {
+                if (ncols >= 32) consume(std::false_type{}, std::true_type{}); else consume(std::true_type{}, std::true_type{});
+            } else {
+                if (ncols >= 32) consume(std::false_type{}, std::false_type{}); else consume(std::true_type{}, std::false_type{});
+            }
         }
 
         // ---- per-mode finalisation
@@ -331,72 +378,105 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
             }
         } else if (MODE == GM_HIST) {
             epi_barrier();
-            if (qt == 0 && row_ok) {
-                int cum = 0, bin = HIST_BINS - 1, before = 0;
+            if (qt == 0 && row_ok && (level0 || refine_row)) {
+                int cum = 0, bin = HIST_BINS - 1, before = 0, cnt = 0;
                 bool found = false;
                 for (int q = 0; q < HIST_BINS / 2 && !found; ++q) {
                     const uint32_t w = hist[q];
                     const int c0 = (int)(w & 0xffffu), c1 = (int)(w >> 16);
-                    if (cum + c0 >= krem) { bin = 2 * q; before = cum; found = true; }
-                    else if (cum + c0 + c1 >= krem) { bin = 2 * q + 1; before = cum + c0; found = true; }
+                    if (cum + c0 >= krem) { bin = 2 * q; before = cum; cnt = c0; found = true; }
+                    else if (cum + c0 + c1 >= krem) { bin = 2 * q + 1; before = cum + c0; cnt = c1; found = true; }
                     cum += c0 + c1;
                 }
-                if (!found) before = max(0, krem - 1);          // cannot happen (bins partition the window)
-                const float lo_new = 4.0f * win_lo + (float)bin / hscale;   // distance units; exact: multiples of 2^-6 / 2^-14 below 4
-                a.rowinfo[grow] = make_int2(__float_as_int(lo_new), krem - before);
+                // not found: the k-th smallest lies among the elements with u >= 1 (distance 4, antipodal rows) at level 0;
+                // COLLECT then finds no consistent rank in the last bin's window and raises the overflow flag
+                if (!found) before = max(0, krem - 1);
+                if (level0) {
+                    const uint32_t lo_u = (LOG_BASE + (uint32_t)bin) << LOG_SHIFT;            // bits of the bin's lower edge
+                    const int code = 131 - (int)(lo_u >> 23);                                  // bin width 2^(E - 127 - 4) = 2^-code
+                    const bool mark = found && cnt > REFINE_ABOVE;
+                    if (mark) atomicOr(a.overflow + 1, 1);
+                    a.rowinfo[grow] = make_int2((int)lo_u, (krem - before) | (code << 24) | (mark ? (int)0x80000000u : 0));
+                } else {
+                    const float lo_new = win_lo + ldexpf((float)bin, -(wcode + 8));           // exact: a multiple of the sub-bin width
+                    a.rowinfo[grow] = make_int2(__float_as_int(lo_new), (krem - before) | ((wcode + 8) << 24));
+                }
             }
         } else if (MODE == GM_COLLECT) {
-            // exact fp32 recompute of the candidates: every epilogue warp owns 8 rows and works on 4 of them at a time,
-            // 8 lanes per row (lane l8 of a group owns dims 16 l8 .. 16 l8 + 15), 4 candidates per row in flight -- the
-            // global-load latency of the candidate rows is what this tail costs, so it is paid twice per warp, not 8 times
-            float* vals_w = reinterpret_cast<float*>(scratch + (size_t)G_EPI * CAND_Q * 2) + ew * 16 * CAND_Q;
-            int* below_s = reinterpret_cast<int*>(scratch + (size_t)G_EPI * CAND_Q * 2 + 16 * 16 * CAND_Q * sizeof(float));
-            int* ncand_s = below_s + G_EPI;
+            // Tail.  Every epilogue warp owns 8 rows and works on 4 of them at a time, 8 lanes per row.
+            //  (1) t_k = the (k - below)-th smallest kept tensor-core value (rank counting over <= 64 values);
+            //  (2) the kept elements within BW_MARGIN_U of t_k are the only ones whose fp32 order can differ from their
+            //      tensor-core order: L = number of kept elements below that band, the band's columns are compacted;
+            //  (3) exact fp32 recompute of the band (lane l8 of a group owns dims 16 l8 .. 16 l8 + 15, 4 candidates in
+            //      flight) and the (k - below - L)-th smallest of those = the exact fp32 order statistic.
             below_s[row * 4 + qt] = below;
-            ncand_s[row * 4 + qt] = ncand;
             epi_barrier();
+            float* vals_w = reinterpret_cast<float*>(scratch + (size_t)G_BM * CAND_ROW * 6 + (size_t)(G_BM + G_EPI) * sizeof(int)) + ew * 4 * CAND_ROW;
             const int k = max(1, min(a.kth[b], N));
-            const uint16_t* call = reinterpret_cast<const uint16_t*>(scratch);
             const int grp = lane >> 3, l8 = lane & 7;
-            float* vals = vals_w + grp * 4 * CAND_Q;
+            float* vals = vals_w + grp * CAND_ROW;
             for (int rr = 0; rr < 2; ++rr) {
                 const int r = 8 * ew + 4 * rr + grp;
                 const bool in_range = r0 + r < N;
-                int n4[4] = {0, 0, 0, 0}, nc = 0, bel = 0;
+                uint32_t* rv = reinterpret_cast<uint32_t*>(scratch) + (size_t)r * CAND_ROW;
+                uint16_t* rc = reinterpret_cast<uint16_t*>(scratch + (size_t)G_BM * CAND_ROW * 4) + (size_t)r * CAND_ROW;
+                int nc = 0, bel = 0;
                 bool over = false;
                 if (in_range) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        n4[q] = ncand_s[4 * r + q];
-                        over |= n4[q] > CAND_Q;
-                        nc += n4[q];
-                        bel += below_s[4 * r + q];
-                    }
+                    nc = ccnt_all[r];
+                    over = nc > CAND_ROW;
+                    bel = (below_s[4 * r] + below_s[4 * r + 1]) + (below_s[4 * r + 2] + below_s[4 * r + 3]);
                 }
-                const int m = k - bel;                                          // m-th smallest candidate (1-based)
+                const int m = k - bel;                                          // m-th smallest kept element (1-based)
                 const bool bad = in_range && (over || m < 1 || m > nc);
                 if (bad && l8 == 0) { atomicExch(a.overflow, 1); a.rowval[(size_t)b * N + r0 + r] = 0.f; }
                 if (!in_range || bad) nc = 0;
+                // (1) t_k on the tensor-core values (bit patterns order like the values; ties broken by list position)
+                uint32_t tk = 0u;
+                bool have = false;
+                for (int ci = l8; ci < nc; ci += 8) {
+                    const uint32_t vi = rv[ci];
+                    int rank = 0;
+                    for (int cj = 0; cj < nc; ++cj) {
+                        const uint32_t vj = rv[cj];
+                        rank += (vj < vi || (vj == vi && cj < ci)) ? 1 : 0;
+                    }
+                    if (rank == m - 1) { tk = vi; have = true; }
+                }
+                unsigned ball = (__ballot_sync(0xffffffffu, have) >> (8 * grp)) & 0xffu;
+                tk = __shfl_sync(0xffffffffu, tk, ball ? 8 * grp + __ffs(ball) - 1 : lane);       // every lane takes part
+                // (2) band around t_k: lane 0 of the group compacts its columns to the front of the row's column list
+                int ns = 0, L = 0;
+                if (l8 == 0 && nc > 0) {
+                    const float tkf = __uint_as_float(tk);
+                    const uint32_t band_lo = __float_as_uint(fmaxf(tkf - BW_MARGIN_U, 0.f)), band_hi = __float_as_uint(tkf + BW_MARGIN_U);
+                    for (int ci = 0; ci < nc; ++ci) {
+                        const uint32_t vi = rv[ci];
+                        const uint16_t cc = rc[ci];
+                        if (vi < band_lo) ++L;
+                        else if (vi <= band_hi) rc[ns++] = cc;                  // ns <= ci: never overwrites an unread entry
+                    }
+                }
+                ns = __shfl_sync(0xffffffffu, ns, 8 * grp);
+                L = __shfl_sync(0xffffffffu, L, 8 * grp);
+                __syncwarp();
+                const int mm = m - L;                                           // rank inside the band (1-based)
+                // (3) exact fp32 distances of the band
                 float4 xr[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    xr[e] = nc > 0 ? __ldg(reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + r0 + r) * G_D) + 4 * l8 + e)
+                    xr[e] = ns > 0 ? __ldg(reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + r0 + r) * G_D) + 4 * l8 + e)
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-                auto cand_of = [&](int ci) -> int {
-                    int q = 0;
-                    while (q < 3 && ci >= n4[q]) { ci -= n4[q]; ++q; }
-                    return call[(size_t)(4 * r + q) * CAND_Q + ci];
-                };
-                int ncmax = nc;                                                 // warp-uniform trip count
+                int nsmax = ns;                                                 // warp-uniform trip count
 #pragma unroll
-                for (int o = 8; o < 32; o <<= 1) ncmax = max(ncmax, __shfl_xor_sync(0xffffffffu, ncmax, o));
-                for (int c0 = 0; c0 < ncmax; c0 += 4) {
+                for (int o = 8; o < 32; o <<= 1) nsmax = max(nsmax, __shfl_xor_sync(0xffffffffu, nsmax, o));
+                for (int c0 = 0; c0 < nsmax; c0 += 4) {
                     float acc[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         acc[u] = 0.f;
-                        if (c0 < nc) {
-                            const float4* wrow = reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + cand_of(min(c0 + u, nc - 1))) * G_D) + 4 * l8;
+                        if (c0 < ns) {
+                            const float4* wrow = reinterpret_cast<const float4*>(a.X32 + ((size_t)b * N + rc[min(c0 + u, ns - 1)]) * G_D) + 4 * l8;
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float4 w = __ldg(wrow + e);
@@ -408,22 +488,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                     for (int u = 0; u < 4; ++u)
 #pragma unroll
                         for (int o = 4; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-                    if (l8 < 4 && c0 + l8 < nc)
+                    if (l8 < 4 && c0 + l8 < ns)
                         vals[c0 + l8] = 2.0f - 2.0f * (l8 == 0 ? acc[0] : l8 == 1 ? acc[1] : l8 == 2 ? acc[2] : acc[3]);
                 }
                 __syncwarp();
                 float found = 0.f;
-                bool have = false;
-                for (int ci = l8; ci < nc; ci += 8) {
+                have = false;
+                for (int ci = l8; ci < ns; ci += 8) {
                     const float vi = vals[ci];
                     int rank = 0;
-                    for (int cj = 0; cj < nc; ++cj) {
+                    for (int cj = 0; cj < ns; ++cj) {
                         const float vj = vals[cj];
                         rank += (vj < vi || (vj == vi && cj < ci)) ? 1 : 0;
                     }
-                    if (rank == m - 1) { found = vi; have = true; }
+                    if (rank == mm - 1) { found = vi; have = true; }
                 }
-                const unsigned ball = (__ballot_sync(0xffffffffu, have) >> (8 * grp)) & 0xffu;
+                ball = (__ballot_sync(0xffffffffu, have) >> (8 * grp)) & 0xffu;
                 const float res = __shfl_sync(0xffffffffu, found, ball ? 8 * grp + __ffs(ball) - 1 : lane);   // every lane takes part
                 if (nc > 0 && l8 == 0) {
                     if (ball) a.rowval[(size_t)b * N + r0 + r] = sqrtf(fmaxf(res, 1e-6f));           // guard_sqrt(., 1e-6)
@@ -508,10 +588,10 @@ int prifit_tc_bandwidth_rows(const float* X, int B, int N, const int32_t* kth, _
     if (rc) return rc;
     GramArgs a = {};
     a.Xs = Xs_ws; a.X32 = X; a.N = N; a.B = B; a.kth = kth; a.rowinfo = rowinfo_ws; a.rowval = rowval; a.overflow = overflow;
-    a.level = 0;
+    a.level = 0;                                   // logarithmic bins: one pass locates the k-th to 6 %
     rc = launch_gram<GM_HIST>(map, a, st);
     if (rc) return rc;
-    a.level = 1;
+    a.level = 1;                                   // every CTA returns at once unless level 0 set overflow[1] (a crowded bin)
     rc = launch_gram<GM_HIST>(map, a, st);
     if (rc) return rc;
     return launch_gram<GM_COLLECT>(map, a, st);

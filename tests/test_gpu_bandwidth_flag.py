@@ -31,3 +31,32 @@ def test_duplicates_trigger_the_device_fallback(cuda):
     bw = ops.bandwidth(X, torch.tensor([30], dtype=torch.int32, device=cuda))
     assert ops.last_bandwidth_fell_back()
     assert float(bw[0]) == pytest.approx(1e-3, rel=1e-4)
+
+
+@pytest.mark.parametrize("family", ["hier", "smooth", "unbalanced", "random"])
+def test_log_binned_bandwidth_is_exact_over_distance_scales(cuda, family):
+    """The logarithmic histogram level covers distances from 6e-5 to 4: tight clusters (hier: k-th distances ~ 0.006),
+    smooth embeddings without modes, unbalanced noisy clusters, i.i.d. directions (distances ~ 2) -- the tensor-core path
+    must return the exact fp32 order statistic of the CUDA-core kernel for several quantiles, without falling back."""
+    from prifit_b200 import _lib, ops, synthetic
+
+    if family == "hier":
+        E, _, _ = synthetic.hier_shapes(2, seed=11)
+    elif family == "smooth":
+        E, _ = synthetic.smooth_shapes(2, n_points=1536, freq=0.5, seed=12)
+    elif family == "unbalanced":
+        E, _, _ = synthetic.unbalanced_shapes(2, n_points=2048, sigma=0.03, seed=13)
+    else:
+        E, _ = synthetic.random_shapes(2, n_points=1280, seed=14)
+    X = R.normalize_twice(E).to(cuda)
+    n = X.shape[1]
+    for q in (0.01, 0.05, 0.3):
+        k = torch.full((2,), int(q * n), dtype=torch.int32, device=cuda)
+        bw = ops.bandwidth(X, k)
+        assert not ops.last_bandwidth_fell_back(), (family, q)
+        prev = _lib.load().prifit_set_gram_engine(1)
+        try:
+            exact = ops.bandwidth(X, k)
+        finally:
+            _lib.load().prifit_set_gram_engine(prev)
+        assert float((bw - exact).abs().max() / exact.abs().max()) < 1e-6, (family, q, bw.tolist(), exact.tolist())
