@@ -126,7 +126,20 @@ def launch_count():
     return _launches
 
 
+# bench.py sets this to a list to collect (entry point, start event, end event) around every C-ABI call of the eager path
+# (CUDA events on the launching stream -- the stream handle is the last argument of every entry point)
+TIMING = None
+
+
 def call(name, *args):
     global _launches
-    check(getattr(load(), name)(*args), name)
+    if TIMING is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(load(), name)(*args), name)
+        e1.record()
+        TIMING.append((name, e0, e1))
+    else:
+        check(getattr(load(), name)(*args), name)
     _launches += LAUNCHES.get(name, 0)

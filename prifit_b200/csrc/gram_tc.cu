@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
         float* vt = reinterpret_cast<float*>(scratch + (size_t)3 * G_BM * 8);              // BEST: [2][128]
         uint32_t* hist = reinterpret_cast<uint32_t*>(scratch) + (size_t)row * HIST_WORDS;  // HIST: own row
         const uint32_t hist_s = smem_u32(hist);
+        const uint32_t hist_log = hist_s - ((LOG_BASE >> 1) << 2);                         // level 0: word (bits >> 20) of the row
         // COLLECT scratch: values [128][64] u32 | columns [128][64] u16 | per-row counters [128] | per-thread below [512] | tail values
         uint32_t* cval = reinterpret_cast<uint32_t*>(scratch) + (size_t)row * CAND_ROW;
         uint16_t* ccol = reinterpret_cast<uint16_t*>(scratch + (size_t)G_BM * CAND_ROW * 4) + (size_t)row * CAND_ROW;
@@ -329,16 +330,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                         //   level 0: bin = top bits of u (logarithmic, 16 bins per binade)
                         //   level 1: bin = floor((u - lo) * 256 / width) through a round-down FMA onto 2^23 (FMA pipe; F2I is an
                         //            8-cycle XU instruction): the low mantissa bits of floor(y) + 2^23 are floor(y) for 0 <= y < 2^22
-                        uint32_t ub;
                         if (LEVEL0) {
-                            ub = (__float_as_uint(dist) >> LOG_SHIFT) - LOG_BASE;
+                            // bin = (bits >> 19) - LOG_BASE; u >= 2^-16 always, so the range test is one compare against the
+                            // bits of 1.0f; word address and half-word shift come straight from the bit pattern (6 ALU-pipe
+                            // instructions per element: SHF, LEA, SHF, LOP, SHL, ISETP -- the ALU pipe is what bounds HIST)
+                            const uint32_t bits = __float_as_uint(dist);
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, 0x3f800000;\n\t@p red.shared.add.u32 [%1], %2;\n\t}"
+                                         :: "r"(bits), "r"(hist_log + ((bits >> 20) << 2)), "r"(1u << ((bits >> 15) & 16u)) : "memory");
                         } else {
                             const float biased = __fmaf_rd(dist - win_lo, hscale4, 8388608.0f);
-                            ub = refine_row ? __float_as_uint(biased) - 0x4b000000u : 0xffffffffu;
+                            const uint32_t ub = refine_row ? __float_as_uint(biased) - 0x4b000000u : 0xffffffffu;
+                            const uint32_t sh = (ub & 1u) << 4;
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, 256;\n\t@p red.shared.add.u32 [%1], %2;\n\t}"
+                                         :: "r"(ub), "r"(hist_s + ((ub >> 1) << 2)), "r"(1u << sh) : "memory");
                         }
-                        const uint32_t sh = (ub & 1u) << 4;
-                        asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, 256;\n\t@p red.shared.add.u32 [%1], %2;\n\t}"
-                                     :: "r"(ub), "r"(hist_s + ((ub >> 1) << 2)), "r"(1u << sh) : "memory");
                     } else if (MODE == GM_COLLECT) {
                         // q >= 0, so its bit pattern orders like the value: two integer compares instead of three NaN-aware
                         // float compares on the (half-rate) ALU pipe

@@ -59,4 +59,6 @@ def test_log_binned_bandwidth_is_exact_over_distance_scales(cuda, family):
             exact = ops.bandwidth(X, k)
         finally:
             _lib.load().prifit_set_gram_engine(prev)
-        assert float((bw - exact).abs().max() / exact.abs().max()) < 1e-6, (family, q, bw.tolist(), exact.tolist())
+        # both are exact fp32 order statistics; they differ by the summation order of the 128-term dot product behind
+        # 2 - 2 <x_i, x_j> (one ulp of a number near 1 = 6e-8 on a distance that can be as small as 6e-3: hier, q = 0.01)
+        assert float((bw - exact).abs().max() / exact.abs().max()) < 4e-6, (family, q, bw.tolist(), exact.tolist())
