@@ -379,7 +379,7 @@ def run_ours(args):
                    "guard_passes_mean": passes, "loss": float(last["L"]),
                    "l2": "rotating %d input sets (%.0f MB of embeddings) > 126 MB L2" % (n_sets, n_sets * B * N * D * 4 / 1e6),
                    "parallelism": "shapes sharded %d/GPU, one 8-byte NCCL all-reduce per step" % B,
-                   "execution": ("3 CUDA graphs per step, %d parallel branches of shapes" % graph_step.default_branches()) if use_graph
+                   "execution": ("2 CUDA graphs per step (forward; speculative backward) + the two normalisation kernels, %d parallel branches of shapes" % graph_step.default_branches()) if use_graph
                                 else "eager launches on one stream",
                    "eager_ms_per_step": None if eager_ms is None else round(eager_ms, 4)},
         "e2e": {"value": round(e2e_sps, 2), "unit": "shapes/s", "ms_per_step": round(e2e_ms / args.steps, 4),

@@ -152,6 +152,12 @@ int prifit_fit_bwd(const float* P, const float* W, const int32_t* K, const float
  *   noise) and only the k >= K[b] entries are zeroed -- lets one captured launch sequence serve both cases. */
 int prifit_noise_scatter(const float* flat, const int32_t* K, int B, int Kcap, const int32_t* direct,
                          float* noise_out, void* stream);
+/* The same for the shapes [b0, b0 + Bb) only (all pointers are those of the whole batch). */
+int prifit_noise_scatter_range(const float* flat, const int32_t* K, int b0, int Bb, int Kcap, const int32_t* direct,
+                               float* noise_out, void* stream);
+/* out[2B + 1] = [K | n_labels | ++*serial_inout]: the guard predicate's inputs (src/ellipsoid_utils.py:23) packed for ONE
+ * device -> host copy; the serial number lets a host that polls pinned memory recognise the copy of the current step. */
+int prifit_pack_counts(const int32_t* K, const int32_t* n_labels, int B, int32_t* serial_inout, int32_t* out, void* stream);
 
 /* k8 -- SDF half of the fitting loss.  convex_loss.py:313-343 + src/utils.py:407-411.
  *   Q[B,M,3]; loss_out[B] = 0.5 * mean_j (min_k |sdf_kj|)^2 over valid ellipsoids (0 if none);

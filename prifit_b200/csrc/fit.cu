@@ -444,8 +444,8 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_bwd_kernel(
 // attempted cluster, shapes outer / clusters inner (src/ellipsoid_fitting.py:38), so cluster (b, k) owns draw number
 // prefix(b) + k of the host stream.  Done on the device so that the host need not know K to stage the draws.
 __global__ void noise_scatter_kernel(const float* __restrict__ flat, const int32_t* __restrict__ K, int Kcap,
-                                     const int32_t* __restrict__ direct, float* __restrict__ noise) {
-    const int b = blockIdx.x;
+                                     const int32_t* __restrict__ direct, float* __restrict__ noise, int b0) {
+    const int b = b0 + blockIdx.x;
     int off = 0;
     if (direct && *direct) {
         off = b * Kcap;                                  // flat is already laid out [B, Kcap, 3, 3]
@@ -461,7 +461,35 @@ extern "C" int prifit_noise_scatter(const float* flat, const int32_t* K, int B, 
                                     float* noise_out, void* stream) {
     PF_CHECK_ARG(flat && K && noise_out, PRIFIT_E_BADARG, "null pointer");
     PF_CHECK_ARG(B > 0 && Kcap > 0, PRIFIT_E_BADARG, "B, Kcap > 0 required");
-    noise_scatter_kernel<<<B, 128, 0, pf_stream(stream)>>>(flat, K, Kcap, direct, noise_out);
+    noise_scatter_kernel<<<B, 128, 0, pf_stream(stream)>>>(flat, K, Kcap, direct, noise_out, 0);
+    PF_LAUNCH_CHECK();
+    return 0;
+}
+
+// the same for the shapes [b0, b0 + Bb) of the batch only (pointers are those of the whole batch): cluster (b, k) needs the
+// counts of the shapes in front of it, so a group of shapes can be served as soon as the groups before it have their counts
+extern "C" int prifit_noise_scatter_range(const float* flat, const int32_t* K, int b0, int Bb, int Kcap, const int32_t* direct,
+                                          float* noise_out, void* stream) {
+    PF_CHECK_ARG(flat && K && noise_out, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(b0 >= 0 && Bb > 0 && Kcap > 0, PRIFIT_E_BADARG, "b0 >= 0, Bb, Kcap > 0 required");
+    noise_scatter_kernel<<<Bb, 128, 0, pf_stream(stream)>>>(flat, K, Kcap, direct, noise_out, b0);
+    PF_LAUNCH_CHECK();
+    return 0;
+}
+
+// [K[0..B) | n_labels[0..B) | ++serial] -> out[2B + 1]: what the host's guard decision needs, in one buffer for one D2H copy;
+// the serial number tells the polling host that the copy it sees belongs to this replay
+__global__ void pack_counts_kernel(const int32_t* __restrict__ K, const int32_t* __restrict__ nlab, int B,
+                                   int32_t* __restrict__ serial, int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) { out[i] = K[i]; out[B + i] = nlab[i]; }
+    if (i == 0) { const int32_t s = *serial + 1; *serial = s; out[2 * B] = s; }
+}
+
+extern "C" int prifit_pack_counts(const int32_t* K, const int32_t* nlab, int B, int32_t* serial_inout, int32_t* out, void* stream) {
+    PF_CHECK_ARG(K && nlab && serial_inout && out, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(B > 0, PRIFIT_E_BADARG, "B > 0 required");
+    pack_counts_kernel<<<(B + 127) / 128, 128, 0, pf_stream(stream)>>>(K, nlab, B, serial_inout, out);
     PF_LAUNCH_CHECK();
     return 0;
 }

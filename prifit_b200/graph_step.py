@@ -1,9 +1,15 @@
-"""The whole hot path of one batch as three CUDA graphs over static buffers, launched back to back.
+"""The whole hot path of one batch as two CUDA graphs over static buffers, launched back to back.
 
-    graph 1  (per branch)  normalise x2 -> bandwidth -> T mean-shift iterations -> NMS     | counts -> pinned host
-    graph 2  noise scatter | (per branch) K-seed trajectories -> membership -> fit -> SDF  | batch mean
-    graph 3  (per branch) SDF -> fit -> membership -> K-seed trajectories backward of  sum_b has_b loss_b   (speculative)
-    + one kernel at autograd-backward time: normalise backward with the upstream scale dL/d(loss) applied
+    kernel   normalise x2 of the caller's embeddings (read in place, row-major or channel-first) -> X
+    graph A  (per branch) bandwidth -> T mean-shift iterations -> NMS -> noise scatter -> K-seed trajectories -> membership
+             -> fit -> SDF            | counts + serial -> pinned host as soon as every branch's NMS is done | batch mean
+    graph B  (per branch) SDF -> fit -> membership -> K-seed trajectories backward of  sum_b has_b loss_b   (speculative)
+    kernel   at autograd-backward time: normalise backward with the upstream scale dL/d(loss) applied
+
+Inside graph A a branch runs straight from its NMS into its own latency chain (its noise matrices only need the cluster
+counts of the shapes in front of it); nothing joins the branches between the cluster stage and the chains, and there is no
+graph boundary (launch gap) either.  The host learns the counts by polling pinned memory for the step's serial number,
+which graph A copies out together with them in the middle of its run.
 
 The backward of the path is linear in dL/d(loss), so when the embeddings require a gradient graph 3 is enqueued right
 behind graph 2 -- before the host has made the guard decision and before autograd asks for it -- computing the gradient
@@ -98,8 +104,8 @@ class GraphStep:
         def buf(*shape, dtype=f32):
             return torch.empty(*shape, dtype=dtype, device=device)
 
-        # ---- static inputs
-        self.E, self.P = (buf(B, d, N) if cf else buf(B, N, d)), buf(B, N, 3)
+        # ---- static inputs (the embeddings are NOT copied: the normalisation kernels read the caller's tensor in place)
+        self.P = buf(B, N, 3)
         self.Q = self.P if M is None else buf(B, M, 3)
         self.Mq = N if M is None else M
         self.flat = buf(B * kcap, 3, 3)
@@ -128,7 +134,11 @@ class GraphStep:
         self.gloss, self.gs, self.gV, self.gc = buf(B), buf(B, kcap, 3), buf(B, kcap, 3, 3), buf(B, kcap, 3)
         self.gW, self.gC, self.gX = buf(B, kcap, N), buf(B, kcap, d), buf(B, N, d)
         self.gE = buf(B, d, N) if cf else buf(B, N, d)
-        self.counts = torch.zeros(2, B, dtype=i32).pin_memory()
+        self.counts = torch.zeros(2 * B + 1, dtype=i32).pin_memory()      # [K | n_labels | serial], polled by the host
+        self.counts_np = self.counts.numpy()
+        self.counts_dev = torch.zeros(2 * B + 1, dtype=i32, device=device)
+        self.serial_dev = torch.zeros(1, dtype=i32, device=device)
+        self.replays = 0
         # ---- per-branch workspaces
         self.ws = []
         for lo, hi in self.ranges:
@@ -160,46 +170,53 @@ class GraphStep:
         for st in self.streams:
             main.wait_stream(st)
 
-    def _seq_cluster(self):
-        N, d, T, kcap, sm = self.N, self.d, self.T, self.kcap, self.small
+    def _normalize_fwd(self, E):
+        """E: the caller's embeddings, [B,N,d] contiguous or (cf) [B,d,N] contiguous -> self.X."""
+        if self.cf:
+            _lib.call("prifit_normalize_fwd_cf", _ptr(E), self.B, self.N, self.d, _ptr(self.X), _stream())
+        else:
+            _lib.call("prifit_normalize_fwd", _ptr(E), self.B * self.N, self.d, _ptr(self.X), _stream())
 
-        def branch(i, lo, hi):
-            Bb, ws, st = hi - lo, self.ws[i], _stream()
-            X, bw, newX = self.X[lo:hi], sm["bw"][lo:hi], self.newX[lo:hi]
-            if self.cf:
-                _lib.call("prifit_normalize_fwd_cf", _ptr(self.E[lo:hi]), Bb, N, d, _ptr(X), st)
-            else:
-                _lib.call("prifit_normalize_fwd", _ptr(self.E[lo:hi]), Bb * N, d, _ptr(X), st)
-            _lib.call("prifit_bandwidth_fwd", _ptr(X), Bb, N, d, None, N, _ptr(self.kth[lo:hi]), _ptr(bw),
-                      _ptr(ws["bw"][0]), ws["bw"][1], st)
-            _lib.call("prifit_meanshift_fwd", _ptr(X), _ptr(bw), Bb, N, d, T, _ptr(newX), self.engine,
-                      _ptr(ws["ms"][0]), ws["ms"][1], st)
-            _lib.call("prifit_nms_fwd", _ptr(newX), _ptr(bw), Bb, N, d, kcap, _ptr(sm["idx"][lo:hi]), _ptr(sm["K"][lo:hi]),
-                      _ptr(sm["labels"][lo:hi]), _ptr(sm["nlab"][lo:hi]), _ptr(ws["nms"][0]), ws["nms"][1], st)
-
-        self._fork_join(branch)
-        self.counts[0].copy_(sm["K"], non_blocking=True)
-        self.counts[1].copy_(sm["nlab"], non_blocking=True)
-
-    def _seq_rest(self):
+    def _seq_forward(self):
         B, N, d, T, kcap, M, sm = self.B, self.N, self.d, self.T, self.kcap, self.Mq, self.small
-        _lib.call("prifit_noise_scatter", _ptr(self.flat), _ptr(sm["K"]), B, kcap, _ptr(self.direct), _ptr(self.noise), _stream())
-
-        def branch(i, lo, hi):
-            Bb, ws, st = hi - lo, self.ws[i], _stream()
-            X, bw, idx, K = self.X[lo:hi], sm["bw"][lo:hi], sm["idx"][lo:hi], sm["K"][lo:hi]
-            C, W = self.C[lo:hi], self.W[lo:hi]
-            s, V, c, valid = sm["s"][lo:hi], sm["V"][lo:hi], sm["c"][lo:hi], sm["valid"][lo:hi]
-            _lib.call("prifit_meanshift_rows_fwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), Bb, N, d, T, kcap,
-                      _ptr(self.traj[lo:hi]), _ptr(self.stat[lo:hi]), _ptr(C), self.rows_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
-            _lib.call("prifit_membership_fwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), Bb, N, d, kcap, _ptr(W), _ptr(self.smax[lo:hi]),
-                      _ptr(ws["memb"][0]), ws["memb"][1], st)
-            _lib.call("prifit_fit_fwd", _ptr(self.P[lo:hi]), _ptr(W), _ptr(K), _ptr(self.noise[lo:hi]), Bb, N, kcap,
-                      _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(self.fctx[lo:hi]), st)
-            _lib.call("prifit_sdf_loss_fwd", _ptr(self.Q[lo:hi]), _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(K), Bb, M, kcap,
-                      _ptr(sm["loss_b"][lo:hi]), _ptr(self.argmin[lo:hi]), _ptr(self.sdf[lo:hi]), _ptr(ws["sdf"][0]), ws["sdf"][1], st)
-
-        self._fork_join(branch)
+        main = torch.cuda.current_stream()
+        nms_done = [torch.cuda.Event() for _ in self.ranges]
+        for i, (lo, hi) in enumerate(self.ranges):
+            st_ = self.streams[i]
+            st_.wait_stream(main)
+            with torch.cuda.stream(st_):
+                Bb, ws, st = hi - lo, self.ws[i], _stream()
+                X, bw, newX = self.X[lo:hi], sm["bw"][lo:hi], self.newX[lo:hi]
+                idx, K = sm["idx"][lo:hi], sm["K"][lo:hi]
+                C, W = self.C[lo:hi], self.W[lo:hi]
+                s, V, c, valid = sm["s"][lo:hi], sm["V"][lo:hi], sm["c"][lo:hi], sm["valid"][lo:hi]
+                _lib.call("prifit_bandwidth_fwd", _ptr(X), Bb, N, d, None, N, _ptr(self.kth[lo:hi]), _ptr(bw),
+                          _ptr(ws["bw"][0]), ws["bw"][1], st)
+                _lib.call("prifit_meanshift_fwd", _ptr(X), _ptr(bw), Bb, N, d, T, _ptr(newX), self.engine,
+                          _ptr(ws["ms"][0]), ws["ms"][1], st)
+                _lib.call("prifit_nms_fwd", _ptr(newX), _ptr(bw), Bb, N, d, kcap, _ptr(idx), _ptr(K),
+                          _ptr(sm["labels"][lo:hi]), _ptr(sm["nlab"][lo:hi]), _ptr(ws["nms"][0]), ws["nms"][1], st)
+                nms_done[i].record(st_)
+                # cluster (b, k) owns draw number prefix(K)[b] + k of the host stream: the counts of the shapes in front
+                for j in range(i):
+                    st_.wait_event(nms_done[j])
+                _lib.call("prifit_noise_scatter_range", _ptr(self.flat), _ptr(sm["K"]), lo, Bb, kcap, _ptr(self.direct),
+                          _ptr(self.noise), st)
+                _lib.call("prifit_meanshift_rows_fwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), Bb, N, d, T, kcap,
+                          _ptr(self.traj[lo:hi]), _ptr(self.stat[lo:hi]), _ptr(C), self.rows_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
+                _lib.call("prifit_membership_fwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), Bb, N, d, kcap, _ptr(W), _ptr(self.smax[lo:hi]),
+                          _ptr(ws["memb"][0]), ws["memb"][1], st)
+                _lib.call("prifit_fit_fwd", _ptr(self.P[lo:hi]), _ptr(W), _ptr(K), _ptr(self.noise[lo:hi]), Bb, N, kcap,
+                          _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(self.fctx[lo:hi]), st)
+                _lib.call("prifit_sdf_loss_fwd", _ptr(self.Q[lo:hi]), _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(K), Bb, M, kcap,
+                          _ptr(sm["loss_b"][lo:hi]), _ptr(self.argmin[lo:hi]), _ptr(self.sdf[lo:hi]), _ptr(ws["sdf"][0]), ws["sdf"][1], st)
+        # the guard predicate's inputs leave for the host as soon as every branch has clustered, beside the chains
+        for ev in nms_done:
+            main.wait_event(ev)
+        _lib.call("prifit_pack_counts", _ptr(sm["K"]), _ptr(sm["nlab"]), B, _ptr(self.serial_dev), _ptr(self.counts_dev), _stream())
+        self.counts.copy_(self.counts_dev, non_blocking=True)
+        for st_ in self.streams:
+            main.wait_stream(st_)
         _lib.call("prifit_masked_mean_fwd", _ptr(sm["loss_b"]), _ptr(sm["valid"]), B, kcap, _ptr(sm["has"]), _ptr(sm["stats"]), _stream())
 
     def _seq_backward(self):
@@ -226,14 +243,14 @@ class GraphStep:
 
         self._fork_join(branch)
 
-    def _scaled_normalize_bwd(self):
-        _lib.call("prifit_normalize_bwd_scaled", _ptr(self.E), _ptr(self.gX), self.B, self.N, self.d, 1 if self.cf else 0,
+    def _scaled_normalize_bwd(self, E):
+        _lib.call("prifit_normalize_bwd_scaled", _ptr(E), _ptr(self.gX), self.B, self.N, self.d, 1 if self.cf else 0,
                   _ptr(self.g_sum), _ptr(self.g_mean), _ptr(self.small["stats"]), _ptr(self.gE), _stream())
 
     def _capture(self):
-        seqs = (self._seq_cluster, self._seq_rest, self._seq_backward)
+        seqs = (self._seq_forward, self._seq_backward)
         # eager warm-up on a side stream (first-call initialisation must not happen inside a capture)
-        self.E.normal_()
+        E0 = torch.randn(self.gE.shape, dtype=torch.float32, device=self.device)
         self.P.uniform_(-1, 1)
         if self.Q is not self.P:
             self.Q.uniform_(-1, 1)
@@ -241,12 +258,14 @@ class GraphStep:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
+            self._normalize_fwd(E0)
             for seq in seqs:
                 seq()
-            self._scaled_normalize_bwd()
+            self._scaled_normalize_bwd(E0)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.graphs = []
+        self.launches = [0, 0]
         for i, seq in enumerate(seqs):
             g = torch.cuda.CUDAGraph()
             before = _lib.launch_count()
@@ -256,6 +275,9 @@ class GraphStep:
             self.launches[i] = _lib.launch_count() - before
             self.graphs.append(g)
         _lib._launches -= sum(self.launches)          # capture enqueues nothing; replays are counted in run_*
+        self.serial_dev.zero_()
+        self.counts.zero_()
+        torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------------------------------ per step
     def run_forward(self, E, P, Q, noise, want_grad=False):
@@ -263,7 +285,6 @@ class GraphStep:
         gradient will be asked for -- the speculative backward graph 3) without waiting for anything and returns the
         result dict; finish_forward() then makes the guard decision."""
         self.serial += 1
-        self.E.copy_(E)
         self.P.copy_(P)
         if self.Q is not self.P:
             self.Q.copy_(Q)
@@ -285,11 +306,10 @@ class GraphStep:
         if want_direct != self.direct_host:
             self.direct.fill_(want_direct)
             self.direct_host = want_direct
+        self._normalize_fwd(E)
+        self.replays += 1
         self.graphs[0].replay()
-        self._ev = torch.cuda.Event()
-        self._ev.record()
-        self.graphs[1].replay()
-        _lib._launches += self.launches[0] + self.launches[1]
+        _lib._launches += self.launches[0]
         self._state = state
         # snapshot of the small outputs: enqueued (and its views built) before the host waits, so that after the
         # read-back the host only has the guard decision between itself and the backward launch
@@ -297,8 +317,8 @@ class GraphStep:
         self._ev_fwd = torch.cuda.Event()
         self._ev_fwd.record()                              # forward results complete: what the multi-GPU all-reduce waits for
         if want_grad:
-            self.graphs[2].replay()                        # speculative: d(sum_b has_b loss_b)/dX into self.gX
-            _lib._launches += self.launches[2]
+            self.graphs[1].replay()                        # speculative: d(sum_b has_b loss_b)/dX into self.gX
+            _lib._launches += self.launches[1]
             self.backward_serial = self.serial
         loss_sum, n_valid, loss = snap["stats"].unbind(0)
         out = dict(snap)
@@ -309,8 +329,18 @@ class GraphStep:
     def finish_forward(self, out):
         """Host side of the guard (src/ellipsoid_utils.py:19-26): waits for graph 1 only (graph 2 keeps the device
         busy), reads the counts, settles the host generator.  False = a shape exceeded the cap: redo eagerly."""
-        self._ev.synchronize()                             # the step's one host synchronisation (2 B int32)
-        K_host, nlab_host = self.counts[0].tolist(), self.counts[1].tolist()
+        # the step's one host synchronisation: poll pinned memory until graph A's copy of [K | n_labels | serial] for THIS
+        # replay has landed (the copy happens in the middle of graph A, so no stream / event wait can express it)
+        want, cn, B = self.replays, self.counts_np, self.B
+        spins, t0 = 0, None
+        while cn[2 * B] != want:
+            spins += 1
+            if spins & 0xffff == 0:
+                import time
+                t0 = t0 or time.time()
+                if time.time() - t0 > 30.0:
+                    raise _lib.PrifitError("graph step: the cluster counts of replay %d never arrived (device error?)" % want)
+        K_host, nlab_host = cn[:B].tolist(), cn[B:2 * B].tolist()
         state = self._state
         if state is not None:
             torch.set_rng_state(state)
@@ -323,7 +353,7 @@ class GraphStep:
         out["K_host"], out["n_labels_host"] = K_host, nlab_host
         return True
 
-    def run_backward(self, serial, g_sum, g_mean):
+    def run_backward(self, serial, g_sum, g_mean, E):
         if serial != self.serial:
             raise _lib.PrifitError("the graph-replayed step's buffers were overwritten by a later forward call before its "
                                    "backward ran; call backward first, or use graph=False / PRIFIT_GRAPH=0")
@@ -336,10 +366,10 @@ class GraphStep:
                 dst.copy_(g.reshape(1))
                 self.g_zero[i] = False
         if self.backward_serial != serial:                 # the forward ran without grad mode's speculation (not expected)
-            self.graphs[2].replay()
-            _lib._launches += self.launches[2]
+            self.graphs[1].replay()
+            _lib._launches += self.launches[1]
             self.backward_serial = serial
-        self._scaled_normalize_bwd()                       # gE = normalize_bwd(E, g * gX)
+        self._scaled_normalize_bwd(E)                      # gE = normalize_bwd(E, g * gX)
         return self.gE
 
 
@@ -349,6 +379,7 @@ class _Attach(torch.autograd.Function):
     @staticmethod
     def forward(ctx, E, step, serial, loss_sum, loss):
         ctx.step, ctx.serial = step, serial
+        ctx.save_for_backward(E)                           # read again by the last backward kernel (autograd checks its version)
         ctx.set_materialize_grads(False)
         return loss_sum.view_as(loss_sum), loss.view_as(loss)
 
@@ -356,7 +387,8 @@ class _Attach(torch.autograd.Function):
     def backward(ctx, g_sum, g_mean):
         if g_sum is None and g_mean is None:
             return None, None, None, None, None
-        gE = ctx.step.run_backward(ctx.serial, g_sum, g_mean)
+        (E,) = ctx.saved_tensors
+        gE = ctx.step.run_backward(ctx.serial, g_sum, g_mean, E)
         # Row-major input: the static buffer itself is handed to autograd -- AccumulateGrad copies a gradient whose
         # tensor object something else still references, every other consumer reads it before the next replay.
         # Channel-first input: the gradient reaches the caller's leaf through view nodes (transpose / permute), whose
@@ -399,6 +431,8 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
     # kernels transpose on the fly and the gradient leaves in the caller's layout
     cf = d == 128 and not E.is_contiguous() and E.transpose(1, 2).is_contiguous()
     src = E.transpose(1, 2) if cf else E
+    if not src.is_contiguous():
+        src = src.contiguous()                             # neither layout: one copy, like the eager path's
     step = get_step(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, E.device,
                     default_branches() if branches is None else int(branches), cf)
     np_state = np.random.get_state()
