@@ -12,13 +12,22 @@
 //
 // and per iteration the epilogue renormalises O row-wise (y' = O / ||O||: the 1/rowsum factor of the
 // reference and the 2^10 scale both cancel in the normalisation) and stores it as the next Q (fp16,
-// SWIZZLE_128B, K-major) in shared memory.  TMEM columns: S0|P0 [0,128)  S1|P1 [128,256)  O [256,384).
+// SWIZZLE_128B, K-major) in shared memory.  TMEM columns: S0|P0 [0,128)  S1|P1 [128,256)  S2|P2 [256,384)  O [384,512).
 //
-// What bounds it.  tcgen05.ld and the A-operand fetch of a TMEM-sourced MMA share a tensor-memory read
-// path of ~64 B/clk/SM: per tile the softmax must read S (64 KB) and GEMM2 reads P (32 KB) -> 1536 clk,
-// against 1024 clk of MMA work and 1024 clk of MUFU work.  An earlier version also kept Q in tensor
-// memory (another 32 KB per tile): 2048 clk per tile, measured 2016.  Q therefore lives in shared
-// memory (128 B/clk, otherwise idle) and only P -- produced in registers right next to it -- stays in TMEM.
+// What bounds it (in-kernel phase clocks, PRIFIT_MS_DBG=1 + scripts/ms_phases.py; profiles/r02_ms_phases.txt).
+// tcgen05.mma issue BLOCKS: the queue behind the issuing thread is only an instruction or two deep, so the
+// thread spends ~83 clk per MMA inside the 16 issue slots of a tile (64 clk nominal for M128 N128 K16; an SS MMA
+// of this shape pulls 8 KB out of shared memory = the SM's whole 128 B/clk, next to the TMA fill) and whatever
+// else it does -- barrier waits, commits -- is time the tensor pipe runs dry.  Hence (round 2):
+//   * three S|P buffers and the issue order G1(j+2) . G2(j): the wait for the softmax of tile j has two GEMMs
+//     queued behind it instead of none;
+//   * the two softmax warps of an SM sub-partition work on DIFFERENT tiles (even / odd) and prefetch the next
+//     32-column chunk of S during the exponentials of the current one: a tile's S -> P latency no longer sits
+//     between two GEMMs of the same buffer, and each softmax warp is busy 1750 of the 3900 clk between its tiles;
+//   * one mbarrier arrival per warp instead of per thread; six ring stages.
+// 551 -> 520 us at cfg2.  Measured and rejected: a CTA-pair version (cta_group::2, M = 256, each CTA supplying
+// half of B's N extent: 96 instead of 128 B/clk of operand traffic) -- bit-identical results, 757 us: every
+// S -> P hand-off then crosses the pair and both tensor pipes run in lock-step with the slower softmax.
 //
 // Why kind::f16 and not kind::tf32: fp16 carries the same 10-bit mantissa as tf32 and every operand
 // here lives in [6e-5, 2^10] (unit vectors, weights pre-scaled by 2^10), so the rounding is the same;
@@ -27,7 +36,7 @@
 // halves the tile bytes and doubles the MMA rate.
 //
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-11 = softmax / epilogue (two warps per TMEM lane quarter: thread = seed row x 64-key half).
+// warps 4-11 = softmax (warps 4-7 even key tiles, 8-11 odd ones; thread = seed row) / epilogue (thread = seed row x 64-column half).
 //
 // This pass only feeds the NMS (discrete outcome); the K centres that carry gradient are recomputed in
 // fp32 (meanshift_rows.cu).
@@ -44,12 +53,13 @@ namespace {
 constexpr int TC_D = 128;
 constexpr int TC_BM = 128;                 // seed rows per CTA
 constexpr int TC_BN = 128;                 // keys per tile
-constexpr int TC_STAGES = 5;
+constexpr int TC_STAGES = 6;
 constexpr uint32_t TC_TILE_BYTES = TC_BN * TC_D * 2;      // 32768
 constexpr uint32_t TC_KBLOCK_BYTES = TC_BN * 128;          // one 64-column (128 B) block of the tile
 constexpr int TC_THREADS = 384;             // warps 0-2: TMA / MMA / TMEM alloc, warps 4-11: softmax
 constexpr int TC_SOFTMAX = 256;             // softmax threads: (seed row, 64-key half of every tile)
-constexpr uint32_t COL_S0 = 0, COL_O = 256;
+constexpr int TC_SBUF = 3;                 // S|P accumulators in flight
+constexpr uint32_t COL_S0 = 0, COL_O = 128 * TC_SBUF;      // 3 x 128 + 128 = all 512 columns
 constexpr uint32_t TC_Q_BYTES = TC_BM * TC_D * 2;            // Q tile: two 64-column blocks of [128 rows][128 B]
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float P_SCALE_LOG2 = 10.0f;      // weights are stored as 2^10 * kappa (keeps e^-13 a normal f16)
@@ -57,12 +67,12 @@ constexpr float P_SCALE_LOG2 = 10.0f;      // weights are stored as 2^10 * kappa
 struct TcBarriers {
     uint64_t x_full[TC_STAGES];
     uint64_t x_empty[TC_STAGES];
-    uint64_t s_full[2];
-    uint64_t p_full[2];
+    uint64_t s_full[TC_SBUF];
+    uint64_t p_full[TC_SBUF];
     uint64_t o_full;
     uint64_t q_full;
     uint32_t tmem_base;
-    float ssum[2][2][TC_BM];     // [iteration parity][column half][row] partial ||O||^2
+    float ssum[2][TC_BM];        // [column half][row] partial ||O||^2 (rewritten only after every warp's q_full arrival of the iteration)
 };
 
 constexpr size_t TC_SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)TC_STAGES * TC_TILE_BYTES + TC_Q_BYTES + sizeof(TcBarriers);
@@ -74,6 +84,7 @@ __global__ void to_half_kernel(const float4* __restrict__ in, uint2* __restrict_
     }
 }
 
+template <int DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
     const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ Xh, const float* __restrict__ bw,
     int N, int T, float* __restrict__ newX) {
@@ -89,9 +100,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&bars->x_full[s], 1); mbar_init(&bars->x_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], TC_SOFTMAX); }
+        for (int s = 0; s < TC_SBUF; ++s) { mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], TC_SOFTMAX / 64); }
         mbar_init(&bars->o_full, 1);
-        mbar_init(&bars->q_full, TC_SOFTMAX);
+        mbar_init(&bars->q_full, TC_SOFTMAX / 32);      // one arrival per softmax warp
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) prefetch_tensormap(&tmap);
@@ -120,10 +131,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
         if (lane == 0) {
             constexpr uint32_t idesc1 = idesc_f16(TC_BM, TC_BN, false);   // S = Q . X^T   (B K-major)
             constexpr uint32_t idesc2 = idesc_f16(TC_BM, TC_D, true);     // O += P . X    (B MN-major)
+            // tile i (counted over all iterations) uses ring stage i % STAGES and S|P buffer i % 3
+            long long m_p = 0, m_x = 0, m_q = 0, m_g1 = 0, m_g2 = 0, m_tot = clock64();
+            auto gemm1 = [&](uint32_t i) {
+                const uint32_t st = i % TC_STAGES, xph = (i / TC_STAGES) & 1, buf = i % TC_SBUF;
+                long long k0 = 0;
+                if (DBG) k0 = clock64();
+                mbar_wait(&bars->x_full[st], xph);
+                tc_fence_after();
+                if (DBG) { const long long n = clock64(); m_x += n - k0; k0 = n; }
+                const uint32_t base = smem_u32(tiles + (size_t)st * TC_TILE_BYTES), qbase = smem_u32(qtile);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {      // 16 d-elements (32 B) per MMA
+                        const uint64_t ad = smem_desc_sw128(qbase + kb * TC_KBLOCK_BYTES + ks * 32, 16, 1024);
+                        const uint64_t bd = smem_desc_sw128(base + kb * TC_KBLOCK_BYTES + ks * 32, 16, 1024);
+                        mma_f16_ss(tmem + COL_S0 + buf * 128, ad, bd, idesc1, (kb | ks) != 0);
+                    }
+                mma_commit(&bars->s_full[buf]);
+                if (DBG) m_g1 += clock64() - k0;
+            };
             auto gemm2 = [&](uint32_t i, bool first_of_iter) {
-                const uint32_t st = i % TC_STAGES, buf = i & 1, ph = (i >> 1) & 1;
+                const uint32_t st = i % TC_STAGES, buf = i % TC_SBUF, ph = (i / TC_SBUF) & 1;
+                long long k0 = 0;
+                if (DBG) k0 = clock64();
                 mbar_wait(&bars->p_full[buf], ph);
                 tc_fence_after();
+                if (DBG) { const long long n = clock64(); m_p += n - k0; k0 = n; }
                 const uint32_t base = smem_u32(tiles + (size_t)st * TC_TILE_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < TC_BN / 16; ++kk) {      // 16 keys per MMA = two 8-row groups, 1024 B apart
@@ -133,35 +168,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
                                !(first_of_iter && kk == 0));
                 }
                 mma_commit(&bars->x_empty[st]);
+                if (DBG) m_g2 += clock64() - k0;
             };
+            // Issue order inside an iteration: G1(0) G1(1) | G1(j+2) G2(j) ...: the S tile of key tile j+2 is queued BEFORE
+            // the issuer waits for the softmax of tile j, so the tensor pipe (whose queue is a few MMAs deep: issue
+            // blocks for about one MMA time per instruction) always has work behind the wait and the softmax warps
+            // find their next S tile finished.  G1(j+2) overwrites the buffer of tile j-1, whose GEMM2 was issued before.
             uint32_t it = 0;
             for (int t = 0; t < T; ++t) {
+                long long q0 = 0;
+                if (DBG) q0 = clock64();
                 mbar_wait(&bars->q_full, t & 1);
                 tc_fence_after();
+                if (DBG) m_q += clock64() - q0;
+                gemm1(it);
+                if (nt > 1) gemm1(it + 1);
                 for (int j = 0; j < nt; ++j, ++it) {
-                    const uint32_t st = it % TC_STAGES, xph = (it / TC_STAGES) & 1, buf = it & 1;
-                    mbar_wait(&bars->x_full[st], xph);
-                    tc_fence_after();
-                    const uint32_t base = smem_u32(tiles + (size_t)st * TC_TILE_BYTES), qbase = smem_u32(qtile);
-#pragma unroll
-                    for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {      // 16 d-elements (32 B) per MMA
-                            const uint64_t ad = smem_desc_sw128(qbase + kb * TC_KBLOCK_BYTES + ks * 32, 16, 1024);
-                            const uint64_t bd = smem_desc_sw128(base + kb * TC_KBLOCK_BYTES + ks * 32, 16, 1024);
-                            mma_f16_ss(tmem + COL_S0 + buf * 128, ad, bd, idesc1, (kb | ks) != 0);
-                        }
-                    mma_commit(&bars->s_full[buf]);
-                    if (j > 0) gemm2(it - 1, j == 1);
+                    if (j + 2 < nt) gemm1(it + 2);
+                    gemm2(it, j == 0);
                 }
-                gemm2(it - 1, nt == 1);
                 mma_commit(&bars->o_full);
             }
+            if (DBG && blockIdx.x == 0 && blockIdx.y == 0)
+                printf("mma thread: tiles %u  per tile: wait_x %lld  issue_g1+commit %lld  wait_p %lld  issue_g2+commit %lld | per iteration wait_q %lld | total %lld\n",
+                       it, m_x / it, m_g1 / it, m_p / it, m_g2 / it, m_q / T, clock64() - m_tot);
         }
     } else if (warp >= 4) {
         // ============================= softmax / epilogue ==============================
-        // Two warps per SM sub-partition: thread = (seed row, 64-key half).  One warp alone cannot hide the
-        // tcgen05.ld -> ex2 -> tcgen05.st latency chain; two interleave and keep the MUFU pipe busy.
         const int ew = warp - 4, half = ew >> 2;
         const int row = 32 * (ew & 3) + lane;                    // TMEM lane == seed row within the tile
         const uint32_t lane_base = (uint32_t)(32 * (ew & 3)) << 16;
@@ -177,50 +210,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
         for (int c = 0; c < 8; ++c)
             *reinterpret_cast<uint4*>(qrow + ((c ^ (row & 7)) << 4)) = row_ok ? xrow[c] : make_uint4(0u, 0u, 0u, 0u);
         fence_proxy_async();
-        mbar_arrive(&bars->q_full);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->q_full);
 
-        uint32_t it = 0;
+        // Softmax: warps 4-7 take the even key tiles, warps 8-11 the odd ones (thread = one seed row, all 128 keys of the
+        // tile), so the two warps that share an SM sub-partition are out of phase: while one waits for its S tile, loads
+        // or stores, the other keeps the MUFU pipe busy.  Inside a tile the row is processed in four 32-column chunks with
+        // the tcgen05.ld of the next chunk in flight during the exponentials of the current one.
+        auto to_p = [&](const uint32_t (&sv)[32], int key0, uint32_t dst) {
+            // P = 2^10 exp(clamp((s-1)/bw^2, -13, .)) as f16 pairs; padded keys weigh nothing
+            if (key0 + 32 <= N) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float x0 = fmaxf(fmaf(__uint_as_float(sv[2 * e]), c1, c0), lo2);
+                    const float x1 = fmaxf(fmaf(__uint_as_float(sv[2 * e + 1]), c1, c0), lo2);
+                    h[e] = pack_f16x2(ex2_approx(x0), ex2_approx(x1));
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    float p0 = ex2_approx(fmaxf(fmaf(__uint_as_float(sv[2 * e]), c1, c0), lo2));
+                    float p1 = ex2_approx(fmaxf(fmaf(__uint_as_float(sv[2 * e + 1]), c1, c0), lo2));
+                    if (key0 + 2 * e >= N) p0 = 0.f;
+                    if (key0 + 2 * e + 1 >= N) p1 = 0.f;
+                    h[e] = pack_f16x2(p0, p1);
+                }
+            }
+            tmem_st16(dst, h);
+        };
+        uint32_t it = 0, mine = 0;
+        long long c_wait = 0, c_busy = 0, c_epi = 0, c_tot = clock64();
         for (int t = 0; t < T; ++t) {
             for (int j = 0; j < nt; ++j, ++it) {
-                const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+                if ((int)(it & 1) != half) continue;
+                const uint32_t buf = it % TC_SBUF, ph = (it / TC_SBUF) & 1;
+                long long k0 = 0, k1 = 0;
+                if (DBG) k0 = clock64();
                 mbar_wait(&bars->s_full[buf], ph);
                 tc_fence_after();
-                const uint32_t sbase = tmem + lane_base + COL_S0 + buf * 128 + 64 * half;
-                const int key0 = j * TC_BN + 64 * half;
-                tmem_ld32(sbase, v[0]);
-                tmem_ld32(sbase + 32, v[1]);
+                if (DBG) k1 = clock64();
+                // S columns [32 c, 32 c + 32) -> P (packed pairs) in columns 64 (c / 2) + 16 (c % 2) .. + 16 of the same buffer:
+                // every store lands on columns this thread has already loaded
+                const uint32_t sb = tmem + lane_base + COL_S0 + buf * 128;
+                const int key0 = j * TC_BN;
+                tmem_ld32(sb, v[0]);
                 tmem_wait_ld();
-                // P = 2^10 exp(clamp((s-1)/bw^2, -13, .)) packed as f16 pairs over the first 32 of this
-                // thread's own 64 S columns (already in registers); padded keys weigh nothing
-                if (key0 + 64 <= N) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const float x0 = fmaxf(fmaf(__uint_as_float(v[c][2 * e]), c1, c0), lo2);
-                            const float x1 = fmaxf(fmaf(__uint_as_float(v[c][2 * e + 1]), c1, c0), lo2);
-                            h[e] = pack_f16x2(ex2_approx(x0), ex2_approx(x1));
-                        }
-                        tmem_st16(sbase + 16 * c, h);
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            float p0 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[c][2 * e]), c1, c0), lo2));
-                            float p1 = ex2_approx(fmaxf(fmaf(__uint_as_float(v[c][2 * e + 1]), c1, c0), lo2));
-                            if (key0 + 32 * c + 2 * e >= N) p0 = 0.f;
-                            if (key0 + 32 * c + 2 * e + 1 >= N) p1 = 0.f;
-                            h[e] = pack_f16x2(p0, p1);
-                        }
-                        tmem_st16(sbase + 16 * c, h);
-                    }
-                }
+                tmem_ld32(sb + 32, v[1]);
+                to_p(v[0], key0, sb);
+                tmem_wait_ld();
+                tmem_ld32(sb + 64, v[0]);
+                to_p(v[1], key0 + 32, sb + 16);
+                tmem_wait_ld();
+                tmem_ld32(sb + 96, v[1]);
+                to_p(v[0], key0 + 64, sb + 64);
+                tmem_wait_ld();
+                to_p(v[1], key0 + 96, sb + 80);
                 tmem_wait_st();
                 tc_fence_before();
-                mbar_arrive(&bars->p_full[buf]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->p_full[buf]);
+                if (DBG) { c_wait += k1 - k0; c_busy += clock64() - k1; ++mine; }
             }
+            long long e0 = 0;
+            if (DBG) e0 = clock64();
             // epilogue of iteration t: y' = O / ||O||  (each thread owns 64 of the row's 128 columns)
             mbar_wait(&bars->o_full, t & 1);
             tc_fence_after();
@@ -232,9 +284,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
             for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int e = 0; e < 32; ++e) ss = fmaf(__uint_as_float(v[c][e]), __uint_as_float(v[c][e]), ss);
-            bars->ssum[t & 1][half][row] = ss;
+            bars->ssum[half][row] = ss;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float inv = 1.0f / sqrtf(bars->ssum[t & 1][0][row] + bars->ssum[t & 1][1][row]);
+            const float inv = 1.0f / sqrtf(bars->ssum[0][row] + bars->ssum[1][row]);
             if (t == T - 1) {
                 if (row_ok) {
                     float4* orow = reinterpret_cast<float4*>(newX + ((size_t)b * N + r0 + row) * TC_D) + 16 * half;
@@ -256,9 +308,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
                         *reinterpret_cast<uint4*>(qrow + (((4 * c + q) ^ (row & 7)) << 4)) = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
                 }
                 fence_proxy_async();
-                mbar_arrive(&bars->q_full);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->q_full);
             }
+            if (DBG) c_epi += clock64() - e0;
         }
+        if (DBG && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 4 || warp == 8))
+            printf("softmax warp %d: own tiles %u  per own tile: wait_s %lld  busy %lld | per iteration epilogue (incl. wait) %lld | total %lld\n",
+                   warp, mine, c_wait / mine, c_busy / mine, c_epi / T, clock64() - c_tot);
     }
     tc_fence_before();
     __syncthreads();
@@ -382,8 +439,10 @@ int prifit_meanshift_fwd_tc(const float* X, const float* bw, int B, int N, int T
     rc = make_tile_map(&map, Xh, B, N);
     if (rc) return rc;
     dim3 grid((N + TC_BM - 1) / TC_BM, B);
-    PF_CUDA(cudaFuncSetAttribute(meanshift_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    meanshift_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map, Xh, bw, N, T, newX);
+    static const bool dbg = [] { const char* e = getenv("PRIFIT_MS_DBG"); return e && atoi(e) != 0; }();   // in-kernel phase clocks (scripts/ms_phases.py)
+    auto kern = dbg ? meanshift_tc_kernel<1> : meanshift_tc_kernel<0>;
+    PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map, Xh, bw, N, T, newX);
     PF_LAUNCH_CHECK();
     return 0;
 }
