@@ -1,35 +1,35 @@
-"""The whole hot path of one batch as two CUDA graphs over static buffers, launched back to back.
+"""The whole hot path of one batch as ONE CUDA graph over static buffers.
 
     kernel   normalise x2 of the caller's embeddings (read in place, row-major or channel-first) -> X
-    graph A  (per branch) bandwidth -> T mean-shift iterations -> NMS -> noise scatter -> K-seed trajectories -> membership
-             -> fit -> SDF            | counts + serial -> pinned host as soon as every branch's NMS is done | batch mean
-    graph B  (per branch) SDF -> fit -> membership -> K-seed trajectories backward of  sum_b has_b loss_b   (speculative)
+    graph    (per branch) bandwidth -> T mean-shift iterations -> NMS -> noise scatter -> K-seed trajectories -> membership
+             -> fit -> SDF -> [SDF -> fit -> membership -> K-seed trajectories backward of sum_b loss_b   (speculative)]
+             | counts + serial -> pinned host as soon as every branch's NMS is done | batch mean at the join
     kernel   at autograd-backward time: normalise backward with the upstream scale dL/d(loss) applied
 
-Inside graph A a branch runs straight from its NMS into its own latency chain (its noise matrices only need the cluster
-counts of the shapes in front of it); nothing joins the branches between the cluster stage and the chains, and there is no
-graph boundary (launch gap) either.  The host learns the counts by polling pinned memory for the step's serial number,
-which graph A copies out together with them in the middle of its run.
+A branch runs straight from its NMS into its own latency chain and -- when the embeddings require a gradient -- straight
+on into its own backward chain: nothing joins the branches before the end of the graph (its noise matrices only need the
+cluster counts of the shapes in front of it; the gradient of sum_b loss_b w.r.t. the unit embeddings needs nothing from
+the other branches, and a shape that kept no ellipsoid has argmin = -1 everywhere and contributes zero).  The host learns
+the counts by polling pinned memory for the step's serial number, which the graph copies out in the middle of its run.
 
-The backward of the path is linear in dL/d(loss), so when the embeddings require a gradient graph 3 is enqueued right
-behind graph 2 -- before the host has made the guard decision and before autograd asks for it -- computing the gradient
-of sum_b has_b loss_b w.r.t. the unit embeddings.  When autograd does call backward, ONE kernel
-(prifit_normalize_bwd_scaled) multiplies by g = dL/d(loss_sum) + dL/d(loss_mean) / n_valid (device scalars) and maps the
-result through the two normalisations.  The device therefore never waits for the host between the forward and the
-backward chain, and the multi-GPU all-reduce of [loss_sum, n_valid] (which only g depends on) runs on a side stream
-beside graph 3 instead of between the two.
+The backward of the path is linear in dL/d(loss), so it is computed before the host has made the guard decision and
+before autograd asks for it.  When autograd does call backward, ONE kernel (prifit_normalize_bwd_scaled) multiplies by
+g = dL/d(loss_sum) + dL/d(loss_mean) / n_valid (device scalars) and maps the result through the two normalisations.  The
+device never waits for the host inside a step.  Three graphs are captured over the same buffers: forward only (no
+gradient wanted), forward + speculative backward (the training step), and a stand-alone backward (a gradient asked for
+after a forward-only replay).
 
 Why.  The eager pipeline (pipeline.fit_loss with graph=False) enqueues ~40 launches per step from Python and runs
 them back to back on one stream, so (1) every kernel's partial last wave leaves SMs idle -- 24 shapes x 16 row
 tiles = 384 CTAs are 2.59 waves of 148 SMs -- and (2) the latency-bound stages (K-seed trajectories: 96 CTAs,
 membership backward: 96 CTAs, the microsecond-scale launches) hold the whole GPU.  Here the batch is cut into
 `branches` contiguous groups of shapes (shapes are independent units) that are captured as parallel
-branches of each graph: the groups drift apart, one group's latency-bound kernels and tails run beside the other
-group's tensor-core kernels, and a replay costs the host three graph launches.
+branches of the graph: the groups drift apart, one group's latency-bound kernels and tails run beside the other
+group's tensor-core kernels, and a replay costs the host one graph launch.
 
 Every kernel is batch-invariant (a shape's result does not depend on the batch it is launched in), so the result
 is bit-identical to the eager path.  The host still makes the guard decision of src/ellipsoid_utils.py:19-26: the
-cluster counts land in pinned memory at the end of graph 1 and are read while graph 2 runs; if a shape exceeds
+cluster counts land in pinned memory as soon as every branch has clustered and are read while the chains run; if a shape exceeds
 max_num_clusters the step is redone on the eager path (quantile doubling, sub-batch re-clustering).
 
 Buffers are static: the tensors returned for a step stay valid until the next step on the same GraphStep; the
@@ -96,6 +96,9 @@ class GraphStep:
             hi = lo + base + (1 if i < rem else 0)
             self.ranges.append((lo, hi))
             lo = hi
+        # Branch i's kernels take free SMs before branch i+1's (stream priorities are recorded in the captured kernel nodes):
+        # the branches then leave the throughput-bound cluster stage one after the other instead of together, and their
+        # latency chains overlap the later branches' tensor-core work instead of each other.
         self.streams = [torch.cuda.Stream(device=device) for _ in self.ranges]
         lib = _lib.load()
         kcap, T = self.kcap, self.T
@@ -114,8 +117,9 @@ class GraphStep:
         self.kth = torch.full((B,), min(kth, N), dtype=i32, device=device)
         self.g_sum, self.g_mean = torch.zeros(1, device=device), torch.zeros(1, device=device)
         self.g_zero = [True, True]
-        self.g_one, self.g_nil = torch.ones(1, device=device), torch.zeros(1, device=device)   # upstream of the speculative backward
-        self.side = torch.cuda.Stream(device=device)                  # multi-GPU all-reduce beside graph 3
+        self.g_one, self.g_nil = torch.ones(1, device=device), torch.zeros(1, device=device)   # upstream of the stand-alone backward graph
+        self.g_ones = torch.ones(B, device=device)                    # dL/d(loss_b) of the speculative backward chains
+        self.side = torch.cuda.Stream(device=device)                  # multi-GPU all-reduce beside the stand-alone backward graph
         self.backward_serial = -1
         # ---- small outputs (snapshotted per step)
         ar = self.arena = _Arena(device)
@@ -177,7 +181,7 @@ class GraphStep:
         else:
             _lib.call("prifit_normalize_fwd", _ptr(E), self.B * self.N, self.d, _ptr(self.X), _stream())
 
-    def _seq_forward(self):
+    def _seq_forward(self, with_backward=False):
         B, N, d, T, kcap, M, sm = self.B, self.N, self.d, self.T, self.kcap, self.Mq, self.small
         main = torch.cuda.current_stream()
         nms_done = [torch.cuda.Event() for _ in self.ranges]
@@ -210,6 +214,10 @@ class GraphStep:
                           _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(self.fctx[lo:hi]), st)
                 _lib.call("prifit_sdf_loss_fwd", _ptr(self.Q[lo:hi]), _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(K), Bb, M, kcap,
                           _ptr(sm["loss_b"][lo:hi]), _ptr(self.argmin[lo:hi]), _ptr(self.sdf[lo:hi]), _ptr(ws["sdf"][0]), ws["sdf"][1], st)
+                if with_backward:
+                    # speculative backward of THIS branch, straight behind its forward: d(sum_b loss_b)/dX needs nothing from
+                    # the other branches (a shape without a valid ellipsoid has argmin = -1 everywhere and contributes zero)
+                    self._branch_backward(i, lo, hi, self.g_ones)
         # the guard predicate's inputs leave for the host as soon as every branch has clustered, beside the chains
         for ev in nms_done:
             main.wait_event(ev)
@@ -219,36 +227,44 @@ class GraphStep:
             main.wait_stream(st_)
         _lib.call("prifit_masked_mean_fwd", _ptr(sm["loss_b"]), _ptr(sm["valid"]), B, kcap, _ptr(sm["has"]), _ptr(sm["stats"]), _stream())
 
+    def _seq_forward_backward(self):
+        self._seq_forward(with_backward=True)
+
+    def _branch_backward(self, i, lo, hi, gloss):
+        """Backward chain of one branch on the current stream; gloss[b] = dL/d(loss_b) up to the scale the last kernel applies."""
+        N, d, T, kcap, M, sm = self.N, self.d, self.T, self.kcap, self.Mq, self.small
+        Bb, ws, st = hi - lo, self.ws[i], _stream()
+        X, bw, idx, K = self.X[lo:hi], sm["bw"][lo:hi], sm["idx"][lo:hi], sm["K"][lo:hi]
+        C, W, gX = self.C[lo:hi], self.W[lo:hi], self.gX[lo:hi]
+        s, V, c, valid = sm["s"][lo:hi], sm["V"][lo:hi], sm["c"][lo:hi], sm["valid"][lo:hi]
+        gs, gV, gc, gW, gC = self.gs[lo:hi], self.gV[lo:hi], self.gc[lo:hi], self.gW[lo:hi], self.gC[lo:hi]
+        _lib.call("prifit_sdf_loss_bwd", _ptr(self.Q[lo:hi]), _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(K),
+                  _ptr(self.argmin[lo:hi]), _ptr(gloss[lo:hi]), Bb, M, kcap, _ptr(gs), _ptr(gV), _ptr(gc), None, st)
+        _lib.call("prifit_fit_bwd", _ptr(self.P[lo:hi]), _ptr(W), _ptr(K), _ptr(self.noise[lo:hi]), _ptr(self.fctx[lo:hi]),
+                  _ptr(valid), _ptr(gs), _ptr(gV), _ptr(gc), Bb, N, kcap, _ptr(gW), None, st)
+        gX.zero_()
+        _lib.call("prifit_membership_bwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), _ptr(W), _ptr(self.smax[lo:hi]), _ptr(gW),
+                  Bb, N, d, kcap, _ptr(gC), _ptr(gX), _ptr(ws["membb"][0]), ws["membb"][1], st)
+        _lib.call("prifit_meanshift_rows_bwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), _ptr(self.traj[lo:hi]),
+                  _ptr(self.stat[lo:hi]), _ptr(gC), Bb, N, d, T, kcap, _ptr(gX), self.rows_bwd_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
+
     def _seq_backward(self):
-        B, N, d, T, kcap, M, sm = self.B, self.N, self.d, self.T, self.kcap, self.Mq, self.small
+        """Stand-alone backward (a forward replayed without the speculative backward, then asked for a gradient)."""
+        B, sm = self.B, self.small
         # gloss_b = has_b: the gradient of sum_b has_b loss_b; the true upstream scale is applied by the last kernel
         _lib.call("prifit_masked_mean_bwd", _ptr(self.g_one), _ptr(self.g_nil), _ptr(sm["has"]), _ptr(sm["stats"]), B,
                   _ptr(self.gloss), _stream())
+        self._fork_join(lambda i, lo, hi: self._branch_backward(i, lo, hi, self.gloss))
 
-        def branch(i, lo, hi):
-            Bb, ws, st = hi - lo, self.ws[i], _stream()
-            X, bw, idx, K = self.X[lo:hi], sm["bw"][lo:hi], sm["idx"][lo:hi], sm["K"][lo:hi]
-            C, W, gX = self.C[lo:hi], self.W[lo:hi], self.gX[lo:hi]
-            s, V, c, valid = sm["s"][lo:hi], sm["V"][lo:hi], sm["c"][lo:hi], sm["valid"][lo:hi]
-            gs, gV, gc, gW, gC = self.gs[lo:hi], self.gV[lo:hi], self.gc[lo:hi], self.gW[lo:hi], self.gC[lo:hi]
-            _lib.call("prifit_sdf_loss_bwd", _ptr(self.Q[lo:hi]), _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(K),
-                      _ptr(self.argmin[lo:hi]), _ptr(self.gloss[lo:hi]), Bb, M, kcap, _ptr(gs), _ptr(gV), _ptr(gc), None, st)
-            _lib.call("prifit_fit_bwd", _ptr(self.P[lo:hi]), _ptr(W), _ptr(K), _ptr(self.noise[lo:hi]), _ptr(self.fctx[lo:hi]),
-                      _ptr(valid), _ptr(gs), _ptr(gV), _ptr(gc), Bb, N, kcap, _ptr(gW), None, st)
-            gX.zero_()
-            _lib.call("prifit_membership_bwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), _ptr(W), _ptr(self.smax[lo:hi]), _ptr(gW),
-                      Bb, N, d, kcap, _ptr(gC), _ptr(gX), _ptr(ws["membb"][0]), ws["membb"][1], st)
-            _lib.call("prifit_meanshift_rows_bwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), _ptr(self.traj[lo:hi]),
-                      _ptr(self.stat[lo:hi]), _ptr(gC), Bb, N, d, T, kcap, _ptr(gX), self.rows_bwd_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
-
-        self._fork_join(branch)
-
-    def _scaled_normalize_bwd(self, E):
+    def _scaled_normalize_bwd(self, E, out=None):
+        out = self.gE if out is None else out
         _lib.call("prifit_normalize_bwd_scaled", _ptr(E), _ptr(self.gX), self.B, self.N, self.d, 1 if self.cf else 0,
-                  _ptr(self.g_sum), _ptr(self.g_mean), _ptr(self.small["stats"]), _ptr(self.gE), _stream())
+                  _ptr(self.g_sum), _ptr(self.g_mean), _ptr(self.small["stats"]), _ptr(out), _stream())
+        return out
 
     def _capture(self):
-        seqs = (self._seq_forward, self._seq_backward)
+        # [0] forward, [1] stand-alone backward, [2] forward with every branch's speculative backward behind its forward
+        seqs = (self._seq_forward, self._seq_backward, self._seq_forward_backward)
         # eager warm-up on a side stream (first-call initialisation must not happen inside a capture)
         E0 = torch.randn(self.gE.shape, dtype=torch.float32, device=self.device)
         self.P.uniform_(-1, 1)
@@ -259,13 +275,13 @@ class GraphStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             self._normalize_fwd(E0)
-            for seq in seqs:
+            for seq in seqs[:2]:
                 seq()
             self._scaled_normalize_bwd(E0)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.graphs = []
-        self.launches = [0, 0]
+        self.launches = [0, 0, 0]
         for i, seq in enumerate(seqs):
             g = torch.cuda.CUDAGraph()
             before = _lib.launch_count()
@@ -280,10 +296,11 @@ class GraphStep:
         torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------------------------------ per step
-    def run_forward(self, E, P, Q, noise, want_grad=False):
-        """Enqueues the step (input copies, noise staging, graphs 1 and 2, snapshot of the small outputs, and -- when a
-        gradient will be asked for -- the speculative backward graph 3) without waiting for anything and returns the
-        result dict; finish_forward() then makes the guard decision."""
+    def run_forward(self, E, P, Q, noise, want_grad=False, split_backward=False):
+        """Enqueues the step (input copies, noise staging, the graph -- with the speculative backward chains when a gradient
+        will be asked for --, snapshot of the small outputs) without waiting for anything and returns the result dict;
+        finish_forward() then makes the guard decision.  split_backward (multi-GPU): forward graph, then the stand-alone
+        backward graph, so that the all-reduce of the forward results can run beside the backward."""
         self.serial += 1
         self.P.copy_(P)
         if self.Q is not self.P:
@@ -308,8 +325,9 @@ class GraphStep:
             self.direct_host = want_direct
         self._normalize_fwd(E)
         self.replays += 1
-        self.graphs[0].replay()
-        _lib._launches += self.launches[0]
+        which = 2 if (want_grad and not split_backward) else 0    # each branch's backward chain follows its forward
+        self.graphs[which].replay()
+        _lib._launches += self.launches[which]
         self._state = state
         # snapshot of the small outputs: enqueued (and its views built) before the host waits, so that after the
         # read-back the host only has the guard decision between itself and the backward launch
@@ -317,9 +335,10 @@ class GraphStep:
         self._ev_fwd = torch.cuda.Event()
         self._ev_fwd.record()                              # forward results complete: what the multi-GPU all-reduce waits for
         if want_grad:
-            self.graphs[1].replay()                        # speculative: d(sum_b has_b loss_b)/dX into self.gX
-            _lib._launches += self.launches[1]
-            self.backward_serial = self.serial
+            if split_backward:
+                self.graphs[1].replay()                    # speculative: d(sum_b has_b loss_b)/dX into self.gX
+                _lib._launches += self.launches[1]
+            self.backward_serial = self.serial             # self.gX holds the gradient once the enqueued graphs are through
         loss_sum, n_valid, loss = snap["stats"].unbind(0)
         out = dict(snap)
         out.update({"loss": loss, "loss_sum": loss_sum, "n_valid": n_valid, "W": self.W, "C": self.C, "X": self.X,
@@ -327,10 +346,10 @@ class GraphStep:
         return out
 
     def finish_forward(self, out):
-        """Host side of the guard (src/ellipsoid_utils.py:19-26): waits for graph 1 only (graph 2 keeps the device
+        """Host side of the guard (src/ellipsoid_utils.py:19-26): waits for the cluster stage only (the chains keep the device
         busy), reads the counts, settles the host generator.  False = a shape exceeded the cap: redo eagerly."""
-        # the step's one host synchronisation: poll pinned memory until graph A's copy of [K | n_labels | serial] for THIS
-        # replay has landed (the copy happens in the middle of graph A, so no stream / event wait can express it)
+        # the step's one host synchronisation: poll pinned memory until the graph's copy of [K | n_labels | serial] for THIS
+        # replay has landed (the copy happens in the middle of the graph, so no stream / event wait can express it)
         want, cn, B = self.replays, self.counts_np, self.B
         spins, t0 = 0, None
         while cn[2 * B] != want:
@@ -369,12 +388,16 @@ class GraphStep:
             self.graphs[1].replay()
             _lib._launches += self.launches[1]
             self.backward_serial = serial
-        self._scaled_normalize_bwd(E)                      # gE = normalize_bwd(E, g * gX)
-        return self.gE
+        # gE = normalize_bwd(E, g * gX).  Row-major input: into the static buffer, which is handed to autograd as it is --
+        # AccumulateGrad copies a gradient whose tensor object something else still references, every other consumer reads
+        # it before the next replay.  Channel-first input: the gradient reaches the caller's leaf through view nodes
+        # (transpose / permute), whose fresh view objects AccumulateGrad would adopt without copying, so the kernel writes
+        # into a fresh tensor.
+        return self._scaled_normalize_bwd(E, torch.empty_like(self.gE) if self.cf else None)
 
 
 class _Attach(torch.autograd.Function):
-    """Autograd node of a graph-replayed step: (E) -> (loss_sum, loss_mean); backward replays graph 3."""
+    """Autograd node of a graph-replayed step: (E) -> (loss_sum, loss_mean); backward applies the upstream scale to the speculative gradient."""
 
     @staticmethod
     def forward(ctx, E, step, serial, loss_sum, loss):
@@ -388,12 +411,7 @@ class _Attach(torch.autograd.Function):
         if g_sum is None and g_mean is None:
             return None, None, None, None, None
         (E,) = ctx.saved_tensors
-        gE = ctx.step.run_backward(ctx.serial, g_sum, g_mean, E)
-        # Row-major input: the static buffer itself is handed to autograd -- AccumulateGrad copies a gradient whose
-        # tensor object something else still references, every other consumer reads it before the next replay.
-        # Channel-first input: the gradient reaches the caller's leaf through view nodes (transpose / permute), whose
-        # fresh view objects AccumulateGrad would adopt without copying, so the copy is made here.
-        return (gE.clone() if ctx.step.cf else gE), None, None, None, None
+        return ctx.step.run_backward(ctx.serial, g_sum, g_mean, E), None, None, None, None
 
 
 _steps = {}
@@ -437,11 +455,11 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
                     default_branches() if branches is None else int(branches), cf)
     np_state = np.random.get_state()
     want_grad = E.requires_grad and torch.is_grad_enabled()
-    res = step.run_forward(src.detach(), P.detach(), None if Q is None else Q.detach(), noise, want_grad)
+    res = step.run_forward(src.detach(), P.detach(), None if Q is None else Q.detach(), noise, want_grad, split_backward=bool(dist_reduce))
     loss_sum, loss = res["loss_sum"], res["loss"]
     if want_grad:
         loss_sum, loss = _Attach.apply(src, step, res["serial"], loss_sum, loss)
-    pipeline.replay_shuffles(B, N)                         # host RNG parity (src/mean_shift.py:150) while graph 1 runs
+    pipeline.replay_shuffles(B, N)                         # host RNG parity (src/mean_shift.py:150) while the cluster stage runs
     if not step.finish_forward(res):
         np.random.set_state(np_state)                      # the eager redo replays the shuffles of every pass itself
         return None
