@@ -98,6 +98,12 @@ int prifit_nms_fwd(const float* newX, const float* bw, int B, int N, int d, int 
 /* flag OR-ed into `engine` of prifit_meanshift_rows_bwd: the workspace still holds the split fp16 rows of this X, left there
  * by the prifit_meanshift_rows_fwd call with the same (X, B, N, ws) -- the backward then skips its own split pass */
 #define PRIFIT_ROWS_WS_HOLDS_SPLIT 0x100
+/* flags OR-ed into `engine` of prifit_meanshift_rows_fwd / _bwd (tcgen05 engine): split every shape's keys over 8 CTAs (WIDE) or
+ * 4 (NARROW).  Bit-identical results (the key partial sums are formed per fixed unit of tiles, not per CTA): a scheduling choice.
+ * 8 has 2/3 of the latency when the launch has its 8 B SMs to itself and loses when such launches compete (one CTA per SM).
+ * Neither flag: 8 when 8 B x ceil(Kcap / 32) <= 74 CTAs, else 4. */
+#define PRIFIT_ROWS_WIDE 0x200
+#define PRIFIT_ROWS_NARROW 0x400
 
 /* k2 rows -- fp32 trajectories of the K selected seeds (center = new_X[indices],
  *   src/mean_shift.py:46): traj_out[B, T+1, Kcap, d] (y^0..y^T), stat_out[B, T, Kcap, 2] =

@@ -75,6 +75,8 @@ MS_FP32_SIMT = 1
 ROWS_SPLIT_TCGEN05 = 0
 ROWS_FP32_SIMT = 1
 ROWS_WS_HOLDS_SPLIT = 0x100
+ROWS_WIDE = 0x200
+ROWS_NARROW = 0x400
 
 _lib = None
 

@@ -365,12 +365,13 @@ int launch_rows_bwd(const float* X, const float* bw, const int32_t* idx, const i
 
 size_t prifit_rows_tc_workspace_bytes(int B, int N);
 int prifit_rows_tc_fwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K, int B, int N, int T, int Kcap,
-                       float* traj, float* stat, float* C_out, void* ws, cudaStream_t st);
+                       float* traj, float* stat, float* C_out, void* ws, int wide, cudaStream_t st);
 int prifit_rows_tc_bwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K, const float* traj,
                        const float* stat, const float* gC, int B, int N, int T, int Kcap, float* gX, void* ws, bool ws_holds_split,
-                       cudaStream_t st);
+                       int wide, cudaStream_t st);
 
 extern "C" size_t prifit_meanshift_rows_workspace_bytes(int B, int N, int d, int engine) {
+    engine &= 0xff;
     if (engine == PRIFIT_ROWS_SPLIT_TCGEN05 && d == 128) return prifit_rows_tc_workspace_bytes(B, N);
     return 16;
 }
@@ -382,10 +383,12 @@ extern "C" int prifit_meanshift_rows_fwd(const float* X, const float* bw, const 
     PF_CHECK_ARG(X && bw && idx && K && traj_out && C_out && (stat_out || T == 0), PRIFIT_E_BADARG, "null pointer");
     PF_CHECK_ARG(B > 0 && N > 0 && T >= 0, PRIFIT_E_BADARG, "B, N > 0 and T >= 0 required");
     PF_CHECK_ARG(Kcap > 0 && Kcap % 4 == 0 && Kcap <= 64, PRIFIT_E_SHAPE, "Kcap must be a multiple of 4, <= 64");
+    const int wide = (engine & PRIFIT_ROWS_WIDE) ? 1 : (engine & PRIFIT_ROWS_NARROW) ? 0 : -1;
+    engine &= 0xff;
     if (engine == PRIFIT_ROWS_SPLIT_TCGEN05) {
         PF_CHECK_ARG(d == 128, PRIFIT_E_SHAPE, "the tcgen05 engine is specialised for d == 128");
         PF_CHECK_ARG(ws && ws_bytes >= prifit_meanshift_rows_workspace_bytes(B, N, d, engine), PRIFIT_E_WS, "workspace too small");
-        return prifit_rows_tc_fwd(X, bw, idx, K, B, N, T, Kcap, traj_out, stat_out, C_out, ws, pf_stream(stream));
+        return prifit_rows_tc_fwd(X, bw, idx, K, B, N, T, Kcap, traj_out, stat_out, C_out, ws, wide, pf_stream(stream));
     }
     PF_CHECK_ARG(engine == PRIFIT_ROWS_FP32_SIMT, PRIFIT_E_BADARG, "unknown engine");
     switch (d) {
@@ -404,11 +407,12 @@ extern "C" int prifit_meanshift_rows_bwd(const float* X, const float* bw, const 
     PF_CHECK_ARG(B > 0 && N > 0 && T >= 0, PRIFIT_E_BADARG, "B, N > 0 and T >= 0 required");
     PF_CHECK_ARG(Kcap > 0 && Kcap % 4 == 0 && Kcap <= 64, PRIFIT_E_SHAPE, "Kcap must be a multiple of 4, <= 64");
     const bool ws_holds_split = (engine & PRIFIT_ROWS_WS_HOLDS_SPLIT) != 0;
-    engine &= ~PRIFIT_ROWS_WS_HOLDS_SPLIT;
+    const int wide = (engine & PRIFIT_ROWS_WIDE) ? 1 : (engine & PRIFIT_ROWS_NARROW) ? 0 : -1;
+    engine &= 0xff;
     if (engine == PRIFIT_ROWS_SPLIT_TCGEN05) {
         PF_CHECK_ARG(d == 128, PRIFIT_E_SHAPE, "the tcgen05 engine is specialised for d == 128");
         PF_CHECK_ARG(ws && ws_bytes >= prifit_meanshift_rows_workspace_bytes(B, N, d, engine), PRIFIT_E_WS, "workspace too small");
-        return prifit_rows_tc_bwd(X, bw, idx, K, traj, stat, gC, B, N, T, Kcap, gX_inout, ws, ws_holds_split, pf_stream(stream));
+        return prifit_rows_tc_bwd(X, bw, idx, K, traj, stat, gC, B, N, T, Kcap, gX_inout, ws, ws_holds_split, wide, pf_stream(stream));
     }
     PF_CHECK_ARG(engine == PRIFIT_ROWS_FP32_SIMT, PRIFIT_E_BADARG, "unknown engine");
     switch (d) {

@@ -98,7 +98,7 @@ struct RtMisc {
     uint64_t o_full, y_full;
     uint32_t tmem_base;
     float part_z[RT_SEEDS];
-    float zwarp[8][16];
+    float zwarp[2][8][16];               // [unit][epilogue warp][seed]
     float red[RT_EPI];
     float gmm[RT_SEEDS], dinv[RT_SEEDS], gmax[RT_SEEDS], gbound[RT_SEEDS];
     float scal[4];                        // backward: SG, SD, SE
@@ -205,11 +205,23 @@ struct RowsArgs {
     int dbg;
 };
 
-// key tiles of this CTA: [j0, j0 + ntl)
-__device__ __forceinline__ void my_tiles(int N, int csize, int rank, int& j0, int& ntl) {
-    const int nt = (N + RT_KEYS - 1) / RT_KEYS, tpc = (nt + csize - 1) / csize;
-    j0 = rank * tpc;
-    ntl = max(0, min(nt, j0 + tpc) - j0);
+// The key tiles of a shape form RT_UNITS = 8 fixed UNITS of G = ceil(nt / 8) consecutive tiles, whatever the cluster size.
+// A CTA of a c-CTA cluster (c = 4 or 8) owns 8 / c consecutive units = tiles [j0, j0 + ntl); its first unit ends at local
+// tile G.  Partial sums over keys are formed PER UNIT (one accumulator per unit), units 2r and 2r+1 are added first and the
+// four pair sums then in order -- the same floating-point expression whether a pair is added inside a CTA (c = 4) or by the
+// reducing CTA (c = 8), so a shape's result does not depend on the cluster size its launch was given.
+constexpr int RT_UNITS = 8;
+__device__ __forceinline__ void my_tiles(int N, int csize, int rank, int& j0, int& ntl, int& G) {
+    const int nt = (N + RT_KEYS - 1) / RT_KEYS;
+    G = max(1, (nt + RT_UNITS - 1) / RT_UNITS);
+    const int tpc = G * (RT_UNITS / csize);
+    j0 = min(nt, rank * tpc);
+    ntl = max(0, min(nt, rank * tpc + tpc) - j0);
+}
+// pair sums, then the four pairs in order (see my_tiles)
+__device__ __forceinline__ float unit_sum(const float (&q)[RT_MAXC], int csize) {
+    if (csize == RT_UNITS) return (((q[0] + q[1]) + (q[2] + q[3])) + (q[4] + q[5])) + (q[6] + q[7]);
+    return ((q[0] + q[1]) + q[2]) + q[3];
 }
 
 __device__ __forceinline__ void produce_tile(uint8_t* smem, RtMisc* m, const CUtensorMap* tmap, uint32_t st, int row0, int b, int B) {
@@ -253,8 +265,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
     float* ys = reinterpret_cast<float*>(smem + FwdPlan::ys);
     float* part_o = reinterpret_cast<float*>(smem + FwdPlan::part_o);
 
-    int j0, ntl;
-    my_tiles(N, csize, rank, j0, ntl);
+    int j0, ntl, G;
+    my_tiles(N, csize, rank, j0, ntl, G);
     const bool resident = ntl <= RT_STAGES;       // the CTA's key slice stays in shared memory for all T iterations
 
     if (tid == 0) {
@@ -270,7 +282,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = m->tmem_base;
-    constexpr uint32_t COL_S = 0 /* [buf][x_hi.y_hi + x_lo.y_hi | x_hi.y_lo] */, COL_O = 128 /* same split */;
+    constexpr uint32_t COL_S = 0 /* [buf][x_hi.y_hi + x_lo.y_hi | x_hi.y_lo] */, COL_O = 128 /* [unit][same split] */;
 
     const float* Xb = a.X + (size_t)b * N * RT_D;
     const int32_t* idx_b = a.idx + (size_t)b * Kcap + k0;
@@ -333,8 +345,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                 constexpr uint32_t id2w = idesc_f16_mm(RT_D, 2 * RT_SEEDS, true, true);        // x_hi^T . [p_hi | p_lo]
                 constexpr uint32_t id2n = idesc_f16_mm(RT_D, RT_SEEDS, true, true);            // x_lo^T . p_hi
                 const uint32_t ybase = smem_u32(smem + FwdPlan::y), pbase = smem_u32(smem + FwdPlan::p);
-                auto gemm2 = [&](uint32_t i, int jl, bool first) {
+                auto gemm2 = [&](uint32_t i, int jl) {
                     const uint32_t st = resident ? (uint32_t)jl : i % RT_STAGES;
+                    const bool first = jl == 0 || jl == G;             // first tile of a unit: fresh accumulator
+                    const uint32_t col_o = COL_O + (jl >= G ? 64u : 0u);
                     mbar_wait(&m->c_full, i & 1);
                     tc_fence_after();
                     const uint32_t xb = smem_u32(smem + (size_t)st * RT_STAGE_BYTES);
@@ -343,8 +357,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                         const uint64_t a_hi = smem_desc_sw128(xb + kk * 2048, RT_KBLOCK, 1024);
                         const uint64_t a_lo = smem_desc_sw128(xb + RT_HALF_BYTES + kk * 2048, RT_KBLOCK, 1024);
                         const uint64_t bp = smem_desc_sw128(pbase + kk * 2048, RT_KBLOCK, 1024);
-                        mma_f16_ss(tmem + COL_O, a_hi, bp, id2w, !(first && kk == 0));
-                        mma_f16_ss(tmem + COL_O, a_lo, bp, id2n, true);
+                        mma_f16_ss(tmem + col_o, a_hi, bp, id2w, !(first && kk == 0));
+                        mma_f16_ss(tmem + col_o, a_lo, bp, id2n, true);
                     }
                     if (!resident) mma_commit(&m->x_empty[st]);
                     mma_commit(&m->c_free);
@@ -371,14 +385,14 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                             mma_f16_ss(tmem + COL_S + buf * 64, a_lo, by, id1n, true);
                         }
                     mma_commit(&m->s_full[buf]);
-                    if (jl > 0) gemm2(mit - 1, jl - 1, jl == 1);
+                    if (jl > 0) gemm2(mit - 1, jl - 1);
                 }
-                if (ntl > 0) { gemm2(mit - 1, ntl - 1, ntl == 1); mma_commit(&m->o_full); }
+                if (ntl > 0) { gemm2(mit - 1, ntl - 1); mma_commit(&m->o_full); }
             }
             __syncwarp();
         } else if (warp >= 4) {
             // ============================= coefficients (thread = key) ==============================
-            float zlane = 0.f;
+            float zlane[2] = {0.f, 0.f};                            // per unit
             uint32_t eit = it;
             for (int jl = 0; jl < ntl; ++jl, ++eit) {
                 const uint32_t buf = eit & 1;
@@ -404,7 +418,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
 #pragma unroll
                     for (int s = 0; s < 16; ++s) p[s] = 0.f;
                 }
-                zlane += warp_transpose_sum16(p, lane);
+                const float zt = warp_transpose_sum16(p, lane);
+                if (jl < G) zlane[0] += zt; else zlane[1] += zt;
                 uint32_t h[8], l[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) split2(p[2 * e] * RT_PSCALE, p[2 * e + 1] * RT_PSCALE, h[e], l[e]);
@@ -423,27 +438,39 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                 mbar_arrive(&m->c_full);
                 RT_MARK(7);
             }
-            // partial numerators O^T (lane = column d) and denominators of this CTA's key slice
-            uint32_t v[16], w[16];
+            // partial numerators O^T (lane = column d) and denominators of this CTA's key slice: one per unit, added here
+            float po[16];
+#pragma unroll
+            for (int s = 0; s < 16; ++s) po[s] = 0.f;
             if (ntl > 0) {
+                uint32_t v[16], w[16];
                 mbar_wait(&m->o_full, t & 1);
                 tc_fence_after();
                 tmem_ld16(tmem + lane_base + COL_O + 16 * half, v);
                 tmem_ld16(tmem + lane_base + COL_O + 32 + 16 * half, w);
                 tmem_wait_ld();
-                tc_fence_before();
-            } else {
 #pragma unroll
-                for (int s = 0; s < 16; ++s) { v[s] = 0u; w[s] = 0u; }
+                for (int s = 0; s < 16; ++s) po[s] = (__uint_as_float(v[s]) + __uint_as_float(w[s])) * (1.0f / (RT_XSCALE * RT_PSCALE));
+                if (ntl > G) {                                         // second unit of this CTA
+                    tmem_ld16(tmem + lane_base + COL_O + 64 + 16 * half, v);
+                    tmem_ld16(tmem + lane_base + COL_O + 64 + 32 + 16 * half, w);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int s = 0; s < 16; ++s) po[s] += (__uint_as_float(v[s]) + __uint_as_float(w[s])) * (1.0f / (RT_XSCALE * RT_PSCALE));
+                }
+                tc_fence_before();
             }
 #pragma unroll
-            for (int s = 0; s < 16; ++s)
-                part_o[(16 * half + s) * RT_D + row] = (__uint_as_float(v[s]) + __uint_as_float(w[s])) * (1.0f / (RT_XSCALE * RT_PSCALE));
-            if ((lane & 1) == 0) m->zwarp[ew][lane >> 1] = zlane;
+            for (int s = 0; s < 16; ++s) part_o[(16 * half + s) * RT_D + row] = po[s];
+            if ((lane & 1) == 0) { m->zwarp[0][ew][lane >> 1] = zlane[0]; m->zwarp[1][ew][lane >> 1] = zlane[1]; }
             epi_bar();
             if (et < RT_SEEDS) {
                 const int hz = et >> 4, sz = et & 15;
-                m->part_z[et] = (m->zwarp[4 * hz][sz] + m->zwarp[4 * hz + 1][sz]) + (m->zwarp[4 * hz + 2][sz] + m->zwarp[4 * hz + 3][sz]);
+                float zu[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    zu[u] = (m->zwarp[u][4 * hz][sz] + m->zwarp[u][4 * hz + 1][sz]) + (m->zwarp[u][4 * hz + 2][sz] + m->zwarp[u][4 * hz + 3][sz]);
+                m->part_z[et] = zu[0] + zu[1];
             }
             RT_MARK(11);
         }
@@ -464,10 +491,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
                     oq[q] = q < csize ? reinterpret_cast<const float4*>(cluster.map_shared_rank(part_o, q) + orow * RT_D)[c4]
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                float zsum = 0.f;
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                float ox[RT_MAXC], oy[RT_MAXC], oz[RT_MAXC], ow[RT_MAXC];
 #pragma unroll
-                for (int q = 0; q < RT_MAXC; ++q) { zsum += zq[q]; o.x += oq[q].x; o.y += oq[q].y; o.z += oq[q].z; o.w += oq[q].w; }
+                for (int q = 0; q < RT_MAXC; ++q) { ox[q] = oq[q].x; oy[q] = oq[q].y; oz[q] = oq[q].z; ow[q] = oq[q].w; }
+                const float zsum = unit_sum(zq, csize);
+                const float4 o = make_float4(unit_sum(ox, csize), unit_sum(oy, csize), unit_sum(oz, csize), unit_sum(ow, csize));
                 const float dinv = 1.0f / zsum;
                 const float4 y = reinterpret_cast<const float4*>(ys + orow * RT_D)[c4];
                 float4 u;                                                  // new = y + ((K X) D - y)
@@ -525,8 +553,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
     float* part_o = reinterpret_cast<float*>(smem + BwdPlan::part_o);
     float* gms = reinterpret_cast<float*>(smem + BwdPlan::gms);
 
-    int j0, ntl;
-    my_tiles(N, csize, rank, j0, ntl);
+    int j0, ntl, G;
+    my_tiles(N, csize, rank, j0, ntl, G);
     const bool resident = ntl <= RT_STAGES;
 
     if (tid == 0) {
@@ -545,7 +573,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = m->tmem_base;
-    // S[buf]: [x.y_hi | x.gm_hi | x_hi.y_lo | x_hi.gm_lo] (32 columns each); GY: [x.ds_hi | x_hi.ds_lo]; GX: one 128-column accumulator
+    // S[buf]: [x.y_hi | x.gm_hi | x_hi.y_lo | x_hi.gm_lo] (32 columns each); GY[unit]: [x.ds_hi | x_hi.ds_lo]; GX: one 128-column accumulator
     constexpr uint32_t COL_S = 0, COL_GY = 256, COL_GX = 384;
 
     float* gXb = a.gX + (size_t)b * N * RT_D;
@@ -597,8 +625,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                     constexpr uint32_t id2n = idesc_f16_mm(RT_D, RT_SEEDS, true, true);           // x_lo^T . ds_hi
                     constexpr uint32_t id3 = idesc_f16_mm(RT_KEYS, RT_D, false, true);            // gX = [ds | e1] . [Y ; Gm]
                     const uint32_t ygbase = smem_u32(smem + BwdPlan::yg), cbase = smem_u32(smem + BwdPlan::de);
-                    auto gemm_g = [&](uint32_t i, int jl, bool first) {
+                    auto gemm_g = [&](uint32_t i, int jl) {
                         const uint32_t st = resident ? (uint32_t)jl : i % RT_STAGES;
+                        const bool first = jl == 0 || jl == G;         // first tile of a unit: fresh dL/dy accumulator
+                        const uint32_t col_gy = COL_GY + (jl >= G ? 64u : 0u);
                         mbar_wait(&m->c_full, i & 1);
                         tc_fence_after();
                         const uint32_t xb = smem_u32(smem + (size_t)st * RT_STAGE_BYTES);
@@ -607,8 +637,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                             const uint64_t a_hi = smem_desc_sw128(xb + kk * 2048, RT_KBLOCK, 1024);
                             const uint64_t a_lo = smem_desc_sw128(xb + RT_HALF_BYTES + kk * 2048, RT_KBLOCK, 1024);
                             const uint64_t bd = smem_desc_sw128(cbase + kk * 2048, RT_KBLOCK, 1024);
-                            mma_f16_ss(tmem + COL_GY, a_hi, bd, id2w, !(first && kk == 0));
-                            mma_f16_ss(tmem + COL_GY, a_lo, bd, id2n, true);
+                            mma_f16_ss(tmem + col_gy, a_hi, bd, id2w, !(first && kk == 0));
+                            mma_f16_ss(tmem + col_gy, a_lo, bd, id2n, true);
                         }
                         mbar_wait(&m->gx_free, (i & 1) ^ 1);           // the previous tile's gX has been read out
                         tc_fence_after();
@@ -650,9 +680,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                                 mma_f16_ss(tmem + COL_S + buf * 128, a_lo, bd, id1n, true);
                             }
                         mma_commit(&m->s_full[buf]);
-                        if (jl > 0) gemm_g(mit - 1, jl - 1, jl == 1);
+                        if (jl > 0) gemm_g(mit - 1, jl - 1);
                     }
-                    if (ntl > 0) { gemm_g(mit - 1, ntl - 1, ntl == 1); mma_commit(&m->o_full); }
+                    if (ntl > 0) { gemm_g(mit - 1, ntl - 1); mma_commit(&m->o_full); }
                 }
                 __syncwarp();
             } else if (warp >= 4) {
@@ -833,23 +863,32 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                 }
                 if (ntl > 0) flush(eit - 1, ntl - 1);
                 RT_MARK(9);
-                // partial dL/dy^t of this CTA's keys (lane = column d); the coefficient tile is dead now
-                uint32_t v[16], w[16];
+                // partial dL/dy^t of this CTA's keys (lane = column d), one per unit, added here; the coefficient tile is dead now
+                float po[16];
+#pragma unroll
+                for (int s = 0; s < 16; ++s) po[s] = 0.f;
                 if (ntl > 0) {
+                    uint32_t v[16], w[16];
                     mbar_wait(&m->o_full, itn & 1);
                     tc_fence_after();
                     tmem_ld16(tmem + lane_base + COL_GY + 16 * half, v);
                     tmem_ld16(tmem + lane_base + COL_GY + 32 + 16 * half, w);
                     tmem_wait_ld();
-                    tc_fence_before();
-                } else {
 #pragma unroll
-                    for (int s = 0; s < 16; ++s) { v[s] = 0u; w[s] = 0u; }
+                    for (int s = 0; s < 16; ++s) po[s] = (__uint_as_float(v[s]) + __uint_as_float(w[s])) * gx_mul;
+                    if (ntl > G) {                                     // second unit of this CTA
+                        tmem_ld16(tmem + lane_base + COL_GY + 64 + 16 * half, v);
+                        tmem_ld16(tmem + lane_base + COL_GY + 64 + 32 + 16 * half, w);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int s = 0; s < 16; ++s) po[s] += (__uint_as_float(v[s]) + __uint_as_float(w[s])) * gx_mul;
+                    }
+                    tc_fence_before();
                 }
                 RT_MARK(10);
                 epi_bar();                                             // all flush() loads of this CTA are done with TMEM
 #pragma unroll
-                for (int s = 0; s < 16; ++s) part_o[(16 * half + s) * RT_D + row] = (__uint_as_float(v[s]) + __uint_as_float(w[s])) * gx_mul;
+                for (int s = 0; s < 16; ++s) part_o[(16 * half + s) * RT_D + row] = po[s];
                 RT_MARK(11);
             }
             it += ntl;
@@ -865,9 +904,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                     for (int q = 0; q < RT_MAXC; ++q)
                         oq[q] = q < csize ? reinterpret_cast<const float4*>(cluster.map_shared_rank(part_o, q) + orow * RT_D)[c4]
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float ox[RT_MAXC], oy[RT_MAXC], oz[RT_MAXC], ow[RT_MAXC];
 #pragma unroll
-                    for (int q = 0; q < RT_MAXC; ++q) { o.x += oq[q].x; o.y += oq[q].y; o.z += oq[q].z; o.w += oq[q].w; }
+                    for (int q = 0; q < RT_MAXC; ++q) { ox[q] = oq[q].x; oy[q] = oq[q].y; oz[q] = oq[q].z; ow[q] = oq[q].w; }
+                    const float4 o = make_float4(unit_sum(ox, csize), unit_sum(oy, csize), unit_sum(oz, csize), unit_sum(ow, csize));
                     for (int q = 0; q < csize; ++q) reinterpret_cast<float4*>(cluster.map_shared_rank(gy, q) + orow * RT_D)[c4] = o;
                 }
             }
@@ -890,18 +930,19 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-// Keys of a shape are split over `csize` CTAs (one CTA per SM: shared memory).  The split is independent of
-// the batch size so that a shape's result does not depend on how the batch is sharded (fixed summation
-// order).  4 beats 8 on cfg2 (24 shapes: 96 CTAs in one wave vs 192 in two; 308 vs 420 us backward) and
-// loses little elsewhere.  PRIFIT_ROWS_CLUSTER overrides (diagnostics).
-int pick_cluster(int N) {
-    const int nt = (N + RT_KEYS - 1) / RT_KEYS;
-    int csize = 4;
+// Keys of a shape are split over a cluster of 4 or 8 CTAs (one CTA per SM: shared memory).  The result does not depend on
+// the choice (units, see my_tiles), so it is a pure scheduling decision.  8 has 2/3 of the per-iteration latency (2 resident
+// key tiles per CTA at N = 2048; 8 shapes: forward 124 -> 79 us, backward 257 -> 185 us) as long as all clusters are
+// co-resident: a 24-shape batch would be 192 CTAs in two rounds (375 us backward), and three graph branches of 8 shapes
+// launching 8-CTA clusters side by side lose too (a cluster needs 8 free SMs inside one GPC).  Hence: 8 when the launch is
+// at most half the GPU, else 4; `wide` (PRIFIT_ROWS_WIDE / _NARROW, 1 / 0, -1 = automatic) and PRIFIT_ROWS_CLUSTER=4|8
+// (diagnostics) override.
+int pick_cluster(int wide, int n_clusters) {
+    int csize = wide < 0 ? (8 * n_clusters <= 74 ? 8 : 4) : (wide ? 8 : 4);
     if (const char* e = getenv("PRIFIT_ROWS_CLUSTER")) {
         const int v = atoi(e);
-        if (v >= 1 && v <= RT_MAXC) csize = v;
+        if (v == 4 || v == 8) csize = v;
     }
-    while (csize > 1 && nt < csize) --csize;
     return csize;
 }
 
@@ -943,7 +984,7 @@ static int rows_dbg_begin() {
 size_t prifit_rows_tc_workspace_bytes(int B, int N) { return (size_t)2 * B * N * RT_D * sizeof(__half) + 256; }
 
 int prifit_rows_tc_fwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K, int B, int N, int T, int Kcap,
-                       float* traj, float* stat, float* C_out, void* ws, cudaStream_t st) {
+                       float* traj, float* stat, float* C_out, void* ws, int wide, cudaStream_t st) {
     __half* Xs = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
     CUtensorMap map;
     int rc = prifit_tc_split_rows(X, Xs, B, N, &map, st);
@@ -952,13 +993,13 @@ int prifit_rows_tc_fwd(const float* X, const float* bw, const int32_t* idx, cons
     a.X = X; a.bw = bw; a.idx = idx; a.K = K; a.N = N; a.B = B; a.T = T; a.Kcap = Kcap;
     a.traj = traj; a.stat = stat; a.C_out = C_out;
     a.dbg = rows_dbg_begin();
-    const int csize = pick_cluster(N);
+    const int csize = pick_cluster(wide, B * ((Kcap + RT_SEEDS - 1) / RT_SEEDS));
     return launch_rows_tc(rows_tc_fwd_kernel, 1024 + FwdPlan::total, csize, dim3(csize, (Kcap + RT_SEEDS - 1) / RT_SEEDS, B), map, a, st);
 }
 
 int prifit_rows_tc_bwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K, const float* traj,
                        const float* stat, const float* gC, int B, int N, int T, int Kcap, float* gX, void* ws, bool ws_holds_split,
-                       cudaStream_t st) {
+                       int wide, cudaStream_t st) {
     __half* Xs = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
     CUtensorMap map;
     // the forward call left the split rows of the same X in this workspace: only the tile map is rebuilt (host side)
@@ -968,6 +1009,6 @@ int prifit_rows_tc_bwd(const float* X, const float* bw, const int32_t* idx, cons
     a.X = X; a.bw = bw; a.idx = idx; a.K = K; a.N = N; a.B = B; a.T = T; a.Kcap = Kcap;
     a.traj_in = traj; a.stat_in = stat; a.gC = gC; a.gX = gX;
     a.dbg = rows_dbg_begin();
-    const int csize = pick_cluster(N);
+    const int csize = pick_cluster(wide, B);
     return launch_rows_tc(rows_tc_bwd_kernel, 1024 + BwdPlan::total, csize, dim3(csize, 1, B), map, a, st);
 }

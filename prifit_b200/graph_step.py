@@ -100,6 +100,9 @@ class GraphStep:
         # the branches then leave the throughput-bound cluster stage one after the other instead of together, and their
         # latency chains overlap the later branches' tensor-core work instead of each other.
         self.streams = [torch.cuda.Stream(device=device) for _ in self.ranges]
+        # The K-seed trajectory kernels of the branches run side by side: 4 CTAs per shape (not the 8 a lone small launch
+        # would pick), so that 3 x 8 shapes x 4 = 96 CTAs are co-resident (one CTA per SM).  Same bits either way.
+        self.rows_flags = _lib.ROWS_NARROW if (rows_engine == _lib.ROWS_SPLIT_TCGEN05 and nbr > 1) else 0
         lib = _lib.load()
         kcap, T = self.kcap, self.T
         f32, i32, u8 = torch.float32, torch.int32, torch.uint8
@@ -207,7 +210,7 @@ class GraphStep:
                 _lib.call("prifit_noise_scatter_range", _ptr(self.flat), _ptr(sm["K"]), lo, Bb, kcap, _ptr(self.direct),
                           _ptr(self.noise), st)
                 _lib.call("prifit_meanshift_rows_fwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), Bb, N, d, T, kcap,
-                          _ptr(self.traj[lo:hi]), _ptr(self.stat[lo:hi]), _ptr(C), self.rows_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
+                          _ptr(self.traj[lo:hi]), _ptr(self.stat[lo:hi]), _ptr(C), self.rows_engine | self.rows_flags, _ptr(ws["rows"][0]), ws["rows"][1], st)
                 _lib.call("prifit_membership_fwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), Bb, N, d, kcap, _ptr(W), _ptr(self.smax[lo:hi]),
                           _ptr(ws["memb"][0]), ws["memb"][1], st)
                 _lib.call("prifit_fit_fwd", _ptr(self.P[lo:hi]), _ptr(W), _ptr(K), _ptr(self.noise[lo:hi]), Bb, N, kcap,
@@ -246,7 +249,7 @@ class GraphStep:
         _lib.call("prifit_membership_bwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), _ptr(W), _ptr(self.smax[lo:hi]), _ptr(gW),
                   Bb, N, d, kcap, _ptr(gC), _ptr(gX), _ptr(ws["membb"][0]), ws["membb"][1], st)
         _lib.call("prifit_meanshift_rows_bwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), _ptr(self.traj[lo:hi]),
-                  _ptr(self.stat[lo:hi]), _ptr(gC), Bb, N, d, T, kcap, _ptr(gX), self.rows_bwd_engine, _ptr(ws["rows"][0]), ws["rows"][1], st)
+                  _ptr(self.stat[lo:hi]), _ptr(gC), Bb, N, d, T, kcap, _ptr(gX), self.rows_bwd_engine | self.rows_flags, _ptr(ws["rows"][0]), ws["rows"][1], st)
 
     def _seq_backward(self):
         """Stand-alone backward (a forward replayed without the speculative backward, then asked for a gradient)."""

@@ -142,7 +142,7 @@ def nms(newX, bw, kcap):
 
 def _rows_engine(engine, d):
     engine = DEFAULT_ROWS_ENGINE if engine is None else engine
-    if engine == ROWS_SPLIT_TCGEN05 and d != 128:
+    if (engine & 0xff) == ROWS_SPLIT_TCGEN05 and d != 128:
         engine = ROWS_FP32_SIMT        # the tensor-core kernels are specialised for d = 128
     return engine
 

@@ -268,6 +268,29 @@ def test_rows_tensor_core_result_is_independent_of_the_batch(cuda):
     assert torch.equal(C_all[3:4], C_one) and torch.equal(g_all[3:4], g_one)
 
 
+@pytest.mark.parametrize("n", [2048, 1000, 300, 10000])
+def test_rows_tensor_core_result_is_independent_of_the_cluster_size(cuda, n):
+    """PRIFIT_ROWS_WIDE (8 CTAs per shape instead of 4) is a scheduling choice: the key partial sums are formed per fixed
+    unit of tiles and added in one fixed order, so trajectories, saved statistics and the gradient are bit-identical."""
+    from prifit_b200 import _lib, ops, pipeline, synthetic
+
+    T = 7
+    E, _, _ = synthetic.planted_shapes(3, n_points=n, n_clusters=6, seed=4)
+    X = ops.normalize_fwd(E.to(cuda))
+    res = pipeline.cluster_batch(X, n, 0.05, T, 25)
+    gC = torch.randn(3, res.kcap, 128, generator=torch.Generator().manual_seed(3)).to(cuda)
+    outs = []
+    for flags in (_lib.ROWS_NARROW, _lib.ROWS_WIDE):
+        engine = _lib.ROWS_SPLIT_TCGEN05 | flags
+        traj, stat, C = ops.rows_fwd(X, res.bw, res.idx, res.K, T, res.kcap, engine)
+        gX = torch.zeros_like(X)
+        ops.rows_bwd(X, res.bw, res.idx, res.K, traj, stat, gC, gX, T, res.kcap, engine)
+        outs.append((traj, stat, C, gX))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert float(outs[0][3].abs().max()) > 0
+
+
 @pytest.mark.parametrize("n,kc,T", [(2048, 16, 10), (1500, 9, 10), (10000, 40, 10)])
 def test_rows_engines_agree_on_planted_shapes(cuda, n, kc, T):
     """cfg2 / cfg4-like planted shapes: tensor-core (split-fp16) trajectories and their backward against the
