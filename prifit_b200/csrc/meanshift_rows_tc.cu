@@ -118,6 +118,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// 16 lanes x 64 consecutive 32-bit columns in the accumulator-fragment layout: thread t of the warp holds, for every group
+// k = 0..7 of 8 columns, columns 8k + 2(t % 4) + {0, 1} of lane (t / 4) in r[4k], r[4k+1] and of lane (t / 4) + 8 in r[4k+2], r[4k+3]
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, float w) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
@@ -789,25 +803,38 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
                 auto flush = [&](uint32_t i, int jl) {                 // gX accumulator of tile i -> global (rows owned by this CTA)
                     mbar_wait(&m->gx_full, i & 1);
                     tc_fence_after();
+                    // This warp's 32 lanes x 64 columns in the fragment layout (two 16-lane loads): a quad of threads holds 8
+                    // consecutive columns of one row.  One exchange inside the quad turns two such groups into four consecutive
+                    // columns per thread, so that every red.global.add.v4 of the warp covers 8 rows x 64 contiguous bytes --
+                    // full 32-byte sectors (one row per lane touched 32 half-used sectors per instruction).
                     uint32_t g0[32], g1[32];
-                    tmem_ld32(tmem + lane_base + COL_GX + 64 * half, g0);
-                    tmem_ld32(tmem + lane_base + COL_GX + 64 * half + 32, g1);
+                    tmem_ld_16x256b_x8(tmem + lane_base + COL_GX + 64 * half, g0);
+                    tmem_ld_16x256b_x8(tmem + lane_base + (16u << 16) + COL_GX + 64 * half, g1);
                     tmem_wait_ld();
                     tc_fence_before();
                     mbar_arrive(&m->gx_free);
-                    const int key = (j0 + jl) * RT_KEYS + row;
-                    if (key < N && !(a.dbg & 2)) {
-                        // fire-and-forget vector reductions: no read round trip on the critical path
-                        float* dst = gXb + (size_t)key * RT_D + 64 * half;
+                    if (a.dbg & 2) return;
+                    const int qc = lane & 3, odd = qc & 1;
+                    const int key0 = (j0 + jl) * RT_KEYS + 32 * (ew & 3) + (lane >> 2);
+                    const int cbase = 64 * half + 4 * (qc >> 1) + 8 * odd;         // even threads: group k, odd threads: group k + 1
+                    auto emit = [&](const uint32_t (&g)[32], int rbase) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            red_add_v4(dst + 4 * e, __uint_as_float(g0[4 * e]) * gx_mul, __uint_as_float(g0[4 * e + 1]) * gx_mul,
-                                       __uint_as_float(g0[4 * e + 2]) * gx_mul, __uint_as_float(g0[4 * e + 3]) * gx_mul);
+                        for (int kp = 0; kp < 4; ++kp)                             // groups 2 kp, 2 kp + 1
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            red_add_v4(dst + 32 + 4 * e, __uint_as_float(g1[4 * e]) * gx_mul, __uint_as_float(g1[4 * e + 1]) * gx_mul,
-                                       __uint_as_float(g1[4 * e + 2]) * gx_mul, __uint_as_float(g1[4 * e + 3]) * gx_mul);
-                    }
+                            for (int rh = 0; rh < 2; ++rh) {                       // lane t/4, lane t/4 + 8
+                                const uint32_t a0 = g[8 * kp + 2 * rh], a1 = g[8 * kp + 2 * rh + 1];          // group 2 kp
+                                const uint32_t b0 = g[8 * kp + 4 + 2 * rh], b1 = g[8 * kp + 4 + 2 * rh + 1];  // group 2 kp + 1
+                                const uint32_t s0 = odd ? a0 : b0, s1 = odd ? a1 : b1;                          // what the partner wants
+                                const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                                const float x0 = __uint_as_float(odd ? r0 : a0), x1 = __uint_as_float(odd ? r1 : a1);
+                                const float x2 = __uint_as_float(odd ? b0 : r0), x3 = __uint_as_float(odd ? b1 : r1);
+                                const int key = key0 + rbase + 8 * rh;
+                                if (key < N)
+                                    red_add_v4(gXb + (size_t)key * RT_D + cbase + 16 * kp, x0 * gx_mul, x1 * gx_mul, x2 * gx_mul, x3 * gx_mul);
+                            }
+                    };
+                    emit(g0, 0);
+                    emit(g1, 16);
                 };
 
                 uint32_t eit = it;
