@@ -2,6 +2,7 @@
 // reference src/mean_shift.py:230-247 (membership):
 //     sim = C X^T / bw^2 ; sim -= sim.max().detach() ; e = guard_exp(sim) ; mem = e / sum_k e
 // Output layout is the reference's [K, N] (cluster-major), padded to [B, Kcap, N].
+#include <stdlib.h>
 #include "rowgemm.cuh"
 
 namespace {
@@ -77,9 +78,10 @@ __global__ void __launch_bounds__(256) membership_softmax_kernel(
 //   gC_k  = sum_j dsim_kj x_j         (partial sums over MB_SPLIT key slices, reduced in fixed order by a second kernel)
 //   gX_j += sum_k dsim_kj c_k
 // The keys of a shape are cut into MB_SPLIT slices (a number that depends on N only, so a shape's result does not depend on
-// the batch it is launched in); with 102 KB of shared memory two CTAs share an SM and the 24 x 8 = 192 CTAs of cfg2 are one
-// wave.  (The first version used a 4-CTA cluster per shape and a DSMEM reduction: 96 CTAs, 82 us.)
-constexpr int MB_SPLIT = 8;
+// the batch it is launched in); with 102 KB of shared memory two CTAs share an SM.  16 slices (one 128-key tile per CTA at
+// N = 2048): the 8 shapes of a graph branch are 128 CTAs, 24.4 us (8 slices: 64 CTAs, 37.8 us); a 24-shape batch 50.6 (54.8) us.
+// (The first version used a 4-CTA cluster per shape and a DSMEM reduction: 96 CTAs, 82 us.)
+constexpr int MB_SPLIT = 16;
 
 template <int D>
 __global__ void __launch_bounds__(RG_THREADS, 2) membership_bwd_kernel(

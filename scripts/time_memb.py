@@ -24,19 +24,19 @@ def timeit(fn, n=20):
 
 def main():
     dev = torch.device("cuda:0")
-    B, N = 24, 2048
-    E, _, _ = synthetic.planted_shapes(B, n_points=N, n_clusters=16, seed=0)
-    X = ops.normalize_fwd(E.to(dev))
-    res = pipeline.cluster_batch(X, N, 0.05, 10, 25)
-    _, _, C = ops.rows_fwd(X, res.bw, res.idx, res.K, 10, res.kcap)
-    W, smax = ops.membership_fwd(C, X, res.bw, res.K)
-    gW = torch.randn_like(W)
-    gX = torch.zeros_like(X)
-    for cs in (8, 4, 2):
-        os.environ["PRIFIT_MEMB_CLUSTER"] = str(cs)
+    N = 2048
+    for B in (8, 24):
+        E, _, _ = synthetic.planted_shapes(B, n_points=N, n_clusters=16, seed=0)
+        X = ops.normalize_fwd(E.to(dev))
+        res = pipeline.cluster_batch(X, N, 0.05, 10, 25)
+        _, _, C = ops.rows_fwd(X, res.bw, res.idx, res.K, 10, res.kcap)
+        W, smax = ops.membership_fwd(C, X, res.bw, res.K)
+        gW = torch.randn_like(W)
+        gX = torch.zeros_like(X)
         tf = timeit(lambda: ops.membership_fwd(C, X, res.bw, res.K))
+        print("B=%d  fwd %.1f us" % (B, tf), flush=True)
         tb = timeit(lambda: ops.membership_bwd(C, X, res.bw, res.K, W, smax, gW, gX))
-        print("cluster=%d  fwd %.1f us  bwd %.1f us" % (cs, tf, tb), flush=True)
+        print("B=%d  bwd %.1f us" % (B, tb), flush=True)
 
 
 if __name__ == "__main__":
