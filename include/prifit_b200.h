@@ -92,11 +92,19 @@ int prifit_nms_fwd(const float* newX, const float* bw, int B, int N, int d, int 
                    int32_t* idx_out, int32_t* K_out, int32_t* labels_out, int32_t* n_labels_out,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* step 5 of the NMS alone (src/mean_shift.py:200-201): prifit_nms_fwd may be called with labels_out = n_labels_out = NULL -- it
+ *   then stops at the centres (idx_out, K_out) -- and this call, on the same workspace, computes the hard labels and their count
+ *   afterwards, e.g. on another stream beside the consumers of the centres. */
+int prifit_nms_labels(const float* newX, int B, int N, int d, int Kcap, const int32_t* K,
+                      int32_t* idx_out, int32_t* labels_out, int32_t* n_labels_out,
+                      void* ws, size_t ws_bytes, void* stream);
+
 /* engines of the K-seed trajectory kernels */
 #define PRIFIT_ROWS_SPLIT_TCGEN05 0 /* tensor cores, split-fp16 (hi + lo) operands, 3 tcgen05.mma per product: fp32-class; d == 128 */
 #define PRIFIT_ROWS_FP32_SIMT     1 /* CUDA-core fp32 (cross-check; d in {64, 128, 256}) */
-/* flag OR-ed into `engine` of prifit_meanshift_rows_bwd: the workspace still holds the split fp16 rows of this X, left there
- * by the prifit_meanshift_rows_fwd call with the same (X, B, N, ws) -- the backward then skips its own split pass */
+/* flag OR-ed into `engine` of prifit_meanshift_rows_fwd / _bwd: the workspace still holds the split fp16 rows of this X, left
+ * there by prifit_meanshift_rows_prepare or by the prifit_meanshift_rows_fwd call with the same (X, B, N, ws) -- the call then
+ * skips its own split pass */
 #define PRIFIT_ROWS_WS_HOLDS_SPLIT 0x100
 /* flags OR-ed into `engine` of prifit_meanshift_rows_fwd / _bwd (tcgen05 engine): split every shape's keys over 8 CTAs (WIDE) or
  * 4 (NARROW).  Bit-identical results (the key partial sums are formed per fixed unit of tiles, not per CTA): a scheduling choice.
@@ -109,6 +117,8 @@ int prifit_nms_fwd(const float* newX, const float* bw, int B, int N, int d, int 
  *   src/mean_shift.py:46): traj_out[B, T+1, Kcap, d] (y^0..y^T), stat_out[B, T, Kcap, 2] =
  *   (Z_t, ||u_t||), C_out[B,Kcap,d] = y^T.  Rows k >= K[b] are zero.  engine = PRIFIT_ROWS_*. */
 size_t prifit_meanshift_rows_workspace_bytes(int B, int N, int d, int engine);
+/* optional: the operand preparation of the tensor-core engine (split fp16 rows of X into ws) ahead of time; X is all it needs */
+int prifit_meanshift_rows_prepare(const float* X, int B, int N, int d, int engine, void* ws, size_t ws_bytes, void* stream);
 int prifit_meanshift_rows_fwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K,
                               int B, int N, int d, int T, int Kcap,
                               float* traj_out, float* stat_out, float* C_out,

@@ -30,6 +30,8 @@ SIGNATURES = {
     "prifit_meanshift_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _sz, _p]),
     "prifit_nms_workspace_bytes": (_sz, [_i, _i, _i]),
     "prifit_nms_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "prifit_nms_labels": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "prifit_meanshift_rows_prepare": (_i, [_p, _i, _i, _i, _i, _p, _sz, _p]),
     "prifit_meanshift_rows_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "prifit_meanshift_rows_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _sz, _p]),
     "prifit_meanshift_rows_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _sz, _p]),
@@ -112,7 +114,7 @@ def check(rc, what):
 # kernels (and memset nodes) each entry point enqueues; bench.py reports the sum as `gpu_launches`
 LAUNCHES = {
     "prifit_normalize_fwd": 1, "prifit_normalize_bwd": 1, "prifit_normalize_fwd_cf": 1, "prifit_normalize_bwd_cf": 1, "prifit_normalize_bwd_scaled": 1, "prifit_bandwidth_fwd": 6, "prifit_meanshift_fwd": 3,
-    "prifit_nms_fwd": 10, "prifit_meanshift_rows_fwd": 2, "prifit_meanshift_rows_bwd": 2,
+    "prifit_nms_fwd": 10, "prifit_nms_labels": 2, "prifit_meanshift_rows_prepare": 1, "prifit_meanshift_rows_fwd": 2, "prifit_meanshift_rows_bwd": 2,
     "prifit_membership_fwd": 2, "prifit_membership_bwd": 2, "prifit_fit_fwd": 1, "prifit_fit_bwd": 1,
     "prifit_sdf_loss_fwd": 2, "prifit_sdf_loss_bwd": 1,
     "prifit_masked_mean_fwd": 1, "prifit_masked_mean_bwd": 1, "prifit_noise_scatter": 1, "prifit_noise_scatter_range": 1, "prifit_pack_counts": 1,
@@ -135,7 +137,8 @@ def launch_count():
 TIMING = None
 
 
-def call(name, *args):
+def call(name, *args, launches=None):
+    """launches: kernels this particular call enqueues when that differs from the entry point's usual count."""
     global _launches
     if TIMING is not None:
         import torch
@@ -146,4 +149,4 @@ def call(name, *args):
         TIMING.append((name, e0, e1))
     else:
         check(getattr(load(), name)(*args), name)
-    _launches += LAUNCHES.get(name, 0)
+    _launches += LAUNCHES.get(name, 0) if launches is None else launches

@@ -365,7 +365,8 @@ int launch_rows_bwd(const float* X, const float* bw, const int32_t* idx, const i
 
 size_t prifit_rows_tc_workspace_bytes(int B, int N);
 int prifit_rows_tc_fwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K, int B, int N, int T, int Kcap,
-                       float* traj, float* stat, float* C_out, void* ws, int wide, cudaStream_t st);
+                       float* traj, float* stat, float* C_out, void* ws, bool ws_holds_split, int wide, cudaStream_t st);
+int prifit_rows_tc_prepare(const float* X, int B, int N, void* ws, cudaStream_t st);
 int prifit_rows_tc_bwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K, const float* traj,
                        const float* stat, const float* gC, int B, int N, int T, int Kcap, float* gX, void* ws, bool ws_holds_split,
                        int wide, cudaStream_t st);
@@ -376,6 +377,14 @@ extern "C" size_t prifit_meanshift_rows_workspace_bytes(int B, int N, int d, int
     return 16;
 }
 
+extern "C" int prifit_meanshift_rows_prepare(const float* X, int B, int N, int d, int engine, void* ws, size_t ws_bytes, void* stream) {
+    PF_CHECK_ARG(X && B > 0 && N > 0, PRIFIT_E_BADARG, "X, B, N > 0 required");
+    engine &= 0xff;
+    if (engine != PRIFIT_ROWS_SPLIT_TCGEN05 || d != 128) return 0;          // the fp32 engine reads X as it is
+    PF_CHECK_ARG(ws && ws_bytes >= prifit_meanshift_rows_workspace_bytes(B, N, d, engine), PRIFIT_E_WS, "workspace too small");
+    return prifit_rows_tc_prepare(X, B, N, ws, pf_stream(stream));
+}
+
 extern "C" int prifit_meanshift_rows_fwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K,
                                          int B, int N, int d, int T, int Kcap,
                                          float* traj_out, float* stat_out, float* C_out,
@@ -384,11 +393,12 @@ extern "C" int prifit_meanshift_rows_fwd(const float* X, const float* bw, const 
     PF_CHECK_ARG(B > 0 && N > 0 && T >= 0, PRIFIT_E_BADARG, "B, N > 0 and T >= 0 required");
     PF_CHECK_ARG(Kcap > 0 && Kcap % 4 == 0 && Kcap <= 64, PRIFIT_E_SHAPE, "Kcap must be a multiple of 4, <= 64");
     const int wide = (engine & PRIFIT_ROWS_WIDE) ? 1 : (engine & PRIFIT_ROWS_NARROW) ? 0 : -1;
+    const bool ws_holds_split = (engine & PRIFIT_ROWS_WS_HOLDS_SPLIT) != 0;
     engine &= 0xff;
     if (engine == PRIFIT_ROWS_SPLIT_TCGEN05) {
         PF_CHECK_ARG(d == 128, PRIFIT_E_SHAPE, "the tcgen05 engine is specialised for d == 128");
         PF_CHECK_ARG(ws && ws_bytes >= prifit_meanshift_rows_workspace_bytes(B, N, d, engine), PRIFIT_E_WS, "workspace too small");
-        return prifit_rows_tc_fwd(X, bw, idx, K, B, N, T, Kcap, traj_out, stat_out, C_out, ws, wide, pf_stream(stream));
+        return prifit_rows_tc_fwd(X, bw, idx, K, B, N, T, Kcap, traj_out, stat_out, C_out, ws, ws_holds_split, wide, pf_stream(stream));
     }
     PF_CHECK_ARG(engine == PRIFIT_ROWS_FP32_SIMT, PRIFIT_E_BADARG, "unknown engine");
     switch (d) {

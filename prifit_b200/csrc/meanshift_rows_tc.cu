@@ -1011,10 +1011,10 @@ static int rows_dbg_begin() {
 size_t prifit_rows_tc_workspace_bytes(int B, int N) { return (size_t)2 * B * N * RT_D * sizeof(__half) + 256; }
 
 int prifit_rows_tc_fwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K, int B, int N, int T, int Kcap,
-                       float* traj, float* stat, float* C_out, void* ws, int wide, cudaStream_t st) {
+                       float* traj, float* stat, float* C_out, void* ws, bool ws_holds_split, int wide, cudaStream_t st) {
     __half* Xs = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
     CUtensorMap map;
-    int rc = prifit_tc_split_rows(X, Xs, B, N, &map, st);
+    int rc = ws_holds_split ? prifit_tc_make_tile_map(&map, Xs, 2 * B, N) : prifit_tc_split_rows(X, Xs, B, N, &map, st);
     if (rc) return rc;
     RowsArgs a = {};
     a.X = X; a.bw = bw; a.idx = idx; a.K = K; a.N = N; a.B = B; a.T = T; a.Kcap = Kcap;
@@ -1022,6 +1022,13 @@ int prifit_rows_tc_fwd(const float* X, const float* bw, const int32_t* idx, cons
     a.dbg = rows_dbg_begin();
     const int csize = pick_cluster(wide, B * ((Kcap + RT_SEEDS - 1) / RT_SEEDS));
     return launch_rows_tc(rows_tc_fwd_kernel, 1024 + FwdPlan::total, csize, dim3(csize, (Kcap + RT_SEEDS - 1) / RT_SEEDS, B), map, a, st);
+}
+
+// the split fp16 rows of X into the workspace, ahead of the forward / backward calls that then pass PRIFIT_ROWS_WS_HOLDS_SPLIT
+int prifit_rows_tc_prepare(const float* X, int B, int N, void* ws, cudaStream_t st) {
+    __half* Xs = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    CUtensorMap map;
+    return prifit_tc_split_rows(X, Xs, B, N, &map, st);
 }
 
 int prifit_rows_tc_bwd(const float* X, const float* bw, const int32_t* idx, const int32_t* K, const float* traj,

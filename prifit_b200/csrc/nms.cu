@@ -212,6 +212,14 @@ __global__ void __launch_bounds__(256) nms_nlabels_kernel(const int32_t* __restr
     }
 }
 
+// idx_out[b][:Kcap] = the first Kcap centres of the full list, -1 padded (the centres-only call: nms_nlabels_kernel writes the
+// same values when the labels are computed in the same call)
+__global__ void nms_idx_kernel(const int32_t* __restrict__ Kfound, const int32_t* __restrict__ idx_full, int N, int Kcap,
+                               int32_t* __restrict__ idx_out) {
+    const int b = blockIdx.x, Kf = Kfound[b];
+    for (int k = threadIdx.x; k < Kcap; k += blockDim.x) idx_out[(size_t)b * Kcap + k] = k < Kf ? idx_full[(size_t)b * N + k] : -1;
+}
+
 struct NmsWs {
     int32_t *nearest, *votes, *best, *flags, *used, *rowsel, *nrows, *idx_full;
 };
@@ -268,9 +276,29 @@ int launch_nms(const float* newX, const float* bw, int B, int N, int Kcap, int32
     PF_LAUNCH_CHECK();
     nms_compact_kernel<<<B, 1024, 0, st>>>(w.flags, N, N, w.idx_full, K_out);
     PF_LAUNCH_CHECK();
+    if (!labels_out) {          // centres only: the label pass follows as prifit_nms_labels (possibly on another stream)
+        nms_idx_kernel<<<B, 64, 0, st>>>(K_out, w.idx_full, N, Kcap, idx_out);
+        PF_LAUNCH_CHECK();
+        return 0;
+    }
     nms_label_kernel<D><<<gt, RG_THREADS, smem, st>>>(newX, N, w.idx_full, K_out, labels_out, w.used);
     PF_LAUNCH_CHECK();
     nms_nlabels_kernel<<<B, 256, 0, st>>>(w.used, K_out, w.idx_full, N, Kcap, idx_out, n_labels_out);
+    PF_LAUNCH_CHECK();
+    return 0;
+}
+
+// step 5 alone, after a centres-only launch_nms on the same workspace (full centre list and zeroed `used` flags are there)
+template <int D>
+int launch_nms_labels(const float* newX, int B, int N, int Kcap, const int32_t* K, int32_t* idx_out, int32_t* labels_out,
+                      int32_t* n_labels_out, void* ws, cudaStream_t st) {
+    NmsWs w = carve(ws, B, N);
+    const size_t smem = ((size_t)(RG_ROWS + RG_KEYS) * (D + 4) + 16 * RG_KEYS) * sizeof(float);
+    PF_CUDA(cudaFuncSetAttribute(nms_label_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 gt((N + RG_KEYS - 1) / RG_KEYS, B);
+    nms_label_kernel<D><<<gt, RG_THREADS, smem, st>>>(newX, N, w.idx_full, K, labels_out, w.used);
+    PF_LAUNCH_CHECK();
+    nms_nlabels_kernel<<<B, 256, 0, st>>>(w.used, K, w.idx_full, N, Kcap, idx_out, n_labels_out);
     PF_LAUNCH_CHECK();
     return 0;
 }
@@ -285,7 +313,8 @@ extern "C" size_t prifit_nms_workspace_bytes(int B, int N, int d) {
 extern "C" int prifit_nms_fwd(const float* newX, const float* bw, int B, int N, int d, int Kcap,
                               int32_t* idx_out, int32_t* K_out, int32_t* labels_out, int32_t* n_labels_out,
                               void* ws, size_t ws_bytes, void* stream) {
-    PF_CHECK_ARG(newX && bw && idx_out && K_out && labels_out && n_labels_out && ws, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(newX && bw && idx_out && K_out && ws, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG((labels_out == nullptr) == (n_labels_out == nullptr), PRIFIT_E_BADARG, "labels_out and n_labels_out go together");
     PF_CHECK_ARG(B > 0 && N > 0, PRIFIT_E_BADARG, "B, N > 0 required");
     PF_CHECK_ARG(Kcap > 0 && Kcap % 4 == 0 && Kcap <= 64, PRIFIT_E_SHAPE, "Kcap must be a multiple of 4, <= 64");
     PF_CHECK_ARG(ws_bytes >= prifit_nms_workspace_bytes(B, N, d), PRIFIT_E_WS, "workspace too small");
@@ -294,5 +323,20 @@ extern "C" int prifit_nms_fwd(const float* newX, const float* bw, int B, int N, 
         case 128: return launch_nms<128>(newX, bw, B, N, Kcap, idx_out, K_out, labels_out, n_labels_out, ws, pf_stream(stream));
         case 256: return launch_nms<256>(newX, bw, B, N, Kcap, idx_out, K_out, labels_out, n_labels_out, ws, pf_stream(stream));
         default: prifit_set_error("prifit_nms_fwd: d must be 64, 128 or 256 (got %d)", d); return PRIFIT_E_SHAPE;
+    }
+}
+
+extern "C" int prifit_nms_labels(const float* newX, int B, int N, int d, int Kcap, const int32_t* K,
+                                 int32_t* idx_out, int32_t* labels_out, int32_t* n_labels_out,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    PF_CHECK_ARG(newX && K && idx_out && labels_out && n_labels_out && ws, PRIFIT_E_BADARG, "null pointer");
+    PF_CHECK_ARG(B > 0 && N > 0, PRIFIT_E_BADARG, "B, N > 0 required");
+    PF_CHECK_ARG(Kcap > 0 && Kcap % 4 == 0 && Kcap <= 64, PRIFIT_E_SHAPE, "Kcap must be a multiple of 4, <= 64");
+    PF_CHECK_ARG(ws_bytes >= prifit_nms_workspace_bytes(B, N, d), PRIFIT_E_WS, "workspace too small");
+    switch (d) {
+        case 64: return launch_nms_labels<64>(newX, B, N, Kcap, K, idx_out, labels_out, n_labels_out, ws, pf_stream(stream));
+        case 128: return launch_nms_labels<128>(newX, B, N, Kcap, K, idx_out, labels_out, n_labels_out, ws, pf_stream(stream));
+        case 256: return launch_nms_labels<256>(newX, B, N, Kcap, K, idx_out, labels_out, n_labels_out, ws, pf_stream(stream));
+        default: prifit_set_error("prifit_nms_labels: d must be 64, 128 or 256 (got %d)", d); return PRIFIT_E_SHAPE;
     }
 }

@@ -84,6 +84,7 @@ class GraphStep:
         # the rows workspace of a branch is touched by nothing but its K-seed forward and backward, and X is static: the
         # backward reuses the split fp16 rows the forward left there
         self.rows_bwd_engine = rows_engine | _lib.ROWS_WS_HOLDS_SPLIT if rows_engine == _lib.ROWS_SPLIT_TCGEN05 else rows_engine
+        self.rows_fwd_engine = self.rows_bwd_engine      # the split rows are prepared beside the cluster stage (prifit_meanshift_rows_prepare)
         self.device = device
         self.serial = 0
         kth = int(self.quantile * N)                                  # src/mean_shift.py:155
@@ -100,6 +101,9 @@ class GraphStep:
         # the branches then leave the throughput-bound cluster stage one after the other instead of together, and their
         # latency chains overlap the later branches' tensor-core work instead of each other.
         self.streams = [torch.cuda.Stream(device=device) for _ in self.ranges]
+        # work that is NOT on a branch's critical chain runs beside it: the operand preparation of the K-seed kernels (needs X
+        # only), the zero-fill of the gradient buffer, the hard labels (the chain needs the centres only), the noise scatter
+        self.side_streams = [torch.cuda.Stream(device=device) for _ in self.ranges]
         # The K-seed trajectory kernels of the branches run side by side: 4 CTAs per shape (not the 8 a lone small launch
         # would pick), so that 3 x 8 shapes x 4 = 96 CTAs are co-resident (one CTA per SM).  Same bits either way.
         self.rows_flags = _lib.ROWS_NARROW if (rows_engine == _lib.ROWS_SPLIT_TCGEN05 and nbr > 1) else 0
@@ -188,6 +192,9 @@ class GraphStep:
         B, N, d, T, kcap, M, sm = self.B, self.N, self.d, self.T, self.kcap, self.Mq, self.small
         main = torch.cuda.current_stream()
         nms_done = [torch.cuda.Event() for _ in self.ranges]
+        cent_done = [torch.cuda.Event() for _ in self.ranges]
+        side_done = [torch.cuda.Event() for _ in self.ranges]
+        presplit = self.rows_engine == _lib.ROWS_SPLIT_TCGEN05
         for i, (lo, hi) in enumerate(self.ranges):
             st_ = self.streams[i]
             st_.wait_stream(main)
@@ -197,22 +204,38 @@ class GraphStep:
                 idx, K = sm["idx"][lo:hi], sm["K"][lo:hi]
                 C, W = self.C[lo:hi], self.W[lo:hi]
                 s, V, c, valid = sm["s"][lo:hi], sm["V"][lo:hi], sm["c"][lo:hi], sm["valid"][lo:hi]
+                sd_ = self.side_streams[i]
+                sd_.wait_stream(st_)
+                with torch.cuda.stream(sd_):                # beside the cluster stage: everything that needs X only
+                    if presplit:
+                        _lib.call("prifit_meanshift_rows_prepare", _ptr(X), Bb, N, d, self.rows_engine, _ptr(ws["rows"][0]), ws["rows"][1], _stream())
+                    if with_backward:
+                        self.gX[lo:hi].zero_()
                 _lib.call("prifit_bandwidth_fwd", _ptr(X), Bb, N, d, None, N, _ptr(self.kth[lo:hi]), _ptr(bw),
                           _ptr(ws["bw"][0]), ws["bw"][1], st)
                 _lib.call("prifit_meanshift_fwd", _ptr(X), _ptr(bw), Bb, N, d, T, _ptr(newX), self.engine,
                           _ptr(ws["ms"][0]), ws["ms"][1], st)
+                # the chain needs the centres (idx, K) only: the hard labels and their count follow on the side stream
                 _lib.call("prifit_nms_fwd", _ptr(newX), _ptr(bw), Bb, N, d, kcap, _ptr(idx), _ptr(K),
-                          _ptr(sm["labels"][lo:hi]), _ptr(sm["nlab"][lo:hi]), _ptr(ws["nms"][0]), ws["nms"][1], st)
-                nms_done[i].record(st_)
-                # cluster (b, k) owns draw number prefix(K)[b] + k of the host stream: the counts of the shapes in front
-                for j in range(i):
-                    st_.wait_event(nms_done[j])
-                _lib.call("prifit_noise_scatter_range", _ptr(self.flat), _ptr(sm["K"]), lo, Bb, kcap, _ptr(self.direct),
-                          _ptr(self.noise), st)
+                          None, None, _ptr(ws["nms"][0]), ws["nms"][1], st, launches=9)
+                cent_done[i].record(st_)
+                sd_.wait_event(cent_done[i])
+                with torch.cuda.stream(sd_):
+                    _lib.call("prifit_nms_labels", _ptr(newX), Bb, N, d, kcap, _ptr(K), _ptr(idx), _ptr(sm["labels"][lo:hi]),
+                              _ptr(sm["nlab"][lo:hi]), _ptr(ws["nms"][0]), ws["nms"][1], _stream())
+                    nms_done[i].record(sd_)
+                    # cluster (b, k) owns draw number prefix(K)[b] + k of the host stream: the counts of the shapes in front
+                    for j in range(i):
+                        sd_.wait_event(cent_done[j])
+                    _lib.call("prifit_noise_scatter_range", _ptr(self.flat), _ptr(sm["K"]), lo, Bb, kcap, _ptr(self.direct),
+                              _ptr(self.noise), _stream())
+                    side_done[i].record(sd_)
                 _lib.call("prifit_meanshift_rows_fwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), Bb, N, d, T, kcap,
-                          _ptr(self.traj[lo:hi]), _ptr(self.stat[lo:hi]), _ptr(C), self.rows_engine | self.rows_flags, _ptr(ws["rows"][0]), ws["rows"][1], st)
+                          _ptr(self.traj[lo:hi]), _ptr(self.stat[lo:hi]), _ptr(C), self.rows_fwd_engine | self.rows_flags,
+                          _ptr(ws["rows"][0]), ws["rows"][1], st, launches=1 if presplit else None)
                 _lib.call("prifit_membership_fwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), Bb, N, d, kcap, _ptr(W), _ptr(self.smax[lo:hi]),
                           _ptr(ws["memb"][0]), ws["memb"][1], st)
+                st_.wait_event(side_done[i])                # the noise matrices (fit) and, for the backward, the zeroed gX
                 _lib.call("prifit_fit_fwd", _ptr(self.P[lo:hi]), _ptr(W), _ptr(K), _ptr(self.noise[lo:hi]), Bb, N, kcap,
                           _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(self.fctx[lo:hi]), st)
                 _lib.call("prifit_sdf_loss_fwd", _ptr(self.Q[lo:hi]), _ptr(s), _ptr(V), _ptr(c), _ptr(valid), _ptr(K), Bb, M, kcap,
@@ -220,7 +243,7 @@ class GraphStep:
                 if with_backward:
                     # speculative backward of THIS branch, straight behind its forward: d(sum_b loss_b)/dX needs nothing from
                     # the other branches (a shape without a valid ellipsoid has argmin = -1 everywhere and contributes zero)
-                    self._branch_backward(i, lo, hi, self.g_ones)
+                    self._branch_backward(i, lo, hi, self.g_ones, zero_gx=False)     # zeroed on the side stream
         # the guard predicate's inputs leave for the host as soon as every branch has clustered, beside the chains
         for ev in nms_done:
             main.wait_event(ev)
@@ -233,7 +256,7 @@ class GraphStep:
     def _seq_forward_backward(self):
         self._seq_forward(with_backward=True)
 
-    def _branch_backward(self, i, lo, hi, gloss):
+    def _branch_backward(self, i, lo, hi, gloss, zero_gx=True):
         """Backward chain of one branch on the current stream; gloss[b] = dL/d(loss_b) up to the scale the last kernel applies."""
         N, d, T, kcap, M, sm = self.N, self.d, self.T, self.kcap, self.Mq, self.small
         Bb, ws, st = hi - lo, self.ws[i], _stream()
@@ -245,7 +268,8 @@ class GraphStep:
                   _ptr(self.argmin[lo:hi]), _ptr(gloss[lo:hi]), Bb, M, kcap, _ptr(gs), _ptr(gV), _ptr(gc), None, st)
         _lib.call("prifit_fit_bwd", _ptr(self.P[lo:hi]), _ptr(W), _ptr(K), _ptr(self.noise[lo:hi]), _ptr(self.fctx[lo:hi]),
                   _ptr(valid), _ptr(gs), _ptr(gV), _ptr(gc), Bb, N, kcap, _ptr(gW), None, st)
-        gX.zero_()
+        if zero_gx:
+            gX.zero_()
         _lib.call("prifit_membership_bwd", _ptr(C), _ptr(X), _ptr(bw), _ptr(K), _ptr(W), _ptr(self.smax[lo:hi]), _ptr(gW),
                   Bb, N, d, kcap, _ptr(gC), _ptr(gX), _ptr(ws["membb"][0]), ws["membb"][1], st)
         _lib.call("prifit_meanshift_rows_bwd", _ptr(X), _ptr(bw), _ptr(idx), _ptr(K), _ptr(self.traj[lo:hi]),
