@@ -204,15 +204,15 @@ class GraphStep:
                 idx, K = sm["idx"][lo:hi], sm["K"][lo:hi]
                 C, W = self.C[lo:hi], self.W[lo:hi]
                 s, V, c, valid = sm["s"][lo:hi], sm["V"][lo:hi], sm["c"][lo:hi], sm["valid"][lo:hi]
+                _lib.call("prifit_bandwidth_fwd", _ptr(X), Bb, N, d, None, N, _ptr(self.kth[lo:hi]), _ptr(bw),
+                          _ptr(ws["bw"][0]), ws["bw"][1], st)
                 sd_ = self.side_streams[i]
                 sd_.wait_stream(st_)
-                with torch.cuda.stream(sd_):                # beside the cluster stage: everything that needs X only
-                    if presplit:
+                with torch.cuda.stream(sd_):                # beside the all-seed kernel (tensor-bound, no memory traffic to speak
+                    if presplit:                            # of): what needs X only, and the zero-fill of the gradient buffer
                         _lib.call("prifit_meanshift_rows_prepare", _ptr(X), Bb, N, d, self.rows_engine, _ptr(ws["rows"][0]), ws["rows"][1], _stream())
                     if with_backward:
                         self.gX[lo:hi].zero_()
-                _lib.call("prifit_bandwidth_fwd", _ptr(X), Bb, N, d, None, N, _ptr(self.kth[lo:hi]), _ptr(bw),
-                          _ptr(ws["bw"][0]), ws["bw"][1], st)
                 _lib.call("prifit_meanshift_fwd", _ptr(X), _ptr(bw), Bb, N, d, T, _ptr(newX), self.engine,
                           _ptr(ws["ms"][0]), ws["ms"][1], st)
                 # the chain needs the centres (idx, K) only: the hard labels and their count follow on the side stream

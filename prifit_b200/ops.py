@@ -125,7 +125,9 @@ def meanshift(X, bw, iterations, engine=None):
     return out
 
 
-def nms(newX, bw, kcap):
+def nms(newX, bw, kcap, two_calls=False):
+    """two_calls: centres first (prifit_nms_fwd without label outputs), then prifit_nms_labels on the same workspace -- what
+    the graph step does to keep the label pass off a branch's critical chain; the results are the one-call ones."""
     newX, bw = _chk(newX), _chk(bw)
     B, N, d = newX.shape
     dev = newX.device
@@ -135,8 +137,14 @@ def nms(newX, bw, kcap):
     K = torch.empty(B, dtype=torch.int32, device=dev)
     labels = torch.empty(B, N, dtype=torch.int32, device=dev)
     nlab = torch.empty(B, dtype=torch.int32, device=dev)
-    _lib.call("prifit_nms_fwd", _ptr(newX), _ptr(bw), B, N, d, kcap, _ptr(idx), _ptr(K), _ptr(labels), _ptr(nlab),
-              _ptr(ws), nbytes, _stream())
+    if two_calls:
+        _lib.call("prifit_nms_fwd", _ptr(newX), _ptr(bw), B, N, d, kcap, _ptr(idx), _ptr(K), None, None,
+                  _ptr(ws), nbytes, _stream(), launches=9)
+        _lib.call("prifit_nms_labels", _ptr(newX), B, N, d, kcap, _ptr(K), _ptr(idx), _ptr(labels), _ptr(nlab),
+                  _ptr(ws), nbytes, _stream())
+    else:
+        _lib.call("prifit_nms_fwd", _ptr(newX), _ptr(bw), B, N, d, kcap, _ptr(idx), _ptr(K), _ptr(labels), _ptr(nlab),
+                  _ptr(ws), nbytes, _stream())
     return idx, K, labels, nlab
 
 
@@ -147,13 +155,18 @@ def _rows_engine(engine, d):
     return engine
 
 
-def rows_fwd(X, bw, idx, K, iterations, kcap, engine=None):
+def rows_fwd(X, bw, idx, K, iterations, kcap, engine=None, prepared=False):
+    """prepared: the operand preparation as a call of its own (prifit_meanshift_rows_prepare) before the forward -- what the
+    graph step does beside the all-seed kernel; same result."""
     B, N, d = X.shape
     dev = X.device
     T = int(iterations)
     engine = _rows_engine(engine, d)
     nbytes = _lib.load().prifit_meanshift_rows_workspace_bytes(B, N, d, engine)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    if prepared and (engine & 0xff) == ROWS_SPLIT_TCGEN05:
+        _lib.call("prifit_meanshift_rows_prepare", _ptr(X), B, N, d, engine, _ptr(ws), nbytes, _stream())
+        engine |= _lib.ROWS_WS_HOLDS_SPLIT
     traj = torch.empty(B, T + 1, kcap, d, dtype=torch.float32, device=dev)
     stat = torch.empty(B, max(T, 1), kcap, 2, dtype=torch.float32, device=dev)
     C = torch.empty(B, kcap, d, dtype=torch.float32, device=dev)

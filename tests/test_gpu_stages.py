@@ -159,6 +159,27 @@ def test_nms_planted_vs_oracle(cuda, n, kc):
         label_map(lab[0].cpu().numpy(), labels.numpy())
 
 
+def test_nms_in_two_calls_and_prepared_rows_equal_the_one_call_forms(cuda):
+    """prifit_nms_fwd(labels = NULL) + prifit_nms_labels, and prifit_meanshift_rows_prepare + forward with
+    PRIFIT_ROWS_WS_HOLDS_SPLIT (the graph step's way of keeping work off a branch's critical chain) give the bits of the
+    single calls."""
+    from prifit_b200 import ops, synthetic
+
+    E, _, _ = synthetic.planted_shapes(3, n_points=1500, n_clusters=9, seed=11)
+    X = ops.normalize_fwd(E.to(cuda))
+    kth = torch.full((3,), 75, dtype=torch.int32, device=cuda)
+    bw = ops.bandwidth(X, kth)
+    newX = ops.meanshift(X, bw, 8)
+    one, two = ops.nms(newX, bw, 32), ops.nms(newX, bw, 32, two_calls=True)
+    for a, b in zip(one, two):
+        assert torch.equal(a, b)
+    idx, K = one[0], one[1]
+    assert int(K.min()) >= 2
+    r1, r2 = ops.rows_fwd(X, bw, idx, K, 8, 32), ops.rows_fwd(X, bw, idx, K, 8, 32, prepared=True)
+    for a, b in zip(r1, r2):
+        assert torch.equal(a, b)
+
+
 def test_nms_many_modes_reports_count(cuda):
     """Bandwidth so small that every point is its own mode: K = N > Kcap must be reported (guard input)."""
     from prifit_b200 import ops
