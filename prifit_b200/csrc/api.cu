@@ -153,6 +153,17 @@ __global__ void __launch_bounds__(256) normalize_bwd_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------
 constexpr int CF_D = 128, CF_PTS = 32;
 
+__device__ __forceinline__ void warp_sum4(float (&v)[4]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+}
+
+// One CTA = 32 points x 128 channels through a shared-memory tile; a warp owns 4 points and carries them through the row
+// arithmetic TOGETHER (four interleaved shuffle reductions instead of four dependent chains), the 16 channel-row loads /
+// stores of a warp are independent and unrolled.  (First version: one point at a time, 26 / 46 us forward / backward at cfg2
+// against 13 / 21 us of the row-major kernels.)
 template <bool BWD>
 __global__ void __launch_bounds__(256) normalize_cf_kernel(const float* __restrict__ Ecf, const float* __restrict__ gX, int N,
                                                            float* __restrict__ out, const float* __restrict__ g_sum = nullptr,
@@ -162,46 +173,78 @@ __global__ void __launch_bounds__(256) normalize_cf_kernel(const float* __restri
     const int b = blockIdx.y, n0 = blockIdx.x * CF_PTS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* Eb = Ecf + (size_t)b * CF_D * N;
-    for (int c = warp; c < CF_D; c += 8) tile[c][lane] = n0 + lane < N ? Eb[(size_t)c * N + n0 + lane] : 0.f;
+    const bool in_n = n0 + lane < N;
+    float ld[CF_D / 8];
+#pragma unroll
+    for (int i = 0; i < CF_D / 8; ++i) ld[i] = in_n ? Eb[(size_t)(warp + 8 * i) * N + n0 + lane] : 0.f;
+#pragma unroll
+    for (int i = 0; i < CF_D / 8; ++i) tile[warp + 8 * i][lane] = ld[i];
     __syncthreads();
-    for (int p = warp * 4; p < warp * 4 + 4; ++p) {
-        const int n = n0 + p;
-        if (n >= N) break;                                           // warp-uniform
-        const float4 v = make_float4(tile[4 * lane][p], tile[4 * lane + 1][p], tile[4 * lane + 2][p], tile[4 * lane + 3][p]);
-        float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        ss = warp_sum(ss);
-        const float r0 = sqrtf(ss), nrm0 = fmaxf(r0, 1e-12f);
-        const float4 x1 = make_float4(v.x / nrm0, v.y / nrm0, v.z / nrm0, v.w / nrm0);
-        float ss1 = x1.x * x1.x + x1.y * x1.y + x1.z * x1.z + x1.w * x1.w;
-        ss1 = warp_sum(ss1);
-        const float r1 = sqrtf(ss1), nrm1 = fmaxf(r1, 1e-12f);
-        if (!BWD) {
-            reinterpret_cast<float4*>(out + ((size_t)b * N + n) * CF_D)[lane] =
-                make_float4(x1.x / nrm1, x1.y / nrm1, x1.z / nrm1, x1.w / nrm1);
-        } else {
-            float4 g = reinterpret_cast<const float4*>(gX + ((size_t)b * N + n) * CF_D)[lane];
-            const float up = upstream_scale(g_sum, g_mean, stats);
-            g.x *= up; g.y *= up; g.z *= up; g.w *= up;
-            float xg = (x1.x / nrm1) * g.x + (x1.y / nrm1) * g.y + (x1.z / nrm1) * g.z + (x1.w / nrm1) * g.w;
-            xg = warp_sum(xg);
-            const bool proj1 = r1 >= 1e-12f, proj0 = r0 >= 1e-12f;
-            const float xv[4] = {x1.x, x1.y, x1.z, x1.w}, gv[4] = {g.x, g.y, g.z, g.w};
-            float g1[4], x1g1 = 0.f;
+    const int p0 = warp * 4;
+    float4 v[4], g[4];
+    float ss[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int p = p0 + q;
+        v[q] = make_float4(tile[4 * lane][p], tile[4 * lane + 1][p], tile[4 * lane + 2][p], tile[4 * lane + 3][p]);
+        if (BWD) {
+            g[q] = n0 + p < N ? reinterpret_cast<const float4*>(gX + ((size_t)b * N + n0 + p) * CF_D)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        ss[q] = v[q].x * v[q].x + v[q].y * v[q].y + v[q].z * v[q].z + v[q].w * v[q].w;
+    }
+    warp_sum4(ss);
+    float4 x1[4];
+    float r0[4], nrm0[4], ss1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        r0[q] = sqrtf(ss[q]); nrm0[q] = fmaxf(r0[q], 1e-12f);
+        x1[q] = make_float4(v[q].x / nrm0[q], v[q].y / nrm0[q], v[q].z / nrm0[q], v[q].w / nrm0[q]);
+        ss1[q] = x1[q].x * x1[q].x + x1[q].y * x1[q].y + x1[q].z * x1[q].z + x1[q].w * x1[q].w;
+    }
+    warp_sum4(ss1);
+    float r1[4], nrm1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { r1[q] = sqrtf(ss1[q]); nrm1[q] = fmaxf(r1[q], 1e-12f); }
+    if (!BWD) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (n0 + p0 + q < N)
+                reinterpret_cast<float4*>(out + ((size_t)b * N + n0 + p0 + q) * CF_D)[lane] =
+                    make_float4(x1[q].x / nrm1[q], x1[q].y / nrm1[q], x1[q].z / nrm1[q], x1[q].w / nrm1[q]);
+    } else {
+        const float up = upstream_scale(g_sum, g_mean, stats);
+        float xg[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            g[q].x *= up; g[q].y *= up; g[q].z *= up; g[q].w *= up;
+            xg[q] = (x1[q].x / nrm1[q]) * g[q].x + (x1[q].y / nrm1[q]) * g[q].y + (x1[q].z / nrm1[q]) * g[q].z + (x1[q].w / nrm1[q]) * g[q].w;
+        }
+        warp_sum4(xg);
+        float g1[4][4], x1g1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool proj1 = r1[q] >= 1e-12f;
+            const float xv[4] = {x1[q].x, x1[q].y, x1[q].z, x1[q].w}, gv[4] = {g[q].x, g[q].y, g[q].z, g[q].w};
+            x1g1[q] = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                g1[i] = (gv[i] - (proj1 ? (xv[i] / nrm1) * xg : 0.f)) / nrm1;
-                x1g1 += xv[i] * g1[i];
+                g1[q][i] = (gv[i] - (proj1 ? (xv[i] / nrm1[q]) * xg[q] : 0.f)) / nrm1[q];
+                x1g1[q] += xv[i] * g1[q][i];
             }
-            x1g1 = warp_sum(x1g1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) tile[4 * lane + i][p] = (g1[i] - (proj0 ? xv[i] * x1g1 : 0.f)) / nrm0;
         }
-    }
-    if (BWD) {
+        warp_sum4(x1g1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool proj0 = r0[q] >= 1e-12f;
+            const float xv[4] = {x1[q].x, x1[q].y, x1[q].z, x1[q].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tile[4 * lane + i][p0 + q] = (g1[q][i] - (proj0 ? xv[i] * x1g1[q] : 0.f)) / nrm0[q];
+        }
         __syncthreads();
         float* Ob = out + (size_t)b * CF_D * N;
-        for (int c = warp; c < CF_D; c += 8)
-            if (n0 + lane < N) Ob[(size_t)c * N + n0 + lane] = tile[c][lane];
+#pragma unroll
+        for (int i = 0; i < CF_D / 8; ++i)
+            if (in_n) Ob[(size_t)(warp + 8 * i) * N + n0 + lane] = tile[warp + 8 * i][lane];
     }
 }
 

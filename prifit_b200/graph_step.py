@@ -443,6 +443,12 @@ class _Attach(torch.autograd.Function):
 
 _steps = {}
 
+# Optional callable run once per graph-replayed step after ALL of the step's device work (and its small host->device noise
+# copy) has been enqueued and before the host blocks on the guard inputs (~2/3 of a step later).  A training loop hangs the
+# host->device prefetch of its NEXT batch here: issued earlier it would sit in front of this step's own 27 KB copy on the
+# H2D engine's single queue; issued after convex_loss() returns it starts two thirds of a step late.
+enqueued_hook = None
+
 
 def default_enabled():
     return os.environ.get("PRIFIT_GRAPH", "1") != "0"
@@ -480,12 +486,15 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
         src = src.contiguous()                             # neither layout: one copy, like the eager path's
     step = get_step(B, N, d, M, quantile, iterations, max_num_clusters, engine, rows_engine, E.device,
                     default_branches() if branches is None else int(branches), cf)
-    np_state = np.random.get_state()
     want_grad = E.requires_grad and torch.is_grad_enabled()
     res = step.run_forward(src.detach(), P.detach(), None if Q is None else Q.detach(), noise, want_grad, split_backward=bool(dist_reduce))
+    np_state = np.random.get_state()                       # (run_forward draws from torch's generator only) after the launch:
+                                                           # everything in front of it delays the device
     loss_sum, loss = res["loss_sum"], res["loss"]
     if want_grad:
         loss_sum, loss = _Attach.apply(src, step, res["serial"], loss_sum, loss)
+    if enqueued_hook is not None:
+        enqueued_hook()                                    # the caller's prefetch of its next batch, before the host blocks
     pipeline.replay_shuffles(B, N)                         # host RNG parity (src/mean_shift.py:150) while the cluster stage runs
     if not step.finish_forward(res):
         np.random.set_state(np_state)                      # the eager redo replays the shuffles of every pass itself
