@@ -279,7 +279,10 @@ def run_ours(args):
                 ev2.record(read_stream)
             pending["ev"], pending["slot"] = ev2, slot
 
+    host_marks = {"n": 0, "stage+wait": 0.0, "convex_loss": 0.0, "backward": 0.0, "hook": 0.0}
+
     def step_e2e(i, last_step):
+        t0 = time.perf_counter()
         if i not in staged:
             stage_inputs(i)
         X, pts, ev = staged.pop(i)
@@ -294,17 +297,23 @@ def run_ours(args):
         fired = []
 
         def hook():
+            th = time.perf_counter()
             fired.append(1)
             if not last_step:
                 stage_inputs(i + 1)
             read_back_previous()
+            host_marks["hook"] += time.perf_counter() - th
         graph_step.enqueued_hook = hook
+        t1 = time.perf_counter()
         total, l, params, labels = cl.convex_loss(pts, pts, X, quantile=q, iterations=T, max_num_clusters=kmax,
                                                   dist_reduce=world > 1, full_chamfer=False)
         graph_step.enqueued_hook = None
         if not fired:                                # eager path (a guard redo, PRIFIT_GRAPH=0): no hook call
             hook()
+        t2 = time.perf_counter()
         total.backward()
+        t3 = time.perf_counter()
+        host_marks["n"] += 1; host_marks["stage+wait"] += t1 - t0; host_marks["convex_loss"] += t2 - t1; host_marks["backward"] += t3 - t2
         ev_l = torch.cuda.Event()
         ev_l.record()
         # l = the global mean (one 8-byte all-reduce inside convex_loss when N > 1)
@@ -391,7 +400,7 @@ def run_ours(args):
         api_ms = api_total / min(args.steps, 10)
     e2e_last = args.warmup + args.steps - 1
     e2e_ms, _ = timed_region(lambda i, timed: step_e2e(i, i == e2e_last or i == args.warmup - 1), args.steps, args.warmup)
-    if args.trace_e2e and rank == 0:
+    if args.trace_e2e and world == 1:                # (one rank tracing alone would leave the others' collectives hanging)
         # diagnostics only (after every measurement): device timeline of the end-to-end loop under CUPTI
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         from device_timeline import print_timeline
@@ -450,6 +459,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(host_Xcf[0].numel() * 4 + host_Pcf[0].numel() * 4), "d2h_bytes_per_step": 4,
                 "api_resident_ms_per_step": None if api_ms is None else round(api_ms, 4),
                 "h2d_copy_ms_per_step": round(statistics.median(a.elapsed_time(b) for a, b in h2d_events[-args.steps:]), 4),
+                "host_us_per_step": {k: round(v / max(host_marks["n"], 1) * 1e6, 1) for k, v in host_marks.items() if k != "n"},
                 "api": "prifit_b200.convex_loss.convex_loss(points[B,3,N], chamfer[B,3,N], X[B,128,N], full_chamfer=False) + backward; "
                        "full_chamfer=False = the SDF half of the fitting loss, the term the metric is defined on (SURVEY 8d); the 25 MB input "
                        "gradient stays on the device (training), only the 4-byte loss is read back"},
