@@ -122,8 +122,6 @@ class GraphStep:
         self.direct = torch.zeros(1, dtype=i32, device=device)
         self.direct_host = 0
         self.kth = torch.full((B,), min(kth, N), dtype=i32, device=device)
-        self.g_sum, self.g_mean = torch.zeros(1, device=device), torch.zeros(1, device=device)
-        self.g_zero = [True, True]
         self.g_one, self.g_nil = torch.ones(1, device=device), torch.zeros(1, device=device)   # upstream of the stand-alone backward graph
         self.g_ones = torch.ones(B, device=device)                    # dL/d(loss_b) of the speculative backward chains
         self.side = torch.cuda.Stream(device=device)                  # multi-GPU all-reduce beside the stand-alone backward graph
@@ -283,10 +281,10 @@ class GraphStep:
                   _ptr(self.gloss), _stream())
         self._fork_join(lambda i, lo, hi: self._branch_backward(i, lo, hi, self.gloss))
 
-    def _scaled_normalize_bwd(self, E, out=None):
+    def _scaled_normalize_bwd(self, E, out=None, g_sum=None, g_mean=None):
         out = self.gE if out is None else out
         _lib.call("prifit_normalize_bwd_scaled", _ptr(E), _ptr(self.gX), self.B, self.N, self.d, 1 if self.cf else 0,
-                  _ptr(self.g_sum), _ptr(self.g_mean), _ptr(self.small["stats"]), _ptr(out), _stream())
+                  _ptr(g_sum), _ptr(g_mean), _ptr(self.small["stats"]), _ptr(out), _stream())
         return out
 
     def _capture(self):
@@ -403,14 +401,10 @@ class GraphStep:
         if serial != self.serial:
             raise _lib.PrifitError("the graph-replayed step's buffers were overwritten by a later forward call before its "
                                    "backward ran; call backward first, or use graph=False / PRIFIT_GRAPH=0")
-        for i, (g, dst) in enumerate(((g_sum, self.g_sum), (g_mean, self.g_mean))):
-            if g is None:
-                if not self.g_zero[i]:
-                    dst.zero_()
-                    self.g_zero[i] = True
-            else:
-                dst.copy_(g.reshape(1))
-                self.g_zero[i] = False
+        # the upstream gradients are read by the kernel where autograd put them (fp32 device scalars; a missing one is a null
+        # pointer = 0): no staging copies on the host's critical path between the guard decision and the next step's launch
+        gs = [None if g is None else (g if (g.dtype == torch.float32 and g.is_cuda) else g.to(self.device, torch.float32)).reshape(1)
+              for g in (g_sum, g_mean)]
         if self.backward_serial != serial:                 # the forward ran without grad mode's speculation (not expected)
             self.graphs[1].replay()
             _lib._launches += self.launches[1]
@@ -420,7 +414,7 @@ class GraphStep:
         # it before the next replay.  Channel-first input: the gradient reaches the caller's leaf through view nodes
         # (transpose / permute), whose fresh view objects AccumulateGrad would adopt without copying, so the kernel writes
         # into a fresh tensor.
-        return self._scaled_normalize_bwd(E, torch.empty_like(self.gE) if self.cf else None)
+        return self._scaled_normalize_bwd(E, torch.empty_like(self.gE) if self.cf else None, gs[0], gs[1])
 
 
 class _Attach(torch.autograd.Function):
