@@ -248,16 +248,24 @@ def run_ours(args):
 
     h2d_events = []
 
+    # two device-side input slots, filled alternately (no allocator traffic in the loop); a slot is refilled only after the
+    # backward of the step that read it (two steps earlier) is through
+    in_slots = [(torch.empty_like(host_Xcf[0], device=dev), torch.empty_like(host_Pcf[0], device=dev)) for _ in range(2)]
+    slot_free = [None, None]
+
     def stage_inputs(i):
+        Xb, Pb = in_slots[i & 1]
         with torch.cuda.stream(copy_stream):
+            if slot_free[i & 1] is not None:
+                copy_stream.wait_event(slot_free[i & 1])
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record(copy_stream)
-            X = host_Xcf[i % n_sets].to(dev, non_blocking=True)
-            pts = host_Pcf[i % n_sets].to(dev, non_blocking=True)
+            Xb.copy_(host_Xcf[i % n_sets], non_blocking=True)
+            Pb.copy_(host_Pcf[i % n_sets], non_blocking=True)
             ev = torch.cuda.Event(enable_timing=True)
             ev.record(copy_stream)
         h2d_events.append((e0, ev))
-        staged[i] = (X, pts, ev)
+        staged[i] = (Xb, Pb, ev)
 
     def drain_loss():
         if "ev" in pending:
@@ -287,8 +295,7 @@ def run_ours(args):
             stage_inputs(i)
         X, pts, ev = staged.pop(i)
         torch.cuda.current_stream().wait_event(ev)
-        X.record_stream(torch.cuda.current_stream()); pts.record_stream(torch.cuda.current_stream())
-        X = X.requires_grad_(True)
+        X = X.detach().requires_grad_(True)
         # Prefetch of the next step's inputs, like a data loader would: issued from graph_step.enqueued_hook, i.e. once this
         # step's device work and its own small host->device copy (the staged noise draws) are enqueued and before the host
         # blocks on the guard inputs.  The H2D copy engine serves one queue: 25 MB in front of the 27 KB noise copy would
@@ -316,6 +323,7 @@ def run_ours(args):
         host_marks["n"] += 1; host_marks["stage+wait"] += t1 - t0; host_marks["convex_loss"] += t2 - t1; host_marks["backward"] += t3 - t2
         ev_l = torch.cuda.Event()
         ev_l.record()
+        slot_free[i & 1] = ev_l                      # this step's input slot may be refilled once its backward is through
         # l = the global mean (one 8-byte all-reduce inside convex_loss when N > 1)
         pending["L"], pending["ev_l"], pending["slot_next"] = l, ev_l, i & 1
         if last_step:

@@ -143,9 +143,18 @@ class GraphStep:
         self.gloss, self.gs, self.gV, self.gc = buf(B), buf(B, kcap, 3), buf(B, kcap, 3, 3), buf(B, kcap, 3)
         self.gW, self.gC, self.gX = buf(B, kcap, N), buf(B, kcap, d), buf(B, N, d)
         self.gE = buf(B, d, N) if cf else buf(B, N, d)
+        # The guard's inputs reach the host in two copies.  [K | K | serial] leaves as soon as every branch has its centres:
+        # n_labels <= K, so K <= max_num_clusters (the usual case) already decides the guard, and K is all the host generator
+        # needs.  [K | n_labels | serial] follows when the label passes (on the side streams, off the chains) are through; the
+        # host waits for it only if some K exceeds the cap, otherwise n_labels_host is read when somebody looks at it.
         self.counts = torch.zeros(2 * B + 1, dtype=i32).pin_memory()      # [K | n_labels | serial], polled by the host
         self.counts_np = self.counts.numpy()
         self.counts_dev = torch.zeros(2 * B + 1, dtype=i32, device=device)
+        self.countsK = torch.zeros(2 * B + 1, dtype=i32).pin_memory()     # [K | K | serial]
+        self.countsK_np = self.countsK.numpy()
+        self.countsK_dev = torch.zeros(2 * B + 1, dtype=i32, device=device)
+        self.serialK_dev = torch.zeros(1, dtype=i32, device=device)
+        self._lazy_nlab = None
         self.serial_dev = torch.zeros(1, dtype=i32, device=device)
         self.replays = 0
         # ---- per-branch workspaces
@@ -243,6 +252,10 @@ class GraphStep:
                     # the other branches (a shape without a valid ellipsoid has argmin = -1 everywhere and contributes zero)
                     self._branch_backward(i, lo, hi, self.g_ones, zero_gx=False)     # zeroed on the side stream
         # the guard predicate's inputs leave for the host as soon as every branch has clustered, beside the chains
+        for ev in cent_done:
+            main.wait_event(ev)
+        _lib.call("prifit_pack_counts", _ptr(sm["K"]), _ptr(sm["K"]), B, _ptr(self.serialK_dev), _ptr(self.countsK_dev), _stream())
+        self.countsK.copy_(self.countsK_dev, non_blocking=True)
         for ev in nms_done:
             main.wait_event(ev)
         _lib.call("prifit_pack_counts", _ptr(sm["K"]), _ptr(sm["nlab"]), B, _ptr(self.serial_dev), _ptr(self.counts_dev), _stream())
@@ -318,6 +331,8 @@ class GraphStep:
         _lib._launches -= sum(self.launches)          # capture enqueues nothing; replays are counted in run_*
         self.serial_dev.zero_()
         self.counts.zero_()
+        self.countsK.zero_()
+        self.serialK_dev.zero_()
         torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------------------------------ per step
@@ -326,7 +341,11 @@ class GraphStep:
         will be asked for --, snapshot of the small outputs) without waiting for anything and returns the result dict;
         finish_forward() then makes the guard decision.  split_backward (multi-GPU): forward graph, then the stand-alone
         backward graph, so that the all-reduce of the forward results can run beside the backward."""
+        if self._lazy_nlab is not None:
+            self._lazy_nlab.resolve()                      # (landed long ago) before this replay overwrites the pinned buffer
+            self._lazy_nlab = None
         self.serial += 1
+        self._normalize_fwd(E)                             # first: the device works on it while the host stages the rest
         self.P.copy_(P)
         if self.Q is not self.P:
             self.Q.copy_(Q)
@@ -348,7 +367,6 @@ class GraphStep:
         if want_direct != self.direct_host:
             self.direct.fill_(want_direct)
             self.direct_host = want_direct
-        self._normalize_fwd(E)
         self.replays += 1
         which = 2 if (want_grad and not split_backward) else 0    # each branch's backward chain follows its forward
         self.graphs[which].replay()
@@ -373,29 +391,35 @@ class GraphStep:
     def finish_forward(self, out):
         """Host side of the guard (src/ellipsoid_utils.py:19-26): waits for the cluster stage only (the chains keep the device
         busy), reads the counts, settles the host generator.  False = a shape exceeded the cap: redo eagerly."""
-        # the step's one host synchronisation: poll pinned memory until the graph's copy of [K | n_labels | serial] for THIS
-        # replay has landed (the copy happens in the middle of the graph, so no stream / event wait can express it)
-        want, cn, B = self.replays, self.counts_np, self.B
+        want, B = self.replays, self.B
+        self._poll(self.countsK_np, want)
+        K_host = self.countsK_np[:B].tolist()
+        state = self._state
+        if state is not None:
+            torch.set_rng_state(state)
+        lazy = _LazyLabelCounts(self, want)
+        if max(K_host) > self.kcap or (max(K_host) > self.kmax and max(lazy) > self.kmax):
+            # src/ellipsoid_utils.py:23-24 (quantile doubling), or a shape accepted with more centres than the padding
+            # holds (re-run in the 64-wide layout): both redo the step on the eager path
+            return False
+        if state is not None:
+            torch.rand(int(sum(K_host)), 3, 3)             # one rand(3, 3) per attempted cluster, like the reference
+        self._lazy_nlab = lazy
+        out["K_host"], out["n_labels_host"] = K_host, lazy
+        return True
+
+    def _poll(self, cn, want):
+        """The step's one host synchronisation: poll pinned memory until the graph's copy for replay number `want` has landed
+        (the copy happens in the middle of the graph, so no stream / event wait can express it)."""
         spins, t0 = 0, None
-        while cn[2 * B] != want:
+        last = cn.shape[0] - 1
+        while cn[last] != want:
             spins += 1
             if spins & 0xffff == 0:
                 import time
                 t0 = t0 or time.time()
                 if time.time() - t0 > 30.0:
                     raise _lib.PrifitError("graph step: the cluster counts of replay %d never arrived (device error?)" % want)
-        K_host, nlab_host = cn[:B].tolist(), cn[B:2 * B].tolist()
-        state = self._state
-        if state is not None:
-            torch.set_rng_state(state)
-        if max(nlab_host) > self.kmax or max(K_host) > self.kcap:
-            # src/ellipsoid_utils.py:23-24 (quantile doubling), or a shape accepted with more centres than the padding
-            # holds (re-run in the 64-wide layout): both redo the step on the eager path
-            return False
-        if state is not None:
-            torch.rand(int(sum(K_host)), 3, 3)             # one rand(3, 3) per attempted cluster, like the reference
-        out["K_host"], out["n_labels_host"] = K_host, nlab_host
-        return True
 
     def run_backward(self, serial, g_sum, g_mean, E):
         if serial != self.serial:
@@ -415,6 +439,37 @@ class GraphStep:
         # (transpose / permute), whose fresh view objects AccumulateGrad would adopt without copying, so the kernel writes
         # into a fresh tensor.
         return self._scaled_normalize_bwd(E, torch.empty_like(self.gE) if self.cf else None, gs[0], gs[1])
+
+
+class _LazyLabelCounts:
+    """n_labels_host of a graph-replayed step: a list of B ints, read from pinned memory when somebody looks at it (the label
+    passes run beside the latency chains and land a few tens of microseconds after the centre counts the host waits for)."""
+
+    def __init__(self, step, want):
+        self._step, self._want, self._vals = step, want, None
+
+    def resolve(self):
+        if self._vals is None:
+            st = self._step
+            st._poll(st.counts_np, self._want)
+            self._vals = st.counts_np[st.B:2 * st.B].tolist()
+            self._step = None
+        return self._vals
+
+    def __len__(self):
+        return len(self.resolve())
+
+    def __iter__(self):
+        return iter(self.resolve())
+
+    def __getitem__(self, i):
+        return self.resolve()[i]
+
+    def __eq__(self, other):
+        return self.resolve() == list(other)
+
+    def __repr__(self):
+        return repr(self.resolve())
 
 
 class _Attach(torch.autograd.Function):
@@ -438,9 +493,12 @@ class _Attach(torch.autograd.Function):
 _steps = {}
 
 # Optional callable run once per graph-replayed step after ALL of the step's device work (and its small host->device noise
-# copy) has been enqueued and before the host blocks on the guard inputs (~2/3 of a step later).  A training loop hangs the
-# host->device prefetch of its NEXT batch here: issued earlier it would sit in front of this step's own 27 KB copy on the
-# H2D engine's single queue; issued after convex_loss() returns it starts two thirds of a step late.
+# copy) has been enqueued, just before the host blocks on the guard inputs (about 0.8 ms after the launch, two thirds of a
+# step before the call returns).  A training loop hangs the host->device prefetch of its NEXT batch and other per-step host
+# chores here: issued before the call, the copy would sit in front of this step's own 27 KB copy on the H2D engine's single
+# queue; issued after the call returns, it starts late and its host cost sits between the guard decision and the next
+# launch, where the device only has ~0.5 ms of latency chains queued.  (The hook must not draw from torch's CPU generator:
+# the noise stream is rewound to the reference's position after the guard decision.)
 enqueued_hook = None
 
 
@@ -487,9 +545,12 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
     loss_sum, loss = res["loss_sum"], res["loss"]
     if want_grad:
         loss_sum, loss = _Attach.apply(src, step, res["serial"], loss_sum, loss)
-    if enqueued_hook is not None:
-        enqueued_hook()                                    # the caller's prefetch of its next batch, before the host blocks
     pipeline.replay_shuffles(B, N)                         # host RNG parity (src/mean_shift.py:150) while the cluster stage runs
+    if enqueued_hook is not None:
+        # the caller's prefetch of its next batch: the last thing before the host blocks (~0.8 ms after the launch), on purpose --
+        # a 25 MB host->device copy that lands during the all-seed kernel (it goes through L2, where that kernel's key tiles
+        # live) cost 10-25 % of the step in bench.py's end-to-end loop; behind it, the latency chains do not care
+        enqueued_hook()
     if not step.finish_forward(res):
         np.random.set_state(np_state)                      # the eager redo replays the shuffles of every pass itself
         return None
