@@ -524,6 +524,28 @@ def test_graph_step_guard_redo_and_stale_backward(cuda, golden_dir):
     o2["loss"].backward()
 
 
+def test_enqueued_hook_and_lazy_label_counts(cuda, monkeypatch):
+    """graph_step.enqueued_hook runs once per graph-replayed step (after the step is enqueued, before the host waits) and not
+    on the eager path; the label counts of a graph step arrive behind the centre counts and are read on first use."""
+    from prifit_b200 import graph_step, pipeline, synthetic
+
+    E, P, _ = synthetic.planted_shapes(4, n_points=600, n_clusters=5, seed=21)
+    E, P = E.to(cuda), P.to(cuda)
+    calls = []
+    monkeypatch.setattr(graph_step, "enqueued_hook", lambda: calls.append(torch.cuda.current_stream().cuda_stream))
+    out = pipeline.fit_loss(E.clone().requires_grad_(True), P, quantile=0.05, iterations=6, max_num_clusters=25)
+    assert out.get("graph") and len(calls) == 1
+    res = out["cluster"]
+    nlab = res.n_labels_host                       # lazy sequence: resolves against pinned memory here
+    assert len(nlab) == 4 and list(nlab) == [int(v) for v in torch.stack([l.unique().numel() * torch.ones((), dtype=torch.int64)
+                                                                            for l in res.labels.cpu()])]
+    assert nlab == list(nlab) and max(nlab) <= min(25, max(res.K_host))
+    out2 = pipeline.fit_loss(E.clone().requires_grad_(True), P, quantile=0.05, iterations=6, max_num_clusters=25)
+    assert len(calls) == 2 and list(out2["cluster"].n_labels_host) == list(nlab)
+    pipeline.fit_loss(E.clone().requires_grad_(True), P, quantile=0.05, iterations=6, max_num_clusters=25, graph=False)
+    assert len(calls) == 2
+
+
 def test_channel_first_public_api_graph_vs_eager(cuda, monkeypatch):
     """convex_loss() takes the reference's channel-first tensors.  The graph path keeps them channel-first (the
     normalisation kernels transpose on the fly, same row arithmetic), the eager path permutes + copies: identical
