@@ -203,12 +203,20 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     _lib.load()
     B, N, q, T, kmax, kc = WORKLOADS[args.workload]
+    strong = args.global_shapes is not None
+    if strong:
+        # strong scaling (SURVEY 8d's extra): a fixed global batch cut over the ranks, one call per rank and step
+        if args.global_shapes % world:
+            raise SystemExit("--global-shapes must be a multiple of the number of GPUs")
+        B = args.global_shapes // world
     engine = ops.MS_FP32_SIMT if args.engine == "fp32" else ops.MS_F16_TCGEN05
     ops.DEFAULT_ENGINE = engine
 
     # rotating synthetic input sets; rank r, set s uses shapes seeded (s*world + r) * B + b
     host_E, host_P = [], []
     n_sets = N_SETS if N <= 4096 else 2          # cfg4: two sets of 82 MB of embeddings already exceed the 126 MB L2
+    if strong:
+        n_sets = max(2, min(N_SETS, (160 << 20) // (B * N * D * 4) + 1))
     for s in range(n_sets):
         E, P, _ = synthetic.planted_shapes(B, n_points=N, n_clusters=kc, seed=1000 + (s * world + rank) * B)
         host_E.append(E.pin_memory()); host_P.append(P.pin_memory())
@@ -450,7 +458,7 @@ def run_ours(args):
         "metric": "shapes/sec mean-shift+ellipsoid fit fwd+bwd (2048 pts)" if N == 2048 else
                   "shapes/sec mean-shift+ellipsoid fit fwd+bwd (%d pts)" % N,
         "value": round(shapes_per_s, 2), "unit": "shapes/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32 (all-seed mean-shift GEMMs: %s)" % ("f16 operands / f32 accumulate, tcgen05" if engine == ops.MS_F16_TCGEN05 else "f32 simt"),
         "data": "synthetic",
         "config": {"workload": "%s: %d shapes x %d pts x %d-d per GPU, T=%d, quantile=%g, max_num_clusters=%d, "
@@ -703,6 +711,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg5"])
+    ap.add_argument("--global-shapes", type=int, default=None, metavar="G",
+                    help="strong scaling: G shapes in total, G / gpus per rank and step (default: the workload's per-GPU batch, weak scaling)")
     ap.add_argument("--no-extras", action="store_true", help="skip the sustained / cfg4 / cfg5 sub-measurements of the default line")
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "fp32"])
     ap.add_argument("--trace-e2e", default=None, metavar="FILE", help="write a device timeline of the end-to-end loop (diagnostics)")
