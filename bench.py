@@ -264,6 +264,7 @@ def run_ours(args):
     def stage_inputs(i):
         Xb, Pb = in_slots[i & 1]
         with torch.cuda.stream(copy_stream):
+            graph_step.gate_on_cluster_stage(copy_stream)   # behind the running step's all-seed kernel (L2), whatever the host's timing
             if slot_free[i & 1] is not None:
                 copy_stream.wait_event(slot_free[i & 1])
             e0 = torch.cuda.Event(enable_timing=True)

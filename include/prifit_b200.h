@@ -174,6 +174,10 @@ int prifit_noise_scatter_range(const float* flat, const int32_t* K, int b0, int 
 /* out[2B + 1] = [K | n_labels | ++*serial_inout]: the guard predicate's inputs (src/ellipsoid_utils.py:23) packed for ONE
  * device -> host copy; the serial number lets a host that polls pinned memory recognise the copy of the current step. */
 int prifit_pack_counts(const int32_t* K, const int32_t* n_labels, int B, int32_t* serial_inout, int32_t* out, void* stream);
+/* Device-side gate: a one-thread kernel on `stream` that returns once *flag >= want (device memory; bounded spin, ~50 ms).  The
+ * host-side graph step bumps such a counter (prifit_pack_counts) when every branch has left the cluster stage; a prefetch stream
+ * gated on it starts its host->device copy behind the all-seed kernel whatever the host's timing. */
+int prifit_spin_until_ge(const int32_t* flag, int32_t want, void* stream);
 
 /* k8 -- SDF half of the fitting loss.  convex_loss.py:313-343 + src/utils.py:407-411.
  *   Q[B,M,3]; loss_out[B] = 0.5 * mean_j (min_k |sdf_kj|)^2 over valid ellipsoids (0 if none);

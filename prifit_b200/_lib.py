@@ -50,6 +50,7 @@ SIGNATURES = {
     "prifit_noise_scatter": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "prifit_noise_scatter_range": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "prifit_pack_counts": (_i, [_p, _p, _i, _p, _p, _p]),
+    "prifit_spin_until_ge": (_i, [_p, _i, _p]),
     "prifit_masked_mean_fwd": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "prifit_masked_mean_bwd": (_i, [_p, _p, _p, _p, _i, _p, _p]),
     "prifit_sample_counts": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
@@ -117,7 +118,7 @@ LAUNCHES = {
     "prifit_nms_fwd": 10, "prifit_nms_labels": 2, "prifit_meanshift_rows_prepare": 1, "prifit_meanshift_rows_fwd": 2, "prifit_meanshift_rows_bwd": 2,
     "prifit_membership_fwd": 2, "prifit_membership_bwd": 2, "prifit_fit_fwd": 1, "prifit_fit_bwd": 1,
     "prifit_sdf_loss_fwd": 2, "prifit_sdf_loss_bwd": 1,
-    "prifit_masked_mean_fwd": 1, "prifit_masked_mean_bwd": 1, "prifit_noise_scatter": 1, "prifit_noise_scatter_range": 1, "prifit_pack_counts": 1,
+    "prifit_masked_mean_fwd": 1, "prifit_masked_mean_bwd": 1, "prifit_noise_scatter": 1, "prifit_noise_scatter_range": 1, "prifit_pack_counts": 1, "prifit_spin_until_ge": 1,
     "prifit_intersect_fwd": 2, "prifit_intersect_bwd": 1, "prifit_entropy_fwd": 2, "prifit_entropy_bwd": 1, "prifit_nn_loss_fwd": 2, "prifit_nn_loss_bwd": 1,
 }
 _launches = 0

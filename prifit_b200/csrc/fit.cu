@@ -477,6 +477,25 @@ extern "C" int prifit_noise_scatter_range(const float* flat, const int32_t* K, i
     return 0;
 }
 
+// Device-side gate: one thread spins (with back-off) until *flag >= want, then the stream it was launched on goes on.  The
+// graph step bumps a device counter when every branch has left the throughput-bound cluster stage; a caller's prefetch stream
+// waits here so that its host->device copy (which goes through L2) lands behind the all-seed kernel whatever the host's timing.
+// Bounded: gives up after ~50 ms (a gate must never hang a stream).
+__global__ void spin_until_ge_kernel(const volatile int32_t* flag, int32_t want) {
+    const long long t0 = clock64();
+    while (*flag < want) {
+        __nanosleep(500);
+        if (clock64() - t0 > 100000000LL) break;
+    }
+}
+
+extern "C" int prifit_spin_until_ge(const int32_t* flag, int32_t want, void* stream) {
+    PF_CHECK_ARG(flag, PRIFIT_E_BADARG, "null pointer");
+    spin_until_ge_kernel<<<1, 1, 0, pf_stream(stream)>>>(flag, want);
+    PF_LAUNCH_CHECK();
+    return 0;
+}
+
 // [K[0..B) | n_labels[0..B) | ++serial] -> out[2B + 1]: what the host's guard decision needs, in one buffer for one D2H copy;
 // the serial number tells the polling host that the copy it sees belongs to this replay
 __global__ void pack_counts_kernel(const int32_t* __restrict__ K, const int32_t* __restrict__ nlab, int B,

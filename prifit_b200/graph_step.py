@@ -35,6 +35,7 @@ max_num_clusters the step is redone on the eager path (quantile doubling, sub-ba
 Buffers are static: the tensors returned for a step stay valid until the next step on the same GraphStep; the
 small ones (losses, cluster lists, labels, ellipsoid parameters) are snapshotted with one copy and stay valid.
 """
+import ctypes
 import os
 
 import numpy as np
@@ -493,13 +494,26 @@ class _Attach(torch.autograd.Function):
 _steps = {}
 
 # Optional callable run once per graph-replayed step after ALL of the step's device work (and its small host->device noise
-# copy) has been enqueued, just before the host blocks on the guard inputs (about 0.8 ms after the launch, two thirds of a
-# step before the call returns).  A training loop hangs the host->device prefetch of its NEXT batch and other per-step host
-# chores here: issued before the call, the copy would sit in front of this step's own 27 KB copy on the H2D engine's single
-# queue; issued after the call returns, it starts late and its host cost sits between the guard decision and the next
-# launch, where the device only has ~0.5 ms of latency chains queued.  (The hook must not draw from torch's CPU generator:
-# the noise stream is rewound to the reference's position after the guard decision.)
+# copy) has been enqueued and before the host blocks on the guard inputs (two thirds of a step).  A training loop hangs its
+# per-step host chores here -- above all the host->device prefetch of its NEXT batch, on a stream gated by
+# gate_on_cluster_stage(): issued before the call, the copy would sit in front of this step's own 27 KB copy on the H2D
+# engine's single queue; issued after the call returns, it starts late and its host cost sits between the guard decision
+# and the next launch, where the device only has ~0.5 ms of latency chains queued.  (The hook must not draw from torch's
+# CPU generator: the noise stream is rewound to the reference's position after the guard decision.)
 enqueued_hook = None
+_last_step = None
+
+
+def gate_on_cluster_stage(stream):
+    """Makes `stream` wait (on the device: a one-thread spin kernel, no host involvement) until the most recently launched
+    graph step has left its throughput-bound cluster stage.  For a prefetch issued from enqueued_hook: a 25 MB host->device
+    copy goes through L2, where the all-seed kernel's key tiles live -- landing during that kernel it cost 10-25 % of the
+    step in bench.py's end-to-end loop, erratically (it depends on how fast the host gets to the hook); behind it, the
+    latency chains do not care."""
+    st = _last_step
+    if st is None:
+        return
+    _lib.call("prifit_spin_until_ge", _ptr(st.serialK_dev), int(st.replays), ctypes.c_void_p(stream.cuda_stream))
 
 
 def default_enabled():
@@ -545,12 +559,11 @@ def fit_loss(E, P, quantile, iterations, max_num_clusters, noise, Q, engine, bra
     loss_sum, loss = res["loss_sum"], res["loss"]
     if want_grad:
         loss_sum, loss = _Attach.apply(src, step, res["serial"], loss_sum, loss)
-    pipeline.replay_shuffles(B, N)                         # host RNG parity (src/mean_shift.py:150) while the cluster stage runs
+    global _last_step
+    _last_step = step
     if enqueued_hook is not None:
-        # the caller's prefetch of its next batch: the last thing before the host blocks (~0.8 ms after the launch), on purpose --
-        # a 25 MB host->device copy that lands during the all-seed kernel (it goes through L2, where that kernel's key tiles
-        # live) cost 10-25 % of the step in bench.py's end-to-end loop; behind it, the latency chains do not care
-        enqueued_hook()
+        enqueued_hook()                                    # the caller's per-step host chores, before the host blocks
+    pipeline.replay_shuffles(B, N)                         # host RNG parity (src/mean_shift.py:150) while the cluster stage runs
     if not step.finish_forward(res):
         np.random.set_state(np_state)                      # the eager redo replays the shuffles of every pass itself
         return None

@@ -532,9 +532,19 @@ def test_enqueued_hook_and_lazy_label_counts(cuda, monkeypatch):
     E, P, _ = synthetic.planted_shapes(4, n_points=600, n_clusters=5, seed=21)
     E, P = E.to(cuda), P.to(cuda)
     calls = []
-    monkeypatch.setattr(graph_step, "enqueued_hook", lambda: calls.append(torch.cuda.current_stream().cuda_stream))
+    side = torch.cuda.Stream(device=cuda)
+    flag = torch.zeros(1, device=cuda)
+
+    def hook():
+        calls.append(1)
+        graph_step.gate_on_cluster_stage(side)      # device-side: `side` continues once the step has left its cluster stage
+        with torch.cuda.stream(side):
+            flag.add_(1.0)
+    monkeypatch.setattr(graph_step, "enqueued_hook", hook)
     out = pipeline.fit_loss(E.clone().requires_grad_(True), P, quantile=0.05, iterations=6, max_num_clusters=25)
     assert out.get("graph") and len(calls) == 1
+    side.synchronize()
+    assert float(flag) == 1.0
     res = out["cluster"]
     nlab = res.n_labels_host                       # lazy sequence: resolves against pinned memory here
     assert len(nlab) == 4 and list(nlab) == [int(v) for v in torch.stack([l.unique().numel() * torch.ones((), dtype=torch.int64)
