@@ -115,7 +115,7 @@ def check(rc, what):
 # kernels (and memset nodes) each entry point enqueues; bench.py reports the sum as `gpu_launches`
 LAUNCHES = {
     "prifit_normalize_fwd": 1, "prifit_normalize_bwd": 1, "prifit_normalize_fwd_cf": 1, "prifit_normalize_bwd_cf": 1, "prifit_normalize_bwd_scaled": 1, "prifit_bandwidth_fwd": 6, "prifit_meanshift_fwd": 3,
-    "prifit_nms_fwd": 10, "prifit_nms_labels": 2, "prifit_meanshift_rows_prepare": 1, "prifit_meanshift_rows_fwd": 2, "prifit_meanshift_rows_bwd": 2,
+    "prifit_nms_fwd": 11, "prifit_nms_labels": 2, "prifit_meanshift_rows_prepare": 1, "prifit_meanshift_rows_fwd": 2, "prifit_meanshift_rows_bwd": 2,
     "prifit_membership_fwd": 2, "prifit_membership_bwd": 2, "prifit_fit_fwd": 1, "prifit_fit_bwd": 1,
     "prifit_sdf_loss_fwd": 2, "prifit_sdf_loss_bwd": 1,
     "prifit_masked_mean_fwd": 1, "prifit_masked_mean_bwd": 1, "prifit_noise_scatter": 1, "prifit_noise_scatter_range": 1, "prifit_pack_counts": 1, "prifit_spin_until_ge": 1,

@@ -103,6 +103,7 @@ struct GramArgs {
     const int32_t* votes;    // [B,N]     (BEST)
     const int32_t* rowsel;   // [B,N]     (BEST) compacted list of the rows to process, ascending
     const int32_t* nrows;    // [B]       (BEST) length of that list
+    int small_rows;          //           (BEST) shapes with at most this many voted rows are skipped (done by the small kernel)
     const int32_t* kth;      // [B]       (HIST / COLLECT), 1-based rank
     int32_t* out_idx;        // [B,N]     (NEAREST / BEST)
     int2* rowinfo;           // [B,N]     (HIST in/out, COLLECT in): x = window start (bits of u), y = remaining rank (24 bits)
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
     int nsel = N;                                              // rows this shape contributes (BEST: voted rows only)
     if (MODE == GM_BEST) nsel = a.nrows[b];
     if (r0 >= nsel) return;                                    // uniform over the CTA, before any barrier / allocation
+    if (MODE == GM_BEST && nsel <= a.small_rows) return;       // few voted rows: nms_best_small_kernel (nms.cu) has done this shape
     if (MODE == GM_HIST && a.level > 0 && a.overflow[1] == 0) return;   // no row of the batch asked for the refinement level
 
     extern __shared__ uint8_t smem_raw[];
@@ -579,9 +581,10 @@ int prifit_tc_nms_nearest(const float* newX, int B, int N, __half* Xs_ws, CUtens
 
 // best[b, i] is written only for the rows listed in rowsel[b, 0 .. nrows[b])
 int prifit_tc_nms_best(const CUtensorMap* map, const __half* Xs, const float* bw, const int32_t* votes,
-                       const int32_t* rowsel, const int32_t* nrows, int B, int N, int32_t* best, cudaStream_t st) {
+                       const int32_t* rowsel, const int32_t* nrows, int B, int N, int small_rows, int32_t* best, cudaStream_t st) {
     GramArgs a = {};
     a.Xs = Xs; a.N = N; a.B = B; a.bw = bw; a.votes = votes; a.rowsel = rowsel; a.nrows = nrows; a.out_idx = best;
+    a.small_rows = small_rows;
     return launch_gram<GM_BEST>(*map, a, st);
 }
 

@@ -15,7 +15,7 @@
 
 int prifit_tc_nms_nearest(const float* newX, int B, int N, __half* Xh_ws, CUtensorMap* map_out, int32_t* nearest, cudaStream_t st);
 int prifit_tc_nms_best(const CUtensorMap* map, const __half* Xs, const float* bw, const int32_t* votes,
-                       const int32_t* rowsel, const int32_t* nrows, int B, int N, int32_t* best, cudaStream_t st);
+                       const int32_t* rowsel, const int32_t* nrows, int B, int N, int small_rows, int32_t* best, cudaStream_t st);
 size_t prifit_tc_gram_split_bytes(int B, int N);
 int prifit_gram_engine();
 
@@ -220,6 +220,54 @@ __global__ void nms_idx_kernel(const int32_t* __restrict__ Kfound, const int32_t
     for (int k = threadIdx.x; k < Kcap; k += blockDim.x) idx_out[(size_t)b * Kcap + k] = k < Kf ? idx_full[(size_t)b * N + k] : -1;
 }
 
+// NMS step 3 when few rows received votes (the usual case: one row per mode): votes are zero outside the voted rows and a
+// voted row is within the threshold of itself, so the arg-max over ALL columns of [dist < bw] * votes is attained on a voted
+// column -- an n x n problem over the n voted rows (n <= NMS_SMALL) instead of a Gram pass of n rows against all N columns
+// through 128-row tensor-core tiles (27 us of latency for 16 real rows).  One CTA per shape, fp32 dot products, lowest index
+// among equal values.  Shapes with more voted rows are left to the Gram pass (which skips the shapes done here).
+constexpr int NMS_SMALL = 64;
+template <int D>
+__global__ void __launch_bounds__(256) nms_best_small_kernel(const float* __restrict__ Xn, const float* __restrict__ bw,
+                                                             const int32_t* __restrict__ votes, const int32_t* __restrict__ rowsel,
+                                                             const int32_t* __restrict__ nrows, int N, int32_t* __restrict__ best) {
+    constexpr int LD = D + 1;                                   // odd stride: lane i reads row i conflict-free
+    extern __shared__ float rows[];                             // [n][LD]
+    __shared__ int sel[NMS_SMALL];
+    __shared__ float vote[NMS_SMALL];
+    const int b = blockIdx.x, n = nrows[b];
+    if (n > NMS_SMALL || n <= 0) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* Xb = Xn + (size_t)b * N * D;
+    if (tid < n) { sel[tid] = rowsel[(size_t)b * N + tid]; vote[tid] = (float)votes[(size_t)b * N + sel[tid]]; }
+    __syncthreads();
+    for (int e = tid; e < n * (D / 4); e += 256) {
+        const int r = e / (D / 4), c = e % (D / 4);
+        const float4 v = reinterpret_cast<const float4*>(Xb + (size_t)sel[r] * D)[c];
+        float* dst = rows + r * LD + 4 * c;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    __syncthreads();
+    const float bwv = bw[b];
+    for (int u = warp; u < n; u += 8) {
+        float bv = -1.0f;
+        int bi = 0x7fffffff;
+        for (int i = lane; i < n; i += 32) {                    // i ascending per lane: '>' keeps the lowest index
+            float dot = 0.f;
+#pragma unroll 8
+            for (int c = 0; c < D; ++c) dot = fmaf(rows[u * LD + c], rows[i * LD + c], dot);
+            const float v = (2.0f - 2.0f * dot) < bwv ? vote[i] : 0.f;
+            if (v > bv) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (gt_max(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) best[(size_t)b * N + sel[u]] = sel[bi];
+    }
+}
+
 struct NmsWs {
     int32_t *nearest, *votes, *best, *flags, *used, *rowsel, *nrows, *idx_full;
 };
@@ -266,7 +314,11 @@ int launch_nms(const float* newX, const float* bw, int B, int N, int Kcap, int32
         // compact them (ascending) and run the Gram pass over those rows alone
         nms_compact_kernel<<<B, 1024, 0, st>>>(w.votes, N, N, w.rowsel, w.nrows);
         PF_LAUNCH_CHECK();
-        int rc = prifit_tc_nms_best(&map, Xh, bw, w.votes, w.rowsel, w.nrows, B, N, w.best, st);
+        const size_t sm_small = (size_t)NMS_SMALL * (D + 1) * sizeof(float);
+        PF_CUDA(cudaFuncSetAttribute(nms_best_small_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_small));
+        nms_best_small_kernel<D><<<B, 256, sm_small, st>>>(newX, bw, w.votes, w.rowsel, w.nrows, N, w.best);
+        PF_LAUNCH_CHECK();
+        int rc = prifit_tc_nms_best(&map, Xh, bw, w.votes, w.rowsel, w.nrows, B, N, NMS_SMALL, w.best, st);
         if (rc) return rc;
     } else {
         nms_gram_kernel<D, 1><<<gt, RG_THREADS, smem, st>>>(newX, bw, N, w.votes, w.best);

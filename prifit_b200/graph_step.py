@@ -225,7 +225,7 @@ class GraphStep:
                           _ptr(ws["ms"][0]), ws["ms"][1], st)
                 # the chain needs the centres (idx, K) only: the hard labels and their count follow on the side stream
                 _lib.call("prifit_nms_fwd", _ptr(newX), _ptr(bw), Bb, N, d, kcap, _ptr(idx), _ptr(K),
-                          None, None, _ptr(ws["nms"][0]), ws["nms"][1], st, launches=9)
+                          None, None, _ptr(ws["nms"][0]), ws["nms"][1], st, launches=10)
                 cent_done[i].record(st_)
                 sd_.wait_event(cent_done[i])
                 with torch.cuda.stream(sd_):

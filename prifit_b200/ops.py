@@ -139,7 +139,7 @@ def nms(newX, bw, kcap, two_calls=False):
     nlab = torch.empty(B, dtype=torch.int32, device=dev)
     if two_calls:
         _lib.call("prifit_nms_fwd", _ptr(newX), _ptr(bw), B, N, d, kcap, _ptr(idx), _ptr(K), None, None,
-                  _ptr(ws), nbytes, _stream(), launches=9)
+                  _ptr(ws), nbytes, _stream(), launches=10)
         _lib.call("prifit_nms_labels", _ptr(newX), B, N, d, kcap, _ptr(K), _ptr(idx), _ptr(labels), _ptr(nlab),
                   _ptr(ws), nbytes, _stream())
     else:
