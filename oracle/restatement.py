@@ -29,8 +29,10 @@ fixtures everywhere.
 Pinned / unpinned: every function below is pinned to outputs of the unmodified reference (fixtures: stages, svd_backward,
 fit_kat, planted_small, guard_small, random_small, entropy, chamfer, pointnet, sampler) EXCEPT the random draw of the
 surface sampler (src/sample_ellipsoid.py:31-35 needs trimesh, absent here): for that one step parity is UNPINNED --
-sample_counts() and surface_points() around it are pinned, the drawn samples are only checked statistically
-(tests/test_gpu_pipeline.py::test_surface_sampler_is_uniform_over_the_surface).
+sample_counts() and surface_points() around it are pinned; the draw itself is trimesh 3.8.1's (environment.yml:136), whose
+published algorithm is restated in oracle/trimesh_even.py (unverifiable here, so still UNPINNED) and serves as the
+distributional yardstick for the device sampler (tests/test_oracle_trimesh.py,
+tests/test_gpu_pipeline.py::test_surface_sampler_against_the_restated_reference_draw, ::test_surface_sampler_is_uniform_over_the_surface).
 
 Dense on purpose: it materialises the N x N kernel matrix per iteration and lets autograd run the
 dense backward, exactly like the reference, so timing it is a fair CPU baseline ("port").
