@@ -508,7 +508,8 @@ def run_ours(args):
         line["cfg5"] = sub_bench(["--workload", "cfg5", "--steps", "10", "--warmup", "3"],
                                  ("value", "ms_per_step", "config", "e2e", "clocks"))
     if rank == 0:
-        line["cpu_baseline"] = cpu_baseline(args.workload, shapes=min(B, 12))
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload, shapes=min(B, 12))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -718,6 +719,7 @@ def main():
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "fp32"])
     ap.add_argument("--trace-e2e", default=None, metavar="FILE", help="write a device timeline of the end-to-end loop (diagnostics)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replays")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="diagnostics (A/B runs of two builds): skip the 12 s CPU leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

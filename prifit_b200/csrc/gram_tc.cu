@@ -75,6 +75,8 @@ constexpr int HIST_WORDS = HIST_BINS / 2 + 1;            // packed uint16 pairs;
 constexpr float BW_UOFF = 1.0f / 32768.0f;
 constexpr uint32_t LOG_SHIFT = 19;                       // 4 mantissa bits: 16 bins per binade, 6.25 % wide
 constexpr uint32_t LOG_BASE = 111u << 4;                 // first bin starts at u = 2^-16 (biased exponent 111): 16 binades up to u = 1
+constexpr uint32_t LOG_LO_BITS = LOG_BASE << LOG_SHIFT;  // bit pattern of 2^-16
+constexpr uint32_t LOG_PAD = (uint32_t)(HIST_BINS / 2) << (LOG_SHIFT + 1);   // (bits - LOG_LO_BITS) of u = 1: word 128 = the pad word
 constexpr float BW_MARGIN = 2.0e-5f;                     // >= 2 x the bound on |tensor-core - fp32| distance
 constexpr float BW_MARGIN_U = 0.25f * BW_MARGIN;         // the same in u units
 constexpr int CAND_ROW = 64;                             // candidates per row (COLLECT)
@@ -141,7 +143,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
     if (MODE == GM_HIST && a.level > 0 && a.overflow[1] == 0) return;   // no row of the batch asked for the refinement level
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an offset on the __shared__ symbol (not through an integer round trip), so that every scratch
+    // access below is known to be in shared memory: LDS / STS / ATOMS instead of generic LD.E / ST.E / ATOM.E
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* tiles = smem;
     GBars* bars = reinterpret_cast<GBars*>(smem + (size_t)G_STAGES * G_STAGE_BYTES);
     uint8_t* scratch = smem + (size_t)G_STAGES * G_STAGE_BYTES + 256;
@@ -249,7 +253,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
         float* vt = reinterpret_cast<float*>(scratch + (size_t)3 * G_BM * 8);              // BEST: [2][128]
         uint32_t* hist = reinterpret_cast<uint32_t*>(scratch) + (size_t)row * HIST_WORDS;  // HIST: own row
         const uint32_t hist_s = smem_u32(hist);
-        const uint32_t hist_log = hist_s - ((LOG_BASE >> 1) << 2);                         // level 0: word (bits >> 20) of the row
         // COLLECT scratch: values [128][64] u32 | columns [128][64] u16 | per-row counters [128] | per-thread below [512] | tail values
         uint32_t* cval = reinterpret_cast<uint32_t*>(scratch) + (size_t)row * CAND_ROW;
         uint16_t* ccol = reinterpret_cast<uint16_t*>(scratch + (size_t)G_BM * CAND_ROW * 4) + (size_t)row * CAND_ROW;
@@ -333,12 +336,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                         //   level 1: bin = floor((u - lo) * 256 / width) through a round-down FMA onto 2^23 (FMA pipe; F2I is an
                         //            8-cycle XU instruction): the low mantissa bits of floor(y) + 2^23 are floor(y) for 0 <= y < 2^22
                         if (LEVEL0) {
-                            // bin = (bits >> 19) - LOG_BASE; u >= 2^-16 always, so the range test is one compare against the
-                            // bits of 1.0f; word address and half-word shift come straight from the bit pattern (6 ALU-pipe
-                            // instructions per element: SHF, LEA, SHF, LOP, SHL, ISETP -- the ALU pipe is what bounds HIST)
-                            const uint32_t bits = __float_as_uint(dist);
-                            asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, 0x3f800000;\n\t@p red.shared.add.u32 [%1], %2;\n\t}"
-                                         :: "r"(bits), "r"(hist_log + ((bits >> 20) << 2)), "r"(1u << ((bits >> 15) & 16u)) : "memory");
+                            // t = (bits of u) - (bits of 2^-16), clamped to [0, 128 << 20]: word t >> 20 of the OWN row -- 0..127 are the
+                            // 256 bins (16 per binade, half-word picked by bit 19), 128 is the row's pad word, which takes u >= 1 and
+                            // whatever a non-unit input row could produce (the wrap of u < 2^-16 included).  The atomic is therefore
+                            // UNCONDITIONAL: a predicated one compiles to a BSSY / BRA / BSYNC region per element around the address
+                            // arithmetic (12.5 instructions per element, no overlap between elements; now 9 and straight-line).
+                            const uint32_t t = min(__float_as_uint(dist) - LOG_LO_BITS, LOG_PAD);
+                            asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hist_s + ((t >> 20) << 2)), "r"(1u << ((t >> 15) & 16u)) : "memory");
                         } else {
                             const float biased = __fmaf_rd(dist - win_lo, hscale4, 8388608.0f);
                             const uint32_t ub = refine_row ? __float_as_uint(biased) - 0x4b000000u : 0xffffffffu;
@@ -349,9 +353,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tc_kernel(const __grid_cons
                     } else if (MODE == GM_COLLECT) {
                         // q >= 0, so its bit pattern orders like the value: two integer compares instead of three NaN-aware
                         // float compares on the (half-rate) ALU pipe
+                        // (both patterns are below 2^31, so the wrapped difference has its top bit set exactly when qb < lo_bits:
+                        // one subtraction serves the count and the window test, and the count is an add, not a select chain)
                         const uint32_t qb = __float_as_uint(dist);
-                        below += qb < lo_bits ? 1 : 0;
-                        if (qb - lo_bits <= win_bits) {                  // rare: one list per row, slots handed out atomically
+                        const uint32_t dlo = qb - lo_bits;
+                        below += (int)(dlo >> 31);
+                        if (dlo <= win_bits) {                           // rare: one list per row, slots handed out atomically
                             const int slot = atomicAdd(ccnt, 1);
                             if (slot < CAND_ROW) { cval[slot] = qb; ccol[slot] = (uint16_t)col; }
                         }

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_fwd_kernel(const __grid
     if (nrows == 0) return;   // uniform over the cluster, before any barrier / allocation
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the __shared__ symbol: accesses stay LDS / STS
     RtMisc* m = reinterpret_cast<RtMisc*>(smem + FwdPlan::misc);
     float* ys = reinterpret_cast<float*>(smem + FwdPlan::ys);
     float* part_o = reinterpret_cast<float*>(smem + FwdPlan::part_o);
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rows_tc_bwd_kernel(const __grid
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the __shared__ symbol: accesses stay LDS / STS
     RtMisc* m = reinterpret_cast<RtMisc*>(smem + BwdPlan::misc);
     float* gy = reinterpret_cast<float*>(smem + BwdPlan::gy);
     float* part_o = reinterpret_cast<float*>(smem + BwdPlan::part_o);

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) meanshift_tc_kernel(
     const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ Xh, const float* __restrict__ bw,
     int N, int T, float* __restrict__ newX) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the __shared__ symbol: accesses stay LDS / STS
     uint8_t* tiles = smem;
     uint8_t* qtile = smem + (size_t)TC_STAGES * TC_TILE_BYTES;
     TcBarriers* bars = reinterpret_cast<TcBarriers*>(qtile + TC_Q_BYTES);
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const __grid_constant_
                                                            const float* __restrict__ A, int mode, uint32_t lbo, uint32_t sbo,
                                                            float* __restrict__ Dout) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the __shared__ symbol: accesses stay LDS / STS
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_TILE_BYTES);      // [0] tile full, [1] mma done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
     const int warp = threadIdx.x >> 5, row = threadIdx.x;
