@@ -699,8 +699,10 @@ def run_reference(args):
         "value": round(sps, 3), "unit": "shapes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %d pts x %d-d, T=%d, quantile=%g, max_num_clusters=%d (CPU sample: %s)" % (
-            args.workload, N, D, T, q, kmax, sample)},
+        # the same workload string as the CUDA arm's line; what the CPU arm actually timed per step is in `sample`
+        "config": {"workload": "%s: %d shapes x %d pts x %d-d per GPU, T=%d, quantile=%g, max_num_clusters=%d, "
+                               "%d planted clusters (S1)" % (args.workload, B, N, D, T, q, kmax, kc),
+                   "shapes_per_gpu": B, "sample": sample},
         "cpu_baseline": {"value": round(sps, 3), "unit": "shapes/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(sps, 3), "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
