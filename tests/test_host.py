@@ -274,3 +274,36 @@ def test_host_rand_stream_is_prefix_stable():
         after_seq = torch.rand(5)
         assert torch.equal(big[:m], seq)
         assert torch.equal(after_batched, after_seq)
+
+
+def test_tensor_core_kernels_address_shared_memory_as_shared(lib):
+    """SASS lint: in the tcgen05 kernels every scratch access to dynamic shared memory must compile to LDS / STS /
+    ATOMS.  An integer round trip on the shared-memory base pointer hides the address space and turns them into generic
+    LD.E / ST.E / ATOM.E (measured: 4 % of the step).  What may stay generic are the distributed-shared-memory accesses of the
+    cluster kernels (cluster.map_shared_rank): K-seed forward <= 40, backward <= 30.  Also: the tensor-core path is really
+    there (UTCHMMA / tensor-memory loads / TMA in the library's SASS)."""
+    import shutil
+
+    from prifit_b200 import _lib
+
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "Function :" in sass
+    generic, fn = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            continue
+        if fn and re.search(r"\b(LD|ST|ATOM)\.E[. ]", line) and not re.search(r"\b(LDG|STG|ATOMG)\b", line):
+            generic[fn] = generic.get(fn, 0) + 1
+    allowed = {"rows_tc_fwd_kernel": 40, "rows_tc_bwd_kernel": 30}
+    for fn, n in generic.items():
+        if not re.search(r"gram_tc_kernel|meanshift_tc_kernel|rows_tc_(fwd|bwd)_kernel", fn):
+            continue
+        cap = next((v for k, v in allowed.items() if k in fn), 0)
+        assert n <= cap, "%s: %d generic shared-memory accesses (allowed %d)" % (fn, n, cap)
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in sass, mnemonic
